@@ -1,0 +1,210 @@
+/*
+ * ammsb.h -- C ABI of the B200-native SG-MCMC a-MMSB hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, plain pointers and
+ * sizes.  Each entry point replaces one operator of the reference
+ * (ielhelw/mcmc-ammsb-gpu); the reference interface it stands in for is cited
+ * as file:line relative to the reference tree.  The reference has no FFI layer
+ * of its own -- its boundary is the C++ API of libmcmc (mcmc::Learner et al.),
+ * which mcmc-ammsb-gpu_b200/host/ re-implements on top of this header.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message of
+ *     the last failure on the calling thread is ammsb_last_error().
+ *   - no exceptions cross the boundary; no ownership of host pointers is taken.
+ *   - "d_" parameters are device pointers valid on the context's device
+ *     (ammsb_malloc or any CUDA allocation, e.g. a torch tensor's data_ptr).
+ *   - operators are enqueued on the context's stream and return without
+ *     waiting; ammsb_ctx_sync() is the reference's queue.Finish().
+ *   - there is NO CPU fallback: without a CUDA device every call fails.
+ *   - handles may be used from two host threads at once only on disjoint
+ *     handles/contexts (the reference's sampler thread, learner.cc:216-229).
+ */
+#ifndef AMMSB_H_
+#define AMMSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMMSB_MAX_SHARDS 8
+#define AMMSB_IPC_HANDLE_BYTES 64
+
+typedef struct ammsb_ctx ammsb_ctx;     /* clcuda::Context + clcuda::Queue        */
+typedef struct ammsb_rng ammsb_rng;     /* random::OpenClRandom   (random.h:20-42) */
+typedef struct ammsb_set ammsb_set;     /* cuckoo::OpenClSet      (cuckoo.h:71-86) */
+typedef struct ammsb_store ammsb_store; /* RowPartitionedMatrix pi[N,K] + phi[N]
+                                           (partitioned-alloc.h:73-141, learner.h:52-53) */
+
+/* Hyper-parameters that the reference bakes into its kernels as -D flags
+ * (MakeCompileFlags, config.cc:66-83).  The float members must already have
+ * gone through ammsb_round_param(), which reproduces the "%e" text rounding of
+ * config.cc:57-64. */
+typedef struct {
+  uint64_t N;             /* -DN                */
+  uint64_t E;             /* -DE                */
+  uint32_t K;             /* -DK                */
+  uint32_t num_neighbors; /* -DNUM_NEIGHBORS    */
+  float alpha;            /* -DALPHA            */
+  float a, b, c;          /* -DEPS_A/B/C        */
+  float epsilon;          /* -DEPSILON          */
+  float eta0, eta1;       /* -DETA0/1           */
+} ammsb_params;
+
+/* Work-item mapping of the reference launch whose RNG stream / summation
+ * association is reproduced (Config::phi_mode, phi_wg_size, phi_vector_width,
+ * phi_disable_noise; config.h:55-66). */
+enum { AMMSB_MODE_THREAD = 0, AMMSB_MODE_WG = 1 };
+typedef struct {
+  uint32_t mode;          /* AMMSB_MODE_*; WG covers WG-NAIVE/SHARED/CODE_GEN */
+  uint32_t wg;            /* reference work-group size (state pool stride)    */
+  uint32_t disable_noise; /* PHI_RANDN -> literal 1 (phi.cc:673-677)           */
+  uint32_t strict;        /* 1: IEEE, reference-association kernel (slow);
+                             0: production kernel (HBM-roofline path)          */
+} ammsb_phi_opts;
+
+const char* ammsb_last_error(void);
+const char* ammsb_version(void);
+float ammsb_round_param(float f); /* config.cc:57-64 float_to_string */
+float ammsb_eps_t(const ammsb_params* p, uint32_t step_count); /* learner.cc:41-43 */
+
+/* ---- context: clcuda::Platform/Device/Context/Queue (main.cc:17-20,99-101) ---- */
+int ammsb_device_count(int* count);
+int ammsb_ctx_create(int device, ammsb_ctx** out);
+int ammsb_ctx_destroy(ammsb_ctx* ctx);
+int ammsb_ctx_sync(ammsb_ctx* ctx);                    /* Queue::Finish()            */
+int ammsb_ctx_set_stream(ammsb_ctx* ctx, void* cuda_stream); /* borrow a cudaStream_t */
+int ammsb_ctx_device(const ammsb_ctx* ctx, int* device);
+int ammsb_ctx_device_name(const ammsb_ctx* ctx, char* buf, size_t len); /* Device::Name() */
+int ammsb_ctx_sm_count(const ammsb_ctx* ctx, int* sms);
+
+/* ---- buffers: clcuda::Buffer<T> ctor / Read / Write / CopyTo ---- */
+int ammsb_malloc(ammsb_ctx* ctx, size_t bytes, void** d_ptr);
+int ammsb_free(ammsb_ctx* ctx, void* d_ptr);
+int ammsb_memset(ammsb_ctx* ctx, void* d_ptr, int value, size_t bytes);
+int ammsb_h2d(ammsb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* synchronous */
+int ammsb_d2h(ammsb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* synchronous */
+int ammsb_h2d_async(ammsb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int ammsb_d2h_async(ammsb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int ammsb_d2d(ammsb_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+int ammsb_host_alloc(size_t bytes, void** h_ptr); /* pinned */
+int ammsb_host_free(void* h_ptr);
+
+/* ---- timing: clcuda::Event::GetElapsedTime() (phi.cc:755-762 ...) ---- */
+int ammsb_timer_start(ammsb_ctx* ctx);
+int ammsb_timer_stop_ms(ammsb_ctx* ctx, float* ms); /* waits for the stop event */
+
+/* ---- RNG pool: OpenClRandomFactory::CreateRandom(size, seed) (random.h:44-58),
+ *      RandomInit kernel (random.cc:31-44): state[i] = (seed_x + i, seed_y + i) ---- */
+int ammsb_rng_create(ammsb_ctx* ctx, uint64_t num_states, uint64_t seed_x,
+                     uint64_t seed_y, ammsb_rng** out);
+int ammsb_rng_destroy(ammsb_rng* rng);
+int ammsb_rng_size(const ammsb_rng* rng, uint64_t* num_states);
+int ammsb_rng_get_state(ammsb_rng* rng, uint64_t* h_xy /* [2*num_states] */); /* Serialize */
+int ammsb_rng_set_state(ammsb_rng* rng, const uint64_t* h_xy);                /* Parse     */
+/* test/diagnostic streams (random-test.cc:47-99): every state draws `draws` values */
+int ammsb_rng_draw_u64(ammsb_rng* rng, uint32_t draws, uint64_t* h_out /* [num_states*draws] */);
+int ammsb_rng_draw_randn(ammsb_rng* rng, uint32_t draws, float* h_out);
+int ammsb_rng_draw_gamma(ammsb_rng* rng, uint32_t draws, float a, float b, float* h_out);
+
+/* ---- cuckoo edge set: OpenClSetFactory::CreateSet(const Set&) (cuckoo.h:88-103),
+ *      device Set_HasEdge (cuckoo.cc:39-65).  `table` is Set::Serialize()
+ *      (cuckoo.cc:211-220): [2 buckets][num_bins][4 slots] u64, empty = ~0. ---- */
+int ammsb_set_create(ammsb_ctx* ctx, const uint64_t* h_table, uint64_t num_bins,
+                     uint32_t prime_idx, ammsb_set** out);
+int ammsb_set_destroy(ammsb_set* set);
+int ammsb_set_has(ammsb_set* set, const uint64_t* h_keys, uint64_t n, uint8_t* h_out);
+int ammsb_set_has_device(ammsb_set* set, const uint64_t* d_keys, uint64_t n, uint8_t* d_out);
+
+/* ---- pi/phi store: RowPartitionedMatrixFactory<Float>::CreateMatrix(rows, cols)
+ *      (partitioned-alloc.h:152-157) + the phi[N] buffer (learner.cc:83).
+ *      Node-partitioned over `num_shards` GPUs: shard s owns rows
+ *      [s*rows_per_shard, (s+1)*rows_per_shard), rows_per_shard = ceil(N/num_shards)
+ *      (the reference's row -> (block, offset) rule, partitioned-alloc.h:24-28).
+ *      A process owns shard `shard_id`; peers are attached by CUDA IPC handle. ---- */
+int ammsb_store_create(ammsb_ctx* ctx, uint64_t N, uint32_t K, uint32_t num_shards,
+                       uint32_t shard_id, ammsb_store** out);
+int ammsb_store_destroy(ammsb_store* store);
+int ammsb_store_export(ammsb_store* store, uint8_t* pi_handle /* [64] */, uint8_t* phi_handle /* [64] */);
+int ammsb_store_attach(ammsb_store* store, uint32_t shard, const uint8_t* pi_handle, const uint8_t* phi_handle);
+/* single-process multi-device: attach another store's shard by direct peer access */
+int ammsb_store_attach_local(ammsb_store* store, uint32_t shard, ammsb_store* peer);
+int ammsb_store_rows(const ammsb_store* store, uint64_t* first_row, uint64_t* num_rows);
+int ammsb_store_local_ptrs(ammsb_store* store, float** d_pi, float** d_phi);
+/* host access to locally-owned rows (global row numbering) */
+int ammsb_store_write_pi(ammsb_store* store, uint64_t row0, uint64_t nrows, const float* h_src);
+int ammsb_store_read_pi(ammsb_store* store, uint64_t row0, uint64_t nrows, float* h_dst);
+int ammsb_store_write_phi(ammsb_store* store, uint64_t row0, uint64_t nrows, const float* h_src);
+int ammsb_store_read_phi(ammsb_store* store, uint64_t row0, uint64_t nrows, float* h_dst);
+/* RandomGammaAndNormalize (random.cc:159-167, learner.cc:154-155): pi ~ Gamma(eta0,eta1)
+ * row-normalised, phi = row sums; stream = pool N*32 seeded {11,113}, group per row. */
+int ammsb_store_init_pi(ammsb_store* store, float eta0, float eta1);
+
+/* ---- NeighborSampler::operator()(num_samples, nodes) (sample.h:16-28, sample.cc:48-121).
+ *      Bit-exact with the reference stream for the given work-group size `wg`
+ *      (Config::neighbor_sampler_wg_size).  d_hash_out (may be NULL) receives the
+ *      per-slot open-addressing tables [V, 2n] (NeighborSampler::GetHash()). ---- */
+int ammsb_neighbor_sample(ammsb_ctx* ctx, ammsb_rng* pool, const uint32_t* d_nodes,
+                          uint32_t V, uint32_t N, uint32_t n, uint32_t wg,
+                          uint32_t* d_neighbors /* [V, n] */, uint32_t* d_hash_out);
+
+/* ---- PhiUpdater::operator()(nodes, neighbors, V) (phi.h:20-23, phi.cc:728-763),
+ *      split at the reference's own kernel boundary: update_phi writes phi_vec
+ *      (and the row sums), update_pi overwrites pi/phi for the mini-batch nodes. ---- */
+int ammsb_update_phi(ammsb_ctx* ctx, const ammsb_params* p, const ammsb_phi_opts* opts,
+                     const float* d_beta /* [2K] */, ammsb_store* store, ammsb_set* train,
+                     const uint32_t* d_nodes /* [V] */, const uint32_t* d_neighbors /* [V,n] */,
+                     uint32_t V, uint32_t step_count, ammsb_rng* pool,
+                     float* d_phi_vec /* [V,K] */, float* d_phi_sum /* [V] */);
+int ammsb_update_pi(ammsb_ctx* ctx, uint32_t K, ammsb_store* store,
+                    const float* d_phi_vec, const float* d_phi_sum,
+                    const uint32_t* d_nodes, uint32_t V);
+
+/* ---- BetaUpdater::operator()(edges, E_mb, scale) (beta.h:25, beta.cc:334-384).
+ *      ammsb_beta_grads = sum_theta + calculate_grads_partial + sum_grads;
+ *      ammsb_update_theta = update_theta + theta->beta copy + row normalise.
+ *      In a multi-GPU run the [2K] gradient is all-reduced between the two. ---- */
+int ammsb_beta_workspace_bytes(ammsb_ctx* ctx, uint32_t K, size_t* bytes);
+int ammsb_beta_grads(ammsb_ctx* ctx, const ammsb_params* p, const float* d_theta,
+                     const float* d_beta, ammsb_store* store, ammsb_set* train,
+                     const uint64_t* d_edges, uint32_t E_mb, float* d_theta_sum /* [K] */,
+                     float* d_grads /* [2K] */, void* d_workspace, size_t workspace_bytes);
+int ammsb_update_theta(ammsb_ctx* ctx, const ammsb_params* p, float* d_theta, float* d_beta,
+                       const float* d_grads, float scale, uint32_t step_count, ammsb_rng* pool);
+int ammsb_update_beta(ammsb_ctx* ctx, const ammsb_params* p, float* d_theta, float* d_beta,
+                      ammsb_store* store, ammsb_set* train, const uint64_t* d_edges,
+                      uint32_t E_mb, float scale, uint32_t step_count, ammsb_rng* pool,
+                      float* d_theta_sum, float* d_grads, void* d_workspace, size_t workspace_bytes);
+
+/* ---- PerplexityCalculator::operator()() (perplexity.h:34, perplexity.cc:251-274).
+ *      ammsb_perplexity_partial leaves {link_lik, non_link_lik, link_count,
+ *      non_link_count} as 4 doubles in d_sums (all-reduced across GPUs by the
+ *      caller); ammsb_perplexity also copies them back and returns
+ *      -(sum lik)/(sum count) (Learner::HeldoutPerplexity exponentiates). ---- */
+int ammsb_perplexity_workspace_bytes(ammsb_ctx* ctx, size_t* bytes);
+int ammsb_perplexity_partial(ammsb_ctx* ctx, const ammsb_params* p, ammsb_store* store,
+                             const float* d_beta, ammsb_set* heldout, const uint64_t* d_edges,
+                             uint32_t H, float* d_ppx_per_edge, uint32_t call_count,
+                             double* d_sums /* [4] */, void* d_workspace, size_t workspace_bytes);
+int ammsb_perplexity(ammsb_ctx* ctx, const ammsb_params* p, ammsb_store* store,
+                     const float* d_beta, ammsb_set* heldout, const uint64_t* d_edges,
+                     uint32_t H, float* d_ppx_per_edge, uint32_t call_count,
+                     double* h_sums /* [4], may be NULL */, double* h_avg,
+                     void* d_workspace, size_t workspace_bytes);
+
+/* ---- work-group helpers the reference tests directly (wg-sum-test.cc,
+ *      wg-normalize-test.cc): rows of `len` floats, one warp per row, reference
+ *      association for wg = 32 (sum.cc:31-42, normalize.cc:13-32). ---- */
+int ammsb_row_sum(ammsb_ctx* ctx, const float* d_in, uint32_t rows, uint32_t len, float* d_out);
+int ammsb_row_normalize(ammsb_ctx* ctx, float* d_inout, uint32_t rows, uint32_t len, float* d_sum_out);
+
+/* number of kernels this library has launched on the calling process so far */
+int ammsb_launch_count(uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMMSB_H_ */

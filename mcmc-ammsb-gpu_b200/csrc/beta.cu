@@ -1,0 +1,302 @@
+// beta.cu -- update_beta/theta (reference: mcmc/beta.cc).
+//
+// The reference runs sum_theta, calculate_grads_partial (one [2K] partial per
+// mini-batch edge, 128 MB at m=16384,K=1024), a serial sum_grads, update_theta, a
+// theta->beta copy and a normalise kernel, each followed by a queue.Finish().
+// Here:  k_beta_partial  -- warp per edge, both pi rows read once with 128-bit loads,
+//                           per-warp register accumulators of  A_k = sum_{y=0} p_k/S,
+//                           B_k = sum_{y=1} p_k/S, combined per CTA in warp order
+//        k_beta_reduce   -- fixed-order sum over CTAs, theta_sum and the [K,2] gradient
+//        k_update_theta  -- Langevin step + beta = normalised theta
+// The summation order is fixed by the launch geometry, never by atomics, so a run is
+// reproducible (the reference's serialize-test.cc:132 contract).
+#include "common.cuh"
+
+#define BETA_WARPS 8
+
+struct BetaArgs {
+  StoreView sv;
+  SetView set;
+  const float* beta;
+  const uint64_t* edges;
+  uint32_t E_mb, K;
+  float epsilon;
+  float* partial;  // [gridDim.x][2][K]
+};
+
+// KPL4 = number of float4 per lane per row = ceil(K / 128)
+template <int KPL4>
+__global__ void __launch_bounds__(BETA_WARPS * 32)
+    k_beta_partial(const __grid_constant__ BetaArgs a) {
+  extern __shared__ __align__(16) float s_mem[];
+  const uint32_t K = a.K;
+  float* s_beta = s_mem;     // [K]  Beta(k) = beta[2k+1]
+  float* s_acc = s_mem + K;  // [2][K]
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) s_beta[k] = __ldg(&a.beta[2 * k + 1]);
+  __syncthreads();
+
+  float4 accA[KPL4], accB[KPL4];
+#pragma unroll
+  for (int i = 0; i < KPL4; ++i) {
+    accA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const uint32_t gwarp = blockIdx.x * BETA_WARPS + wib;
+  const uint32_t nwarps = gridDim.x * BETA_WARPS;
+  for (uint32_t e = gwarp; e < a.E_mb; e += nwarps) {
+    const uint64_t edge = __ldg(&a.edges[e]);
+    const uint32_t u = (uint32_t)(edge >> 32), v = (uint32_t)(edge & 0xffffffffu);
+    const float* pa = store_row(a.sv, u);
+    const float* pb = store_row(a.sv, v);
+    float4 q[KPL4];
+#pragma unroll
+    for (int i = 0; i < KPL4; ++i) {
+      const uint32_t k = lane * 4 + 128 * i;
+      if (k < K) {
+        const float4 x = ldg_stream4(pa + k);
+        const float4 z = ldg_stream4(pb + k);
+        q[i] = make_float4(x.x * z.x, x.y * z.y, x.z * z.z, x.w * z.w);
+      } else {
+        q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const bool y = set_has(a.set, make_edge(min(u, v), max(u, v)));
+    float pi_sum = 0.f, probs_sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL4; ++i) {
+      const uint32_t k = lane * 4 + 128 * i;
+      if (k < K) {
+        const float4 b = *reinterpret_cast<const float4*>(s_beta + k);
+        pi_sum += (q[i].x + q[i].y) + (q[i].z + q[i].w);
+        // probs_k = y ? beta_k * f : (1 - beta_k) * f   (beta.cc:116-120)
+        q[i].x *= y ? b.x : 1.0f - b.x;
+        q[i].y *= y ? b.y : 1.0f - b.y;
+        q[i].z *= y ? b.z : 1.0f - b.z;
+        q[i].w *= y ? b.w : 1.0f - b.w;
+        probs_sum += (q[i].x + q[i].y) + (q[i].z + q[i].w);
+      }
+    }
+    pi_sum = warp_sum(pi_sum);
+    probs_sum = warp_sum(probs_sum);
+    // prob_0 = (y ? EPSILON : 1 - EPSILON) * (1 - pi_sum)   (beta.cc:124-125)
+    probs_sum += (y ? a.epsilon : 1.0f - a.epsilon) * (1.0f - pi_sum);
+    const float rS = 1.0f / probs_sum;
+    if (y) {
+#pragma unroll
+      for (int i = 0; i < KPL4; ++i) {
+        accB[i].x = fmaf(q[i].x, rS, accB[i].x);
+        accB[i].y = fmaf(q[i].y, rS, accB[i].y);
+        accB[i].z = fmaf(q[i].z, rS, accB[i].z);
+        accB[i].w = fmaf(q[i].w, rS, accB[i].w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KPL4; ++i) {
+        accA[i].x = fmaf(q[i].x, rS, accA[i].x);
+        accA[i].y = fmaf(q[i].y, rS, accA[i].y);
+        accA[i].z = fmaf(q[i].z, rS, accA[i].z);
+        accA[i].w = fmaf(q[i].w, rS, accA[i].w);
+      }
+    }
+  }
+  // combine the CTA's warps in warp order
+  for (uint32_t w = 0; w < BETA_WARPS; ++w) {
+    if (wib == w) {
+#pragma unroll
+      for (int i = 0; i < KPL4; ++i) {
+        const uint32_t k = lane * 4 + 128 * i;
+        if (k < K) {
+          float4* pA = reinterpret_cast<float4*>(s_acc + k);
+          float4* pB = reinterpret_cast<float4*>(s_acc + K + k);
+          if (w == 0) {
+            *pA = accA[i];
+            *pB = accB[i];
+          } else {
+            float4 x = *pA, z = *pB;
+            x.x += accA[i].x; x.y += accA[i].y; x.z += accA[i].z; x.w += accA[i].w;
+            z.x += accB[i].x; z.y += accB[i].y; z.z += accB[i].z; z.w += accB[i].w;
+            *pA = x;
+            *pB = z;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* out = a.partial + (size_t)blockIdx.x * 2 * K;
+  for (uint32_t k = threadIdx.x; k < 2 * K; k += blockDim.x) out[k] = s_acc[k];
+}
+
+// generic-K fallback (K not a multiple of 4 or K > 4096): scalar loads, lane-strided
+__global__ void __launch_bounds__(BETA_WARPS * 32)
+    k_beta_partial_generic(const __grid_constant__ BetaArgs a) {
+  extern __shared__ __align__(16) float s_mem[];
+  const uint32_t K = a.K;
+  const uint32_t WARPS = blockDim.x >> 5;
+  float* s_acc = s_mem;  // [WARPS][2][K]
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* accA = s_acc + (size_t)wib * 2 * K;
+  float* accB = accA + K;
+  for (uint32_t k = lane; k < K; k += 32) {
+    accA[k] = 0.f;
+    accB[k] = 0.f;
+  }
+  const uint32_t gwarp = blockIdx.x * WARPS + wib;
+  const uint32_t nwarps = gridDim.x * WARPS;
+  for (uint32_t e = gwarp; e < a.E_mb; e += nwarps) {
+    const uint64_t edge = __ldg(&a.edges[e]);
+    const uint32_t u = (uint32_t)(edge >> 32), v = (uint32_t)(edge & 0xffffffffu);
+    const float* pa = store_row(a.sv, u);
+    const float* pb = store_row(a.sv, v);
+    const bool y = set_has(a.set, make_edge(min(u, v), max(u, v)));
+    float pi_sum = 0.f, probs_sum = 0.f;
+    for (uint32_t k = lane; k < K; k += 32) {
+      const float f = pa[k] * pb[k];
+      const float b = __ldg(&a.beta[2 * k + 1]);
+      pi_sum += f;
+      probs_sum += (y ? b : 1.0f - b) * f;
+    }
+    pi_sum = warp_sum(pi_sum);
+    probs_sum = warp_sum(probs_sum);
+    probs_sum += (y ? a.epsilon : 1.0f - a.epsilon) * (1.0f - pi_sum);
+    const float rS = 1.0f / probs_sum;
+    float* acc = y ? accB : accA;
+    for (uint32_t k = lane; k < K; k += 32) {
+      const float b = __ldg(&a.beta[2 * k + 1]);
+      acc[k] = fmaf((y ? b : 1.0f - b) * (pa[k] * pb[k]), rS, acc[k]);
+    }
+  }
+  __syncthreads();
+  float* out = a.partial + (size_t)blockIdx.x * 2 * K;
+  for (uint32_t k = threadIdx.x; k < 2 * K; k += blockDim.x) {
+    float s = s_acc[k];
+    for (uint32_t w = 1; w < WARPS; ++w) s += s_acc[(size_t)w * 2 * K + k];
+    out[k] = s;
+  }
+}
+
+// sum_theta (beta.cc:30-37) + the tail of calculate_grads_partial/sum_grads:
+//   g_k0 = A_k (1/theta_k0 - 1/thetaSum_k) - B_k / thetaSum_k
+//   g_k1 = B_k (1/theta_k1 - 1/thetaSum_k) - A_k / thetaSum_k        (beta.cc:130-135)
+__global__ void k_beta_reduce(const float* __restrict__ partial, uint32_t P, uint32_t K,
+                              const float* __restrict__ theta, float* __restrict__ theta_sum,
+                              float* __restrict__ grads) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float A = 0.f, B = 0.f;
+  for (uint32_t p = 0; p < P; ++p) {
+    A += partial[(size_t)p * 2 * K + k];
+    B += partial[(size_t)p * 2 * K + K + k];
+  }
+  const float t0 = theta[2 * k], t1 = theta[2 * k + 1];
+  const float ts = __fadd_rn(t0, t1);
+  const float rts = __fdiv_rn(1.0f, ts);
+  theta_sum[k] = ts;
+  grads[2 * k] = A * (__fdiv_rn(1.0f, t0) - rts) + B * (0.0f - rts);
+  grads[2 * k + 1] = A * (0.0f - rts) + B * (__fdiv_rn(1.0f, t1) - rts);
+}
+
+// update_theta (beta.cc:51-82) + CopyTo(beta) + WG_NORMALIZE_KERNEL rows of 2
+// (beta.cc:378-379, normalize.cc:13-32).  State index k, two normals per k.
+__global__ void k_update_theta(float* __restrict__ theta, float* __restrict__ beta,
+                               const float* __restrict__ grads, uint32_t K, float eps_t, float eta0,
+                               float eta1, float scale, ulonglong2* pool) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  Rng s = rng_load(pool, k);
+  const float half = __fdiv_rn(eps_t, 2.0f);
+  const float r0 = rng_randn(s);
+  float t0 = theta[2 * k];
+  const float f0 = __fsqrt_rn(__fmul_rn(eps_t, t0));
+  t0 = fabsf(__fadd_rn(
+      __fadd_rn(t0, __fmul_rn(half, __fadd_rn(__fsub_rn(eta0, t0), __fmul_rn(scale, grads[2 * k])))),
+      __fmul_rn(f0, r0)));
+  t0 = fmaxf(t0, 1e-24f);
+  const float r1 = rng_randn(s);
+  float t1 = theta[2 * k + 1];
+  const float f1 = __fsqrt_rn(__fmul_rn(eps_t, t1));
+  t1 = fabsf(__fadd_rn(
+      __fadd_rn(t1, __fmul_rn(half, __fadd_rn(__fsub_rn(eta1, t1), __fmul_rn(scale, grads[2 * k + 1])))),
+      __fmul_rn(f1, r1)));
+  t1 = fmaxf(t1, 1e-24f);
+  rng_store(pool, k, s);
+  theta[2 * k] = t0;
+  theta[2 * k + 1] = t1;
+  const float sum = __fadd_rn(__fadd_rn(0.f, t0), t1);
+  beta[2 * k] = __fdiv_rn(t0, sum);
+  beta[2 * k + 1] = __fdiv_rn(t1, sum);
+}
+
+static uint32_t beta_max_ctas(const ammsb_ctx* c) { return (uint32_t)c->sm_count * 2; }
+
+extern "C" int ammsb_beta_workspace_bytes(ammsb_ctx* c, uint32_t K, size_t* bytes) {
+  *bytes = sizeof(float) * 2 * (size_t)K * beta_max_ctas(c);
+  return 0;
+}
+
+extern "C" int ammsb_beta_grads(ammsb_ctx* c, const ammsb_params* p, const float* d_theta,
+                                const float* d_beta, ammsb_store* store, ammsb_set* train,
+                                const uint64_t* d_edges, uint32_t E_mb, float* d_theta_sum,
+                                float* d_grads, void* d_ws, size_t ws_bytes) {
+  AMMSB_REQUIRE(p->K == store->K, "params do not match the store");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  const uint32_t K = p->K;
+  uint32_t ctas = (E_mb + BETA_WARPS - 1) / BETA_WARPS;
+  if (ctas > beta_max_ctas(c)) ctas = beta_max_ctas(c);
+  AMMSB_REQUIRE(ws_bytes >= sizeof(float) * 2 * (size_t)K * (ctas ? ctas : 1), "beta workspace too small");
+  if (ctas > 0) {
+    BetaArgs a;
+    a.sv = store->view();
+    a.set = train->view();
+    a.beta = d_beta;
+    a.edges = d_edges;
+    a.E_mb = E_mb;
+    a.K = K;
+    a.epsilon = p->epsilon;
+    a.partial = (float*)d_ws;
+    const uint32_t kpl4 = (K + 127) / 128;
+    if ((K % 4) == 0 && kpl4 <= 8) {
+      const size_t smem = sizeof(float) * 3 * (size_t)K;
+      if (kpl4 <= 1) k_beta_partial<1><<<ctas, BETA_WARPS * 32, smem, c->stream>>>(a);
+      else if (kpl4 <= 2) k_beta_partial<2><<<ctas, BETA_WARPS * 32, smem, c->stream>>>(a);
+      else if (kpl4 <= 4) k_beta_partial<4><<<ctas, BETA_WARPS * 32, smem, c->stream>>>(a);
+      else k_beta_partial<8><<<ctas, BETA_WARPS * 32, smem, c->stream>>>(a);
+    } else {
+      uint32_t warps = BETA_WARPS;
+      while (warps > 1 && sizeof(float) * 2 * (size_t)K * warps > 160 * 1024) warps >>= 1;
+      const size_t smem = sizeof(float) * 2 * (size_t)K * warps;
+      AMMSB_REQUIRE(smem <= c->smem_optin, "K too large for update_beta");
+      AMMSB_CHECK_CUDA(cudaFuncSetAttribute(k_beta_partial_generic,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_beta_partial_generic<<<ctas, warps * 32, smem, c->stream>>>(a);
+    }
+    AMMSB_LAUNCH_CHECK();
+  }
+  k_beta_reduce<<<(K + 127) / 128, 128, 0, c->stream>>>((const float*)d_ws, ctas, K, d_theta,
+                                                        d_theta_sum, d_grads);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ammsb_update_theta(ammsb_ctx* c, const ammsb_params* p, float* d_theta, float* d_beta,
+                                  const float* d_grads, float scale, uint32_t step_count,
+                                  ammsb_rng* pool) {
+  AMMSB_REQUIRE(pool && pool->n >= p->K, "beta RNG pool smaller than K");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  k_update_theta<<<(p->K + 127) / 128, 128, 0, c->stream>>>(d_theta, d_beta, d_grads, p->K,
+                                                            ammsb_eps_t(p, step_count), p->eta0,
+                                                            p->eta1, scale, pool->d_state);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ammsb_update_beta(ammsb_ctx* c, const ammsb_params* p, float* d_theta, float* d_beta,
+                                 ammsb_store* store, ammsb_set* train, const uint64_t* d_edges,
+                                 uint32_t E_mb, float scale, uint32_t step_count, ammsb_rng* pool,
+                                 float* d_theta_sum, float* d_grads, void* d_ws, size_t ws_bytes) {
+  int rc = ammsb_beta_grads(c, p, d_theta, d_beta, store, train, d_edges, E_mb, d_theta_sum,
+                            d_grads, d_ws, ws_bytes);
+  if (rc) return rc;
+  return ammsb_update_theta(c, p, d_theta, d_beta, d_grads, scale, step_count, pool);
+}

@@ -1,0 +1,445 @@
+// phi.cu -- update_phi / update_pi (reference: mcmc/phi.cc).
+//
+// Two kernels implement update_phi:
+//   k_update_phi_fast    production path.  One warp per mini-batch slot, lane l owns
+//                        the community indices k = l, l+32, ... (exactly the ownership
+//                        of the reference's default launch, WG-NAIVE with phi_wg_size
+//                        32), pi rows are staged into shared memory by the TMA engine
+//                        (cp.async.bulk + mbarrier ring), one reciprocal per neighbor.
+//   k_update_phi_strict  any K / wg / mode; evaluates every expression in the
+//                        reference's order with IEEE round-to-nearest ops and no FMA
+//                        contraction.  It is the on-device twin of the CPU oracle.
+#include "common.cuh"
+
+struct PhiArgs {
+  StoreView sv;
+  SetView set;
+  const float* beta;
+  const uint32_t* nodes;
+  const uint32_t* neighbors;
+  uint32_t V, n, K;
+  uint32_t units;      // reference work-items (THREAD) or groups (WG) that own RNG state
+  uint32_t mode, wg;   // reference launch being reproduced
+  uint32_t disable_noise;
+  float eps_t, alpha, epsilon, Nn;
+  ulonglong2* pool;
+  float* phi_vec;
+  float* phi_sum;
+};
+
+// ------------------------------------------------------------------ strict ---
+
+// Serial/tree summation of s_val[0..K) in the reference's association:
+// THREAD -> serial in k (phi.cc:100-108); WG -> WG_SUM (sum.cc:20-42).
+__device__ float strict_row_sum(const float* s_val, float* s_aux, uint32_t K, uint32_t mode,
+                                uint32_t wg) {
+  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  if (mode == AMMSB_MODE_THREAD) {
+    if (tid == 0) {
+      float s = 0.f;
+      for (uint32_t k = 0; k < K; ++k) s = __fadd_rn(s, s_val[k]);
+      s_aux[0] = s;
+    }
+    __syncthreads();
+  } else {
+    for (uint32_t vl = tid; vl < wg; vl += T) {
+      float ps = 0.f;
+      for (uint32_t k = vl; k < K; k += wg) ps = __fadd_rn(ps, s_val[k]);
+      s_aux[vl] = ps;
+    }
+    __syncthreads();
+    uint32_t p2 = wg;  // power_of_2(wg) >> 1, sum.cc:11-18
+    p2 |= p2 >> 1; p2 |= p2 >> 2; p2 |= p2 >> 4; p2 |= p2 >> 8; p2 |= p2 >> 16;
+    p2 = (p2 + 1) >> 1;
+    for (; p2 > 0; p2 >>= 1) {
+      for (uint32_t lid = tid; lid < p2; lid += T)
+        if (lid + p2 < wg) s_aux[lid] = __fadd_rn(s_aux[lid], s_aux[lid + p2]);
+      __syncthreads();
+    }
+  }
+  const float r = s_aux[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(128) k_update_phi_strict(const __grid_constant__ PhiArgs a) {
+  extern __shared__ float s_mem[];
+  const uint32_t K = a.K, tid = threadIdx.x, T = blockDim.x;
+  float* s_pa = s_mem;
+  float* s_grads = s_pa + K;
+  float* s_probs = s_grads + K;
+  float* s_aux = s_probs + K;  // max(wg,1)
+  const uint32_t vw = a.mode == AMMSB_MODE_THREAD ? 1u : a.wg;
+  for (uint32_t unit = blockIdx.x; unit < a.units && unit < a.V; unit += gridDim.x) {
+    for (uint32_t slot = unit; slot < a.V; slot += a.units) {
+      const uint32_t node = a.nodes[slot];
+      const float* pi = store_row(a.sv, node);
+      const float phi_sum = *store_phi(a.sv, node);
+      for (uint32_t k = tid; k < K; k += T) {
+        s_pa[k] = pi[k];
+        s_grads[k] = 0.f;
+      }
+      __syncthreads();
+      for (uint32_t i = 0; i < a.n; ++i) {
+        const uint32_t nb = a.neighbors[(size_t)slot * a.n + i];
+        const float* pin = store_row(a.sv, nb);
+        const bool y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+        const float e = y ? a.epsilon : __fsub_rn(1.0f, a.epsilon);
+        for (uint32_t k = tid; k < K; k += T) {
+          const float beta_k = a.beta[2 * k + 1];
+          const float f = y ? __fsub_rn(beta_k, a.epsilon) : __fsub_rn(a.epsilon, beta_k);
+          s_probs[k] = __fmul_rn(s_pa[k], __fadd_rn(__fmul_rn(pin[k], f), e));
+        }
+        __syncthreads();
+        const float probs_sum = strict_row_sum(s_probs, s_aux, K, a.mode, a.wg);
+        for (uint32_t k = tid; k < K; k += T) {
+          const float term =
+              __fsub_rn(__fdiv_rn(__fdiv_rn(s_probs[k], probs_sum), __fmul_rn(s_pa[k], phi_sum)),
+                        __fdiv_rn(1.0f, phi_sum));
+          s_grads[k] = __fadd_rn(s_grads[k], term);
+        }
+        __syncthreads();
+      }
+      // noise in the reference's per-state draw order
+      float* s_noise = s_probs;
+      if (a.disable_noise) {
+        for (uint32_t k = tid; k < K; k += T) s_noise[k] = 1.0f;
+      } else {
+        for (uint32_t vl = tid; vl < vw; vl += T) {
+          Rng st = rng_load(a.pool, (uint64_t)unit * vw + vl);
+          for (uint32_t k = vl; k < K; k += vw) s_noise[k] = rng_randn(st);
+          rng_store(a.pool, (uint64_t)unit * vw + vl, st);
+        }
+      }
+      __syncthreads();
+      float* out = a.phi_vec + (size_t)slot * K;
+      for (uint32_t k = tid; k < K; k += T) {
+        const float phi_k = __fmul_rn(s_pa[k], phi_sum);
+        const float drift = __fmul_rn(
+            __fdiv_rn(a.eps_t, 2.0f),
+            __fadd_rn(__fsub_rn(a.alpha, phi_k), __fmul_rn(a.Nn, s_grads[k])));
+        const float v = fabsf(__fadd_rn(__fadd_rn(phi_k, drift),
+                                        __fmul_rn(__fsqrt_rn(__fmul_rn(a.eps_t, phi_k)), s_noise[k])));
+        const float r = fmaxf(v, 1e-24f);
+        out[k] = r;
+        s_pa[k] = r;  // for the row sum below
+      }
+      __syncthreads();
+      const float sum = strict_row_sum(s_pa, s_aux, K, a.mode, a.wg);
+      if (tid == 0) a.phi_sum[slot] = sum;
+      __syncthreads();
+    }
+  }
+}
+
+// -------------------------------------------------------------------- fast ---
+
+template <int KPL, int STAGES, int WARPS, bool EXACT>
+__global__ void __launch_bounds__(WARPS * 32)
+    k_update_phi_fast(const __grid_constant__ PhiArgs a) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const uint32_t K = a.K;
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t row_bytes = K * 4;
+  float* s_own = reinterpret_cast<float*>(s_raw) + (size_t)wib * (STAGES + 1) * K;
+  float* s_stage = s_own + K;
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(s_raw + (size_t)WARPS * (STAGES + 1) * row_bytes) + wib * (STAGES + 1);
+  if (lane == 0) {
+    for (int s = 0; s <= STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  uint32_t phase = 0;  // bit s: parity to wait on for barrier s (bit STAGES = own row)
+
+  // f_k = beta_k - epsilon for the lane's k (phi.cc:237-239); the non-link factor is -f_k
+  float fb[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const uint32_t k = lane + 32 * i;
+    fb[i] = (EXACT || k < K) ? __ldg(&a.beta[2 * k + 1]) - a.epsilon : 0.f;
+  }
+  const float e_link = a.epsilon, e_non = 1.0f - a.epsilon;
+  const float half_eps = a.eps_t / 2;
+  const bool fast_noise = (a.mode == AMMSB_MODE_WG && a.wg == 32);
+  const uint32_t vw = a.mode == AMMSB_MODE_THREAD ? 1u : a.wg;
+
+  const uint32_t gwarp = blockIdx.x * WARPS + wib;
+  const uint32_t total_warps = gridDim.x * WARPS;
+  for (uint32_t unit = gwarp; unit < a.units && unit < a.V; unit += total_warps) {
+    Rng st;
+    if (fast_noise && !a.disable_noise) st = rng_load(a.pool, (uint64_t)unit * 32 + lane);
+    for (uint32_t slot = unit; slot < a.V; slot += a.units) {
+      const uint32_t node = __ldg(&a.nodes[slot]);
+      const float phi_sum = *store_phi(a.sv, node);
+      const float rphi = 1.0f / phi_sum;
+      __syncwarp();  // previous slot's reads of s_own / stages are complete
+      if (lane == 0) {
+        mbar_expect_tx(&bars[STAGES], row_bytes);
+        bulk_g2s(s_own, store_row(a.sv, node), row_bytes, &bars[STAGES]);
+      }
+      // neighbor chunk registers: cur = neighbors [c*32, c*32+32), nxt = the next 32
+      const uint32_t* nbr = a.neighbors + (size_t)slot * a.n;
+      const float* cur_ptr = nullptr;
+      const float* nxt_ptr = nullptr;
+      uint32_t cur_mask = 0, nxt_mask = 0;
+      {
+        bool y = false;
+        if (lane < a.n) {
+          const uint32_t nb = __ldg(&nbr[lane]);
+          cur_ptr = store_row(a.sv, nb);
+          if (lane < STAGES) {
+            mbar_expect_tx(&bars[lane], row_bytes);
+            bulk_g2s(s_stage + (size_t)lane * K, cur_ptr, row_bytes, &bars[lane]);
+          }
+          y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+        }
+        cur_mask = __ballot_sync(FULL_MASK, y);
+        y = false;
+        if (32 + lane < a.n) {
+          const uint32_t nb = __ldg(&nbr[32 + lane]);
+          nxt_ptr = store_row(a.sv, nb);
+          y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+        }
+        nxt_mask = __ballot_sync(FULL_MASK, y);
+      }
+      float g[KPL];
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) g[i] = 0.f;
+
+      mbar_wait(&bars[STAGES], (phase >> STAGES) & 1);
+      phase ^= 1u << STAGES;
+
+      for (uint32_t j = 0; j < a.n; ++j) {
+        const uint32_t jj = j & 31;
+        if (jj == 0 && j > 0) {
+          cur_ptr = nxt_ptr;
+          cur_mask = nxt_mask;
+          bool y = false;
+          nxt_ptr = nullptr;
+          if (j + 32 + lane < a.n) {
+            const uint32_t nb = __ldg(&nbr[j + 32 + lane]);
+            nxt_ptr = store_row(a.sv, nb);
+            y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+          }
+          nxt_mask = __ballot_sync(FULL_MASK, y);
+        }
+        const uint32_t s = j % STAGES;
+        const bool y = (cur_mask >> jj) & 1;
+        const float e = y ? e_link : e_non;
+        mbar_wait(&bars[s], (phase >> s) & 1);
+        phase ^= 1u << s;
+        const float* row = s_stage + (size_t)s * K;
+        float t[KPL];
+        float S = 0.f;
+        if (y) {
+#pragma unroll
+          for (int i = 0; i < KPL; ++i) {
+            const uint32_t k = lane + 32 * i;
+            if (EXACT || k < K) {
+              t[i] = fmaf(row[k], fb[i], e);
+              S = fmaf(s_own[k], t[i], S);
+            } else {
+              t[i] = 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < KPL; ++i) {
+            const uint32_t k = lane + 32 * i;
+            if (EXACT || k < K) {
+              t[i] = fmaf(row[k], -fb[i], e);
+              S = fmaf(s_own[k], t[i], S);
+            } else {
+              t[i] = 0.f;
+            }
+          }
+        }
+        __syncwarp();  // every lane has consumed the stage -> refill it
+        {
+          const uint32_t q = j + STAGES;
+          if (q < a.n && lane == (q & 31)) {
+            const float* src = ((q >> 5) == (j >> 5)) ? cur_ptr : nxt_ptr;
+            mbar_expect_tx(&bars[s], row_bytes);
+            bulk_g2s(s_stage + (size_t)s * K, src, row_bytes, &bars[s]);
+          }
+        }
+        S = warp_sum(S);
+        // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
+        const float inv = 1.0f / (S * phi_sum);
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) g[i] += fmaf(t[i], inv, -rphi);
+      }
+
+      // Langevin noise (phi.cc:266-274) in the reference's per-state draw order
+      float* s_noise = s_stage;  // all stages are drained here
+      if (!a.disable_noise) {
+        if (fast_noise) {
+          for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn(st);
+        } else {
+          for (uint32_t vl = lane; vl < vw; vl += 32) {
+            Rng vs = rng_load(a.pool, (uint64_t)unit * vw + vl);
+            for (uint32_t k = vl; k < K; k += vw) s_noise[k] = rng_randn(vs);
+            rng_store(a.pool, (uint64_t)unit * vw + vl, vs);
+          }
+          __syncwarp();
+        }
+      }
+      float* out = a.phi_vec + (size_t)slot * K;
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const uint32_t k = lane + 32 * i;
+        if (EXACT || k < K) {
+          const float noise = a.disable_noise ? 1.0f : s_noise[k];
+          const float phi_k = s_own[k] * phi_sum;
+          float v = fabsf(phi_k + half_eps * (a.alpha - phi_k + a.Nn * g[i]) +
+                          sqrtf(a.eps_t * phi_k) * noise);
+          v = fmaxf(v, 1e-24f);
+          out[k] = v;
+          lsum += v;
+        }
+      }
+      lsum = warp_sum(lsum);
+      if (lane == 0) a.phi_sum[slot] = lsum;
+    }
+    if (fast_noise && !a.disable_noise) rng_store(a.pool, (uint64_t)unit * 32 + lane, st);
+  }
+}
+
+template <int KPL, int STAGES, int WARPS>
+static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
+  const size_t smem = (size_t)WARPS * (STAGES + 1) * a.K * 4 + (size_t)WARPS * (STAGES + 1) * 8;
+  const bool exact = (a.K == 32u * KPL);
+  auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true>
+                    : k_update_phi_fast<KPL, STAGES, WARPS, false>;
+  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+  AMMSB_REQUIRE(occ > 0, "update_phi: kernel does not fit on an SM");
+  const uint32_t active = a.units < a.V ? a.units : a.V;
+  uint32_t blocks = (active + WARPS - 1) / WARPS;
+  const uint32_t resident = (uint32_t)occ * c->sm_count;
+  if (blocks > resident) blocks = resident;  // persistent: one wave, warps stride over units
+  kern<<<blocks, WARPS * 32, smem, c->stream>>>(a);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb_phi_opts* o,
+                                const float* d_beta, ammsb_store* store, ammsb_set* train,
+                                const uint32_t* d_nodes, const uint32_t* d_neighbors, uint32_t V,
+                                uint32_t step_count, ammsb_rng* pool, float* d_phi_vec,
+                                float* d_phi_sum) {
+  AMMSB_REQUIRE(V > 0, "mini-batch nodes size = 0!");  // phi.cc:732
+  AMMSB_REQUIRE(p->K == store->K && p->N == store->N, "params do not match the store");
+  AMMSB_REQUIRE(o->wg > 0, "work-group size must be > 0");
+  AMMSB_REQUIRE(d_phi_sum != nullptr && d_phi_vec != nullptr, "phi_vec / phi_sum are required");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  PhiArgs a;
+  a.sv = store->view();
+  a.set = train->view();
+  a.beta = d_beta;
+  a.nodes = d_nodes;
+  a.neighbors = d_neighbors;
+  a.V = V;
+  a.n = p->num_neighbors;
+  a.K = p->K;
+  a.mode = o->mode;
+  a.wg = o->wg;
+  a.disable_noise = o->disable_noise;
+  // phi.cc:740-747 launch geometry
+  uint64_t states;
+  if (o->mode == AMMSB_MODE_THREAD) {
+    uint32_t g = V / o->wg + (V % o->wg ? 1 : 0);
+    if (g > 65535u) g = 65535u;
+    a.units = g * o->wg;
+    states = a.units < V ? a.units : V;
+  } else {
+    a.units = V < 65535u ? V : 65535u;
+    states = (uint64_t)a.units * o->wg;
+  }
+  AMMSB_REQUIRE(o->disable_noise || (pool && pool->n >= states),
+                "Num seeds smaller than global threads");  // phi.cc:748-750
+  a.eps_t = ammsb_eps_t(p, step_count);
+  a.alpha = p->alpha;
+  a.epsilon = p->epsilon;
+  a.Nn = (1.0f * p->N) / p->num_neighbors;  // phi.cc:113
+  a.pool = pool ? pool->d_state : nullptr;
+  a.phi_vec = d_phi_vec;
+  a.phi_sum = d_phi_sum;
+
+  const bool fast_ok = !o->strict && (p->K % 4 == 0) && p->K <= 1024;
+  if (fast_ok) {
+    const uint32_t kpl = (p->K + 31) / 32;
+    if (kpl <= 2) return launch_fast<2, 8, 4>(c, a);
+    if (kpl <= 4) return launch_fast<4, 8, 4>(c, a);
+    if (kpl <= 8) return launch_fast<8, 6, 4>(c, a);
+    if (kpl <= 16) return launch_fast<16, 4, 4>(c, a);
+    return launch_fast<32, 3, 4>(c, a);
+  }
+  const uint32_t vw = o->mode == AMMSB_MODE_THREAD ? 1u : o->wg;
+  const size_t smem = sizeof(float) * (3 * (size_t)p->K + vw);
+  AMMSB_REQUIRE(smem <= c->smem_optin, "K too large for the strict update_phi kernel");
+  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(k_update_phi_strict,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  uint32_t blocks = a.units < V ? a.units : V;
+  const uint32_t cap = (uint32_t)c->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  k_update_phi_strict<<<blocks, 128, smem, c->stream>>>(a);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------- update_pi ---
+
+// update_pi, phi.cc:154-173 / :178-197: pi[node][:] = phi_vec[slot][:] / sum,
+// phi[node] = sum.  The row sum was produced by update_phi in the association of
+// the launch mode; the division is IEEE.
+__global__ void __launch_bounds__(256)
+    k_update_pi(StoreView sv, const float* __restrict__ phi_vec, const float* __restrict__ phi_sum,
+                const uint32_t* __restrict__ nodes, uint32_t V) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t K = sv.K;
+  for (; warp < V; warp += nwarps) {
+    const uint32_t node = __ldg(&nodes[warp]);
+    const float* src = phi_vec + (size_t)warp * K;
+    float* dst = store_row(sv, node);
+    float sum;
+    if (phi_sum) {
+      sum = __ldg(&phi_sum[warp]);
+    } else {
+      float ls = 0.f;
+      for (uint32_t k = lane; k < K; k += 32) ls = __fadd_rn(ls, src[k]);
+      sum = warp_sum(ls);
+    }
+    if ((K & 3) == 0) {
+      for (uint32_t k = lane * 4; k < K; k += 128) {
+        float4 v = *reinterpret_cast<const float4*>(src + k);
+        v.x = __fdiv_rn(v.x, sum);
+        v.y = __fdiv_rn(v.y, sum);
+        v.z = __fdiv_rn(v.z, sum);
+        v.w = __fdiv_rn(v.w, sum);
+        *reinterpret_cast<float4*>(dst + k) = v;
+      }
+    } else {
+      for (uint32_t k = lane; k < K; k += 32) dst[k] = __fdiv_rn(src[k], sum);
+    }
+    if (lane == 0) *store_phi(sv, node) = sum;
+  }
+}
+
+extern "C" int ammsb_update_pi(ammsb_ctx* c, uint32_t K, ammsb_store* store, const float* d_phi_vec,
+                               const float* d_phi_sum, const uint32_t* d_nodes, uint32_t V) {
+  AMMSB_REQUIRE(V > 0, "mini-batch nodes size = 0!");
+  AMMSB_REQUIRE(K == store->K, "K does not match the store");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  uint32_t blocks = (V + 7) / 8;
+  const uint32_t cap = (uint32_t)c->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  k_update_pi<<<blocks, 256, 0, c->stream>>>(store->view(), d_phi_vec, d_phi_sum, d_nodes, V);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}

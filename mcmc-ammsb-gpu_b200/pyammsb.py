@@ -1,0 +1,347 @@
+"""ctypes binding of libammsb.so (the C ABI in include/ammsb.h).
+
+Harness-side only: tests, bench.py and __graft_entry__ drive the CUDA path through
+this module.  It fails loudly when the library is missing or no GPU is present --
+there is no CPU fallback anywhere in the product path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libammsb.so")
+
+MODE_THREAD, MODE_WG = 0, 1
+
+
+class Params(C.Structure):
+    _fields_ = [("N", C.c_uint64), ("E", C.c_uint64), ("K", C.c_uint32),
+                ("num_neighbors", C.c_uint32), ("alpha", C.c_float), ("a", C.c_float),
+                ("b", C.c_float), ("c", C.c_float), ("epsilon", C.c_float),
+                ("eta0", C.c_float), ("eta1", C.c_float)]
+
+
+class PhiOpts(C.Structure):
+    _fields_ = [("mode", C.c_uint32), ("wg", C.c_uint32), ("disable_noise", C.c_uint32),
+                ("strict", C.c_uint32)]
+
+
+class AmmsbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AmmsbError("libammsb.so not built: run __graft_entry__.build() "
+                             "(make -C mcmc-ammsb-gpu_b200/csrc)")
+        L = C.CDLL(LIB_PATH)
+        L.ammsb_last_error.restype = C.c_char_p
+        L.ammsb_version.restype = C.c_char_p
+        L.ammsb_round_param.restype = C.c_float
+        L.ammsb_round_param.argtypes = [C.c_float]
+        L.ammsb_eps_t.restype = C.c_float
+        L.ammsb_eps_t.argtypes = [C.c_void_p, C.c_uint32]
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise AmmsbError(lib().ammsb_last_error().decode())
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return a
+
+
+def round_param(f):
+    return float(lib().ammsb_round_param(f))
+
+
+def make_params(N, E, K, n, alpha=None, a=0.0315, b=1024.0, c=0.5, epsilon=1e-7, eta0=1.0,
+                eta1=1.0):
+    if alpha is None or alpha == 0:
+        alpha = float(np.float32(1.0) / np.float32(K))  # main.cc:153
+    r = round_param
+    return Params(N, E, K, n, r(alpha), r(a), r(b), r(c), r(epsilon), r(eta0), r(eta1))
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().ammsb_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def launch_count():
+    n = C.c_uint64(0)
+    lib().ammsb_launch_count(C.byref(n))
+    return n.value
+
+
+class DevBuf:
+    """clcuda::Buffer<T> stand-in: a typed device allocation."""
+
+    def __init__(self, ctx, dtype, count):
+        self.ctx, self.dtype, self.count = ctx, np.dtype(dtype), int(count)
+        self.nbytes = self.dtype.itemsize * self.count
+        ptr = C.c_void_p()
+        _ck(lib().ammsb_malloc(ctx.h, max(self.nbytes, 16), C.byref(ptr)))
+        self.ptr = ptr
+
+    def write(self, arr, offset=0):
+        arr = np.ascontiguousarray(arr, dtype=self.dtype)
+        assert offset + arr.size <= self.count
+        _ck(lib().ammsb_h2d(self.ctx.h, C.c_void_p(self.ptr.value + offset * self.dtype.itemsize),
+                            _p(arr), arr.nbytes))
+        return self
+
+    def read(self, count=None, offset=0):
+        count = self.count - offset if count is None else count
+        out = np.empty(count, dtype=self.dtype)
+        _ck(lib().ammsb_d2h(self.ctx.h, _p(out),
+                            C.c_void_p(self.ptr.value + offset * self.dtype.itemsize), out.nbytes))
+        return out
+
+    def zero(self):
+        _ck(lib().ammsb_memset(self.ctx.h, self.ptr, 0, self.nbytes))
+        return self
+
+    def free(self):
+        if self.ptr is not None:
+            lib().ammsb_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class Ctx:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _ck(lib().ammsb_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def sync(self):
+        _ck(lib().ammsb_ctx_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        _ck(lib().ammsb_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sm_count(self):
+        n = C.c_int(0)
+        _ck(lib().ammsb_ctx_sm_count(self.h, C.byref(n)))
+        return n.value
+
+    def name(self):
+        b = C.create_string_buffer(256)
+        _ck(lib().ammsb_ctx_device_name(self.h, b, 256))
+        return b.value.decode()
+
+    def buf(self, dtype, count):
+        return DevBuf(self, dtype, count)
+
+    def from_host(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return DevBuf(self, arr.dtype, arr.size).write(arr.ravel())
+
+    def timer_start(self):
+        _ck(lib().ammsb_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float(0)
+        _ck(lib().ammsb_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    # ---- operators ----
+    def neighbor_sample(self, pool, d_nodes, V, N, n, wg, d_neighbors, d_hash=None):
+        _ck(lib().ammsb_neighbor_sample(self.h, pool.h, d_nodes.ptr, V, N, n, wg, d_neighbors.ptr,
+                                        d_hash.ptr if d_hash is not None else None))
+
+    def update_phi(self, p, opts, d_beta, store, train, d_nodes, d_neighbors, V, step, pool,
+                   d_phi_vec, d_phi_sum):
+        _ck(lib().ammsb_update_phi(self.h, C.byref(p), C.byref(opts), d_beta.ptr, store.h, train.h,
+                                   d_nodes.ptr, d_neighbors.ptr, V, step,
+                                   pool.h if pool is not None else None, d_phi_vec.ptr,
+                                   d_phi_sum.ptr))
+
+    def update_pi(self, K, store, d_phi_vec, d_phi_sum, d_nodes, V):
+        _ck(lib().ammsb_update_pi(self.h, K, store.h, d_phi_vec.ptr,
+                                  d_phi_sum.ptr if d_phi_sum is not None else None, d_nodes.ptr, V))
+
+    def beta_workspace_bytes(self, K):
+        n = C.c_size_t(0)
+        _ck(lib().ammsb_beta_workspace_bytes(self.h, K, C.byref(n)))
+        return n.value
+
+    def beta_grads(self, p, d_theta, d_beta, store, train, d_edges, E_mb, d_theta_sum, d_grads, ws):
+        _ck(lib().ammsb_beta_grads(self.h, C.byref(p), d_theta.ptr, d_beta.ptr, store.h, train.h,
+                                   d_edges.ptr, E_mb, d_theta_sum.ptr, d_grads.ptr, ws.ptr,
+                                   C.c_size_t(ws.nbytes)))
+
+    def update_theta(self, p, d_theta, d_beta, d_grads, scale, step, pool):
+        _ck(lib().ammsb_update_theta(self.h, C.byref(p), d_theta.ptr, d_beta.ptr, d_grads.ptr,
+                                     C.c_float(scale), step, pool.h))
+
+    def update_beta(self, p, d_theta, d_beta, store, train, d_edges, E_mb, scale, step, pool,
+                    d_theta_sum, d_grads, ws):
+        _ck(lib().ammsb_update_beta(self.h, C.byref(p), d_theta.ptr, d_beta.ptr, store.h, train.h,
+                                    d_edges.ptr, E_mb, C.c_float(scale), step, pool.h,
+                                    d_theta_sum.ptr, d_grads.ptr, ws.ptr, C.c_size_t(ws.nbytes)))
+
+    def perplexity_workspace_bytes(self):
+        n = C.c_size_t(0)
+        _ck(lib().ammsb_perplexity_workspace_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def perplexity(self, p, store, d_beta, heldout, d_edges, H, d_ppx, call_count, ws):
+        sums = (C.c_double * 4)()
+        avg = C.c_double(0)
+        _ck(lib().ammsb_perplexity(self.h, C.byref(p), store.h, d_beta.ptr, heldout.h, d_edges.ptr,
+                                   H, d_ppx.ptr, call_count, sums, C.byref(avg), ws.ptr,
+                                   C.c_size_t(ws.nbytes)))
+        return avg.value, np.array(list(sums))
+
+    def perplexity_partial(self, p, store, d_beta, heldout, d_edges, H, d_ppx, call_count, d_sums,
+                           ws):
+        _ck(lib().ammsb_perplexity_partial(self.h, C.byref(p), store.h, d_beta.ptr, heldout.h,
+                                           d_edges.ptr, H, d_ppx.ptr, call_count, d_sums.ptr,
+                                           ws.ptr, C.c_size_t(ws.nbytes)))
+
+    def row_sum(self, d_in, rows, length, d_out):
+        _ck(lib().ammsb_row_sum(self.h, d_in.ptr, rows, length, d_out.ptr))
+
+    def row_normalize(self, d_inout, rows, length, d_sum):
+        _ck(lib().ammsb_row_normalize(self.h, d_inout.ptr, rows, length,
+                                      d_sum.ptr if d_sum is not None else None))
+
+    def close(self):
+        if self.h is not None:
+            lib().ammsb_ctx_destroy(self.h)
+            self.h = None
+
+
+class Rng:
+    def __init__(self, ctx, n, sx, sy):
+        h = C.c_void_p()
+        _ck(lib().ammsb_rng_create(ctx.h, C.c_uint64(n), C.c_uint64(sx), C.c_uint64(sy), C.byref(h)))
+        self.h, self.n, self.ctx = h, n, ctx
+
+    def get_state(self):
+        out = np.empty((self.n, 2), dtype=np.uint64)
+        _ck(lib().ammsb_rng_get_state(self.h, _p(out)))
+        return out
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, dtype=np.uint64)
+        assert st.shape == (self.n, 2)
+        _ck(lib().ammsb_rng_set_state(self.h, _p(st)))
+
+    def draw_u64(self, draws):
+        out = np.empty((self.n, draws), dtype=np.uint64)
+        _ck(lib().ammsb_rng_draw_u64(self.h, draws, _p(out)))
+        return out
+
+    def draw_randn(self, draws):
+        out = np.empty((self.n, draws), dtype=np.float32)
+        _ck(lib().ammsb_rng_draw_randn(self.h, draws, _p(out)))
+        return out
+
+    def draw_gamma(self, draws, a, b):
+        out = np.empty((self.n, draws), dtype=np.float32)
+        _ck(lib().ammsb_rng_draw_gamma(self.h, draws, C.c_float(a), C.c_float(b), _p(out)))
+        return out
+
+    def free(self):
+        if self.h is not None:
+            lib().ammsb_rng_destroy(self.h)
+            self.h = None
+
+
+class DevSet:
+    def __init__(self, ctx, table, num_bins, prime_idx):
+        table = np.ascontiguousarray(table, dtype=np.uint64)
+        assert table.size == 8 * num_bins
+        h = C.c_void_p()
+        _ck(lib().ammsb_set_create(ctx.h, _p(table), C.c_uint64(num_bins), prime_idx, C.byref(h)))
+        self.h, self.ctx = h, ctx
+
+    def has(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        out = np.zeros(len(keys), dtype=np.uint8)
+        _ck(lib().ammsb_set_has(self.h, _p(keys), C.c_uint64(len(keys)), _p(out)))
+        return out
+
+    def free(self):
+        if self.h is not None:
+            lib().ammsb_set_destroy(self.h)
+            self.h = None
+
+
+class Store:
+    def __init__(self, ctx, N, K, num_shards=1, shard_id=0):
+        h = C.c_void_p()
+        _ck(lib().ammsb_store_create(ctx.h, C.c_uint64(N), K, num_shards, shard_id, C.byref(h)))
+        self.h, self.ctx, self.N, self.K = h, ctx, N, K
+        self.num_shards, self.shard_id = num_shards, shard_id
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _ck(lib().ammsb_store_rows(h, C.byref(a), C.byref(b)))
+        self.first_row, self.local_rows = a.value, b.value
+
+    def init_pi(self, eta0=1.0, eta1=1.0):
+        _ck(lib().ammsb_store_init_pi(self.h, C.c_float(eta0), C.c_float(eta1)))
+
+    def write_pi(self, arr, row0=None):
+        row0 = self.first_row if row0 is None else row0
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1, self.K)
+        _ck(lib().ammsb_store_write_pi(self.h, C.c_uint64(row0), C.c_uint64(arr.shape[0]), _p(arr)))
+
+    def read_pi(self, row0=None, nrows=None):
+        row0 = self.first_row if row0 is None else row0
+        nrows = self.local_rows if nrows is None else nrows
+        out = np.empty((nrows, self.K), dtype=np.float32)
+        _ck(lib().ammsb_store_read_pi(self.h, C.c_uint64(row0), C.c_uint64(nrows), _p(out)))
+        return out
+
+    def write_phi(self, arr, row0=None):
+        row0 = self.first_row if row0 is None else row0
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        _ck(lib().ammsb_store_write_phi(self.h, C.c_uint64(row0), C.c_uint64(arr.size), _p(arr)))
+
+    def read_phi(self, row0=None, nrows=None):
+        row0 = self.first_row if row0 is None else row0
+        nrows = self.local_rows if nrows is None else nrows
+        out = np.empty(nrows, dtype=np.float32)
+        _ck(lib().ammsb_store_read_phi(self.h, C.c_uint64(row0), C.c_uint64(nrows), _p(out)))
+        return out
+
+    def export_handles(self):
+        a = (C.c_uint8 * 64)()
+        b = (C.c_uint8 * 64)()
+        _ck(lib().ammsb_store_export(self.h, a, b))
+        return bytes(a), bytes(b)
+
+    def attach(self, shard, pi_handle, phi_handle):
+        a = (C.c_uint8 * 64).from_buffer_copy(pi_handle)
+        b = (C.c_uint8 * 64).from_buffer_copy(phi_handle)
+        _ck(lib().ammsb_store_attach(self.h, shard, a, b))
+
+    def attach_local(self, shard, peer):
+        _ck(lib().ammsb_store_attach_local(self.h, shard, peer.h))
+
+    def local_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _ck(lib().ammsb_store_local_ptrs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def free(self):
+        if self.h is not None:
+            lib().ammsb_store_destroy(self.h)
+            self.h = None
