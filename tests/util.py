@@ -66,8 +66,19 @@ class Problem:
         self.N, self.K, self.E, self.n = N, K, E, n
         keys = make_edges(N, E, seed)
         self.train_edges, self.heldout_links = split_edges(keys, heldout_ratio)
-        self.train_set = orc.set_build(self.train_edges)
-        self.heldout_set = orc.set_build(self.heldout_links) if len(self.heldout_links) else None
+        # the reference's two hashes are correlated for some table sizes (cuckoo.cc:199-209:
+        # both depend on k mod gcd-factors of N_), so a build can legitimately fail; shrink the
+        # held-out part until both sets build, as a user of the reference would re-split
+        for _ in range(64):
+            try:
+                self.train_set = orc.set_build(self.train_edges)
+                self.heldout_set = orc.set_build(self.heldout_links)
+                break
+            except RuntimeError:
+                self.train_edges = np.concatenate([self.train_edges, self.heldout_links[-1:]])
+                self.heldout_links = self.heldout_links[:-1]
+        else:
+            raise RuntimeError("could not build cuckoo sets")
         self.heldout_nonlinks = fake_nonlinks(N, len(self.heldout_links), keys, seed + 1)
         self.heldout_edges = np.concatenate([self.heldout_links, self.heldout_nonlinks])
         self.pi, self.phi = random_pi(N, K, seed + 2)
