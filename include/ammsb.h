@@ -134,6 +134,9 @@ int ammsb_store_attach(ammsb_store* store, uint32_t shard, const uint8_t* pi_han
 int ammsb_store_attach_local(ammsb_store* store, uint32_t shard, ammsb_store* peer);
 int ammsb_store_rows(const ammsb_store* store, uint64_t* first_row, uint64_t* num_rows);
 int ammsb_store_local_ptrs(ammsb_store* store, float** d_pi, float** d_phi);
+/* make the local shard use caller-owned memory for phi (>= rows_per_shard floats): the
+ * reference keeps phi in a Buffer of its own (learner.h:53) that callers read directly */
+int ammsb_store_bind_phi(ammsb_store* store, float* d_phi);
 /* host access to locally-owned rows (global row numbering) */
 int ammsb_store_write_pi(ammsb_store* store, uint64_t row0, uint64_t nrows, const float* h_src);
 int ammsb_store_read_pi(ammsb_store* store, uint64_t row0, uint64_t nrows, float* h_dst);

@@ -95,6 +95,7 @@ struct ammsb_store {
   float* peer_pi[AMMSB_MAX_SHARDS] = {nullptr};
   float* peer_phi[AMMSB_MAX_SHARDS] = {nullptr};
   bool peer_is_ipc[AMMSB_MAX_SHARDS] = {false};
+  bool owns_phi = true;
   StoreView view() const;
 };
 

@@ -256,7 +256,7 @@ extern "C" int ammsb_store_destroy(ammsb_store* s) {
     }
   }
   cudaFree(s->d_pi);
-  cudaFree(s->d_phi);
+  if (s->owns_phi) cudaFree(s->d_phi);
   delete s;
   return 0;
 }
@@ -320,6 +320,21 @@ extern "C" int ammsb_store_rows(const ammsb_store* s, uint64_t* first_row, uint6
 extern "C" int ammsb_store_local_ptrs(ammsb_store* s, float** d_pi, float** d_phi) {
   if (d_pi) *d_pi = s->d_pi;
   if (d_phi) *d_phi = s->d_phi;
+  return 0;
+}
+
+extern "C" int ammsb_store_bind_phi(ammsb_store* s, float* d_phi) {
+  AMMSB_REQUIRE(d_phi != nullptr, "null phi");
+  AMMSB_CHECK_CUDA(cudaSetDevice(s->ctx->device));
+  if (s->owns_phi) {
+    AMMSB_CHECK_CUDA(cudaMemcpyAsync(d_phi, s->d_phi, sizeof(float) * s->local_rows, cudaMemcpyDeviceToDevice,
+                                     s->ctx->stream));
+    AMMSB_CHECK_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    AMMSB_CHECK_CUDA(cudaFree(s->d_phi));
+  }
+  s->owns_phi = false;
+  s->d_phi = d_phi;
+  s->peer_phi[s->shard_id] = d_phi;
   return 0;
 }
 

@@ -1,0 +1,240 @@
+// capi.cc -- C wrappers over the C++ host API (mcmc::Config / Learner / data / sampling)
+// so that the Python test and bench harness can drive it with ctypes.  Not part of the
+// drop-in surface: a C++ user links libmcmc.so and includes mcmc/learner.h directly.
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <random>
+#include <sstream>
+
+#include "mcmc/learner.h"
+
+using namespace mcmc;
+
+namespace {
+thread_local std::string g_err;
+template <class F>
+int Guard(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char* mcmc_last_error() { return g_err.c_str(); }
+
+// ---- Config ----
+void* mcmc_config_create() { return new Config(); }
+void mcmc_config_destroy(void* c) { delete static_cast<Config*>(c); }
+
+int mcmc_config_set(void* vc, const char* key, double v) {
+  Config* c = static_cast<Config*>(vc);
+  const std::string k(key);
+  if (k == "heldout_ratio") c->heldout_ratio = v;
+  else if (k == "alpha") c->alpha = v;
+  else if (k == "a") c->a = v;
+  else if (k == "b") c->b = v;
+  else if (k == "c") c->c = v;
+  else if (k == "epsilon") c->epsilon = v;
+  else if (k == "eta0") c->eta0 = v;
+  else if (k == "eta1") c->eta1 = v;
+  else if (k == "K") c->K = static_cast<uint64_t>(v);
+  else if (k == "mini_batch_size") c->mini_batch_size = static_cast<uint64_t>(v);
+  else if (k == "num_node_sample") c->num_node_sample = static_cast<uint64_t>(v);
+  else if (k == "ppx_interval") c->ppx_interval = static_cast<uint32_t>(v);
+  else if (k == "neighbor_sampler_wg_size") c->neighbor_sampler_wg_size = static_cast<uint32_t>(v);
+  else if (k == "phi_wg_size") c->phi_wg_size = static_cast<uint32_t>(v);
+  else if (k == "phi_disable_noise") c->phi_disable_noise = v != 0;
+  else if (k == "strategy") c->strategy = static_cast<SampleStrategy>(static_cast<int>(v));
+  else if (k == "phi_mode") c->phi_mode = static_cast<PhiUpdaterMode>(static_cast<int>(v));
+  else if (k == "phi_strict") c->phi_strict = v != 0;
+  else if (k == "stage_timers") c->stage_timers = v != 0;
+  else { g_err = "unknown config key " + k; return 1; }
+  return 0;
+}
+int mcmc_config_set_seed(void* vc, const char* key, uint64_t x, uint64_t y) {
+  Config* c = static_cast<Config*>(vc);
+  const std::string k(key);
+  if (k == "phi_seed") c->phi_seed = {x, y};
+  else if (k == "beta_seed") c->beta_seed = {x, y};
+  else if (k == "neighbor_seed") c->neighbor_seed = {x, y};
+  else { g_err = "unknown seed " + k; return 1; }
+  return 0;
+}
+
+// main.cc:101-154 minus the file I/O: split, build sets and graphs, alpha = 1/K if 0
+int mcmc_config_set_graph(void* vc, uint64_t N, const uint64_t* edges, uint64_t n, unsigned srand_seed) {
+  Config* c = static_cast<Config*>(vc);
+  return Guard([&] {
+    std::vector<Edge> vals(edges, edges + n);
+    c->N = N;
+    c->training_edges.clear();
+    c->heldout_edges.clear();
+    srand(srand_seed);
+    if (!GenerateSetsFromEdges(N, vals, c->heldout_ratio, &c->training_edges, &c->heldout_edges, &c->training,
+                               &c->heldout))
+      throw std::runtime_error("Failed to generate training/heldout sets");
+    c->trainingGraph.reset(new Graph(N, c->training_edges));
+    c->heldoutGraph.reset(new Graph(N, c->heldout_edges));
+    if (c->alpha == 0) c->alpha = static_cast<Float>(1) / c->K;
+    c->E = vals.size();
+  });
+}
+uint64_t mcmc_config_num_training(void* vc) { return static_cast<Config*>(vc)->training_edges.size(); }
+uint64_t mcmc_config_num_heldout(void* vc) { return static_cast<Config*>(vc)->heldout_edges.size(); }
+void mcmc_config_get_edges(void* vc, uint64_t* training, uint64_t* heldout) {
+  Config* c = static_cast<Config*>(vc);
+  if (training) std::memcpy(training, c->training_edges.data(), 8 * c->training_edges.size());
+  if (heldout) std::memcpy(heldout, c->heldout_edges.data(), 8 * c->heldout_edges.size());
+}
+uint64_t mcmc_config_max_fan_out(void* vc) { return static_cast<Config*>(vc)->trainingGraph->MaxFanOut(); }
+uint64_t mcmc_config_max_nodes(void* vc) { return MaxMiniBatchNodes(*static_cast<Config*>(vc)); }
+uint64_t mcmc_config_max_edges(void* vc) { return MaxMiniBatchEdges(*static_cast<Config*>(vc)); }
+int mcmc_config_print(void* vc, char* buf, size_t len) {
+  std::ostringstream o;
+  o << *static_cast<Config*>(vc);
+  std::strncpy(buf, o.str().c_str(), len - 1);
+  buf[len - 1] = 0;
+  return 0;
+}
+void mcmc_config_params(void* vc, ammsb_params* p) { *p = MakeParams(*static_cast<Config*>(vc)); }
+// the training/held-out cuckoo tables as the device sees them
+uint64_t mcmc_config_set_info(void* vc, int which, uint64_t* bins, uint32_t* prime) {
+  Config* c = static_cast<Config*>(vc);
+  Set* s = which == 0 ? c->training.get() : c->heldout.get();
+  *bins = s->BinsPerBucket();
+  *prime = s->PrimeIdx();
+  return s->Capacity();
+}
+void mcmc_config_set_table(void* vc, int which, uint64_t* table) {
+  Config* c = static_cast<Config*>(vc);
+  Set* s = which == 0 ? c->training.get() : c->heldout.get();
+  std::vector<Edge> t = s->Serialize();
+  std::memcpy(table, t.data(), 8 * t.size());
+}
+
+// one host mini-batch with the given strategy (enum order of sample.h)
+float mcmc_sample(void* vc, int strategy, unsigned* seed, uint64_t* edges_out, uint64_t* n_edges,
+                  uint32_t* nodes_out, uint64_t* n_nodes) {
+  Config* c = static_cast<Config*>(vc);
+  std::vector<Edge> edges;
+  float w = 0;
+  switch (strategy) {
+    case Node: w = sampleNode(*c, &edges, seed); break;
+    case NodeLink: w = sampleNodeLink(*c, &edges, seed); break;
+    case NodeNonLink: w = sampleNodeNonLink(*c, &edges, seed); break;
+    case BFLink: w = sampleBreadthFirstLink(*c, &edges, seed); break;
+    case BFNonLink: w = sampleBreadthFirstNonLink(*c, &edges, seed); break;
+    default: w = sampleBreadthFirst(*c, &edges, seed); break;
+  }
+  std::vector<Vertex> nodes;
+  ExtractNodesFromMiniBatch(edges, &nodes);
+  std::memcpy(edges_out, edges.data(), 8 * edges.size());
+  std::memcpy(nodes_out, nodes.data(), 4 * nodes.size());
+  *n_edges = edges.size();
+  *n_nodes = nodes.size();
+  return w;
+}
+
+// standalone host cuckoo build (parity of the table image with the oracle/reference)
+int mcmc_host_set_build(const uint64_t* keys, uint64_t n, uint64_t* table_out, uint64_t table_cap,
+                        uint64_t* bins, uint32_t* prime, uint64_t* size) {
+  std::vector<Edge> v(keys, keys + n);
+  Set s(n);
+  const bool ok = s.SetContents(v.begin(), v.end());
+  *bins = s.BinsPerBucket();
+  *prime = s.PrimeIdx();
+  *size = s.Size();
+  std::vector<Edge> t = s.Serialize();
+  if (t.size() <= table_cap) std::memcpy(table_out, t.data(), 8 * t.size());
+  return ok ? 1 : 0;
+}
+uint64_t mcmc_host_set_bins(uint64_t n) { return Set(n).BinsPerBucket(); }
+
+// theta init stream of Learner::Learner (host mt19937 + gamma_distribution)
+void mcmc_init_theta_host(uint32_t K, float eta0, float eta1, float* theta_out) {
+  std::mt19937 engine(6342455113);
+  std::gamma_distribution<Float> dist(eta0, eta1);
+  auto gamma = std::bind(dist, engine);
+  std::vector<Float> host(2 * K);
+  std::generate(host.begin(), host.end(), gamma);
+  std::memcpy(theta_out, host.data(), 4 * host.size());
+}
+
+// ---- Learner ----
+struct LearnerBox {
+  clcuda::Context ctx;
+  clcuda::Queue queue;
+  std::unique_ptr<Learner> learner;
+};
+
+void* mcmc_learner_create(void* vc, int device) {
+  LearnerBox* b = nullptr;
+  const int rc = Guard([&] {
+    b = new LearnerBox();
+    clcuda::Device dev(device);
+    b->ctx = clcuda::Context(dev);
+    b->queue = clcuda::Queue(b->ctx, dev);
+    b->learner.reset(new Learner(*static_cast<Config*>(vc), b->queue));
+  });
+  if (rc) {
+    delete b;
+    return nullptr;
+  }
+  return b;
+}
+void mcmc_learner_destroy(void* vb) { delete static_cast<LearnerBox*>(vb); }
+int mcmc_learner_run(void* vb, uint32_t iters) {
+  return Guard([&] { static_cast<LearnerBox*>(vb)->learner->Run(iters); });
+}
+int mcmc_learner_heldout_perplexity(void* vb, float* out) {
+  return Guard([&] { *out = static_cast<LearnerBox*>(vb)->learner->HeldoutPerplexity(); });
+}
+int mcmc_learner_print_stats(void* vb) {
+  return Guard([&] { static_cast<LearnerBox*>(vb)->learner->PrintStats(); });
+}
+int mcmc_learner_read(void* vb, float* pi /* [N,K] or null */, float* phi, float* beta, float* theta,
+                      uint64_t N) {
+  return Guard([&] {
+    Learner* l = static_cast<LearnerBox*>(vb)->learner.get();
+    if (pi) l->ReadPi(0, N, pi);
+    if (phi) l->ReadPhi(phi);
+    if (beta) l->ReadBeta(beta);
+    if (theta) l->ReadTheta(theta);
+  });
+}
+uint64_t mcmc_learner_edges_processed(void* vb) { return static_cast<LearnerBox*>(vb)->learner->EdgesProcessed(); }
+// the mini-batch the next Run() iteration will consume
+int mcmc_learner_peek(void* vb, uint64_t* edges, uint64_t* n_edges, uint32_t* nodes, uint64_t* n_nodes,
+                      uint32_t* neighbors /* [n_nodes, n] */, uint32_t n) {
+  return Guard([&] {
+    LearnerBox* b = static_cast<LearnerBox*>(vb);
+    const Sample& s = b->learner->PeekNextSample();
+    *n_edges = s.edges.size();
+    *n_nodes = s.nodes_vec.size();
+    std::memcpy(edges, s.edges.data(), 8 * s.edges.size());
+    std::memcpy(nodes, s.nodes_vec.data(), 4 * s.nodes_vec.size());
+    Sample& ms = const_cast<Sample&>(s);
+    ms.neighbor_sampler.GetData().Read(ms.queue, s.nodes_vec.size() * n, neighbors);
+  });
+}
+int mcmc_learner_serialize(void* vb, const char* path) {
+  return Guard([&] {
+    std::ofstream out(path, std::ios::binary);
+    if (!static_cast<LearnerBox*>(vb)->learner->Serialize(&out)) throw std::runtime_error("Serialize failed");
+  });
+}
+int mcmc_learner_parse(void* vb, const char* path) {
+  return Guard([&] {
+    std::ifstream in(path, std::ios::binary);
+    if (!static_cast<LearnerBox*>(vb)->learner->Parse(&in)) throw std::runtime_error("Parse failed");
+  });
+}
+
+}  // extern "C"

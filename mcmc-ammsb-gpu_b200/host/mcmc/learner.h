@@ -1,0 +1,80 @@
+// mcmc/learner.h -- the SG-MCMC learner for the a-MMSB.
+// Drop-in for the reference's mcmc::Learner (learner.h:18-88): same constructor, Run,
+// HeldoutPerplexity, PrintStats, Serialize, Parse.  Owns all device state; one
+// iteration = (async, double-buffered) mini-batch + neighbor sampling -> update_phi ->
+// update_pi -> update_beta/theta, all on sm_100a kernels through the C ABI.
+#ifndef MCMC_B200_LEARNER_H_
+#define MCMC_B200_LEARNER_H_
+
+#include <signal.h>
+
+#include <future>
+#include <ostream>
+
+#include "mcmc/beta.h"
+#include "mcmc/config.h"
+#include "mcmc/data.h"
+#include "mcmc/perplexity.h"
+#include "mcmc/phi.h"
+
+namespace mcmc {
+
+class Learner {
+ public:
+  // cfg is held by reference (as in the reference): it must outlive the Learner
+  Learner(const Config& cfg, clcuda::Queue queue);
+  ~Learner();
+
+  void Run(uint32_t max_iters, sig_atomic_t* signaled = nullptr);
+  Float HeldoutPerplexity();
+  void PrintStats();
+  bool Serialize(std::ostream* out);
+  bool Parse(std::istream* in);
+
+  static const std::string GetBaseFuncs() { return std::string(); }  // no JIT prelude
+
+  // state access for tests / tools (not in the reference API)
+  void ReadPi(uint64_t row0, uint64_t nrows, Float* host) { pi_->ReadRows(row0, nrows, host); }
+  void ReadPhi(Float* host) { phi_.Read(queue_, cfg_.N, host); }
+  void ReadBeta(Float* host) { beta_.Read(queue_, 2 * cfg_.K, host); }
+  void ReadTheta(Float* host) { theta_.Read(queue_, 2 * cfg_.K, host); }
+  uint32_t StepCount() const { return stepCount_; }
+  uint64_t EdgesProcessed() const { return edgesProcessed_; }
+  // the mini-batch the next iteration will consume (joins the sampler thread)
+  const Sample& PeekNextSample();
+
+ private:
+  Float SampleMiniBatch(std::vector<Edge>* edges, unsigned int* seed);
+  Float DoSample(Sample* sample);
+
+  const Config& cfg_;
+  clcuda::Queue queue_;
+  clcuda::Buffer<Float> beta_;   // [K,2]
+  clcuda::Buffer<Float> theta_;  // [K,2]
+  std::shared_ptr<RowPartitionedMatrixFactory<Float>> allocFactory_;
+  std::unique_ptr<RowPartitionedMatrix<Float>> pi_;  // [N,K]
+  clcuda::Buffer<Float> phi_;                        // [N]
+  std::shared_ptr<OpenClSetFactory> setFactory_;
+  std::unique_ptr<OpenClSet> trainingSet_;
+  std::unique_ptr<OpenClSet> heldoutSet_;
+  clcuda::Buffer<Edge> trainingEdges_;
+  clcuda::Buffer<Edge> heldoutEdges_;
+  std::vector<std::string> compileFlags_;
+  PerplexityCalculator heldoutPerplexity_;
+  PhiUpdater phiUpdater_;
+  BetaUpdater betaUpdater_;
+  Float (*sampler_)(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed);
+  uint32_t stepCount_;
+  uint64_t time_;
+  uint64_t samplingTime_;
+  uint64_t edgesProcessed_;
+  Sample samples_[2];
+  std::future<Float> futures_[2];
+  Float pendingWeight_[2];
+  bool pendingValid_[2];
+  int phase_;
+};
+
+}  // namespace mcmc
+
+#endif  // MCMC_B200_LEARNER_H_

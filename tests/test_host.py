@@ -1,0 +1,95 @@
+"""CPU tests of the C++ host side (libmcmc.so) -- no GPU involved:
+cuckoo build == oracle/reference table image, split + mini-batch strategies == golden
+vectors generated from the reference's own data.cc / sample.cc, checkpoint wire codec."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import pymcmc
+from util import make_edges
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_host_cuckoo_table_equals_oracle(orc):
+    for n, seed in ((5000, 1), (20001, 2), (300, 3)):
+        keys = make_edges(4000, n, seed)
+        want = orc.set_build(keys)
+        ok, table, bins, prime, size = pymcmc.host_set_build(keys)
+        assert ok
+        assert (bins, prime, size) == (want.num_bins, want.prime_idx, want.count)
+        assert np.array_equal(table, want.table())
+
+
+def test_host_cuckoo_golden_table():
+    g = np.load(os.path.join(GOLD, "operators.npz"))
+    ok, table, bins, prime, _ = pymcmc.host_set_build(g["train_edges"])
+    assert ok and np.array_equal(table, g["train_table"])
+    assert (bins, prime) == (int(g["train_bins"]), int(g["train_prime"]))
+
+
+def test_host_cuckoo_build_failure_is_reported(orc):
+    # both hashes depend on k mod 16 when bins == 16: the reference cannot place 100 keys
+    keys = make_edges(800, 6000, 1)[:100]
+    ok = pymcmc.host_set_build(keys)[0]
+    with pytest.raises(RuntimeError):
+        orc.set_build(keys)
+    assert not ok
+
+
+@pytest.fixture(scope="module")
+def host_gold():
+    return np.load(os.path.join(GOLD, "host.npz"))
+
+
+@pytest.fixture(scope="module")
+def cfg(host_gold):
+    g = host_gold
+    c = pymcmc.Config(K=8, mini_batch_size=int(g["m"]), heldout_ratio=float(g["heldout_ratio"]))
+    c.set_graph(int(g["N"]), g["edges"], srand_seed=int(g["srand_seed"]))
+    yield c
+    c.close()
+
+
+def test_split_matches_reference(cfg, host_gold):
+    tr, he = cfg.edges()
+    assert np.array_equal(tr, host_gold["training"])
+    assert np.array_equal(he, host_gold["heldout"])  # held-out links + libc rand() fake non-links
+    assert cfg.max_fan_out() == int(host_gold["max_fan_out"])
+
+
+@pytest.mark.parametrize("strategy", pymcmc.STRATEGIES)
+def test_minibatch_strategies_match_reference(cfg, host_gold, strategy):
+    g = host_gold
+    s = pymcmc.STRATEGIES.index(strategy)
+    seed = C.c_uint(1000 + s)
+    meta = g["mb_%s_meta" % strategy]
+    eoff = noff = 0
+    for it in range(len(meta)):
+        w, edges, nodes = cfg.sample(strategy, seed)
+        ne, nn = int(meta[it][0]), int(meta[it][1])
+        assert (len(edges), len(nodes)) == (ne, nn)
+        assert np.array_equal(edges, g["mb_%s_edges" % strategy][eoff:eoff + ne])  # order included
+        assert np.array_equal(nodes, g["mb_%s_nodes" % strategy][noff:noff + nn])
+        assert np.float32(w) == np.float32(meta[it][2])
+        assert seed.value == int(meta[it][3])
+        eoff += ne
+        noff += nn
+
+
+def test_params_rounding_and_print(cfg):
+    p = cfg.params()
+    assert p.K == 8 and p.alpha == np.float32(0.125)
+    assert abs(p.a - 0.0315) < 1e-9 and p.a == np.float32(float("3.150000e-02"))
+    text = str(cfg)
+    assert "strategy: Node" in text and "phi_mode: WG-NAIVE" in text and "beta-seed: 44,45" in text
+
+
+def test_theta_init_is_the_libstdcxx_stream():
+    a = pymcmc.init_theta_host(64)
+    b = pymcmc.init_theta_host(64)
+    assert np.array_equal(a, b) and (a > 0).all() and abs(float(a.mean()) - 1.0) < 0.25
+    assert np.array_equal(pymcmc.init_theta_host(16), a[:32])
