@@ -209,13 +209,15 @@ int mcmc_learner_read(void* vb, float* pi /* [N,K] or null */, float* phi, float
     if (theta) l->ReadTheta(theta);
   });
 }
+uint64_t mcmc_learner_h2d_bytes(void* vb) { return static_cast<LearnerBox*>(vb)->learner->BytesH2D(); }
 uint64_t mcmc_learner_edges_processed(void* vb) { return static_cast<LearnerBox*>(vb)->learner->EdgesProcessed(); }
 // the mini-batch the next Run() iteration will consume
 int mcmc_learner_peek(void* vb, uint64_t* edges, uint64_t* n_edges, uint32_t* nodes, uint64_t* n_nodes,
-                      uint32_t* neighbors /* [n_nodes, n] */, uint32_t n) {
+                      uint32_t* neighbors /* [n_nodes, n] */, uint32_t n, float* weight) {
   return Guard([&] {
     LearnerBox* b = static_cast<LearnerBox*>(vb);
     const Sample& s = b->learner->PeekNextSample();
+    *weight = b->learner->PeekNextWeight();
     *n_edges = s.edges.size();
     *n_nodes = s.nodes_vec.size();
     std::memcpy(edges, s.edges.data(), 8 * s.edges.size());

@@ -50,6 +50,7 @@ Learner::Learner(const Config& cfg, clcuda::Queue queue)
       time_(0),
       samplingTime_(0),
       edgesProcessed_(0),
+      h2dBytes_(0),
       samples_{Sample(cfg_, queue_), Sample(cfg_, queue_)},
       pendingWeight_{0, 0},
       pendingValid_{false, false},
@@ -85,6 +86,7 @@ Float Learner::DoSample(Sample* sample) {
     throw BackendError("mini-batch exceeds the device buffers");
   sample->dev_edges.Write(sample->queue, sample->edges.size(), sample->edges.data());
   sample->dev_nodes.Write(sample->queue, sample->nodes_vec.size(), sample->nodes_vec.data());
+  h2dBytes_ += sample->edges.size() * sizeof(Edge) + sample->nodes_vec.size() * sizeof(Vertex);
   sample->neighbor_sampler(static_cast<uint32_t>(sample->nodes_vec.size()), &sample->dev_nodes);
   return weight;
 }

@@ -8,6 +8,7 @@
 
 #include <signal.h>
 
+#include <atomic>
 #include <future>
 #include <ostream>
 
@@ -40,8 +41,10 @@ class Learner {
   void ReadTheta(Float* host) { theta_.Read(queue_, 2 * cfg_.K, host); }
   uint32_t StepCount() const { return stepCount_; }
   uint64_t EdgesProcessed() const { return edgesProcessed_; }
+  uint64_t BytesH2D() const { return h2dBytes_; }  // mini-batch edges + nodes copied to the device so far
   // the mini-batch the next iteration will consume (joins the sampler thread)
   const Sample& PeekNextSample();
+  Float PeekNextWeight() { PeekNextSample(); return pendingWeight_[phase_]; }
 
  private:
   Float SampleMiniBatch(std::vector<Edge>* edges, unsigned int* seed);
@@ -68,6 +71,7 @@ class Learner {
   uint64_t time_;
   uint64_t samplingTime_;
   uint64_t edgesProcessed_;
+  std::atomic<uint64_t> h2dBytes_;
   Sample samples_[2];
   std::future<Float> futures_[2];
   Float pendingWeight_[2];

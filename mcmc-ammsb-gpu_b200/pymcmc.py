@@ -54,9 +54,11 @@ def lib():
         L.mcmc_learner_print_stats.argtypes = [C.c_void_p]
         L.mcmc_learner_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.mcmc_learner_edges_processed.restype = C.c_uint64
+        L.mcmc_learner_h2d_bytes.restype = C.c_uint64
+        L.mcmc_learner_h2d_bytes.argtypes = [C.c_void_p]
         L.mcmc_learner_edges_processed.argtypes = [C.c_void_p]
         L.mcmc_learner_peek.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_uint32]
+                                        C.c_uint32, C.c_void_p]
         L.mcmc_learner_serialize.argtypes = [C.c_void_p, C.c_char_p]
         L.mcmc_learner_parse.argtypes = [C.c_void_p, C.c_char_p]
         _lib = L
@@ -188,6 +190,15 @@ class Learner:
         _ck(lib().mcmc_learner_read(self.h, _p(pi_a) if pi else None, _p(phi), _p(beta), _p(theta), N))
         return pi_a, phi, beta, theta
 
+    def read_beta(self, K, out=None):
+        """device -> host read of beta [2K] (the per-iteration result a caller polls)"""
+        beta = np.empty(2 * K, np.float32) if out is None else out
+        _ck(lib().mcmc_learner_read(self.h, None, None, _p(beta), None, 0))
+        return beta
+
+    def h2d_bytes(self):
+        return int(lib().mcmc_learner_h2d_bytes(self.h))
+
     def edges_processed(self):
         return int(lib().mcmc_learner_edges_processed(self.h))
 
@@ -196,8 +207,9 @@ class Learner:
         nb = np.zeros(self.cfg.max_nodes(), dtype=np.uint32)
         nbr = np.zeros(self.cfg.max_nodes() * n, dtype=np.uint32)
         ne, nn = C.c_uint64(0), C.c_uint64(0)
-        _ck(lib().mcmc_learner_peek(self.h, _p(eb), C.byref(ne), _p(nb), C.byref(nn), _p(nbr), n))
-        return eb[:ne.value].copy(), nb[:nn.value].copy(), nbr[:nn.value * n].reshape(-1, n).copy()
+        w = C.c_float(0)
+        _ck(lib().mcmc_learner_peek(self.h, _p(eb), C.byref(ne), _p(nb), C.byref(nn), _p(nbr), n, C.byref(w)))
+        return eb[:ne.value].copy(), nb[:nn.value].copy(), nbr[:nn.value * n].reshape(-1, n).copy(), w.value
 
     def serialize(self, path):
         _ck(lib().mcmc_learner_serialize(self.h, path.encode()))

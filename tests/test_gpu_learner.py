@@ -1,0 +1,198 @@
+"""GPU tests of the C++ host API (mcmc::Learner over the C ABI) against the CPU oracle:
+per-iteration parity, free-running perplexity trajectory, checkpoint/resume determinism
+(serialize-test.cc:90-134), all six mini-batch strategies, and the CLI binary."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import pyammsb as A
+import pymcmc
+from util import make_edges, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-5  # north_star: pi/beta within 1e-5 relative per iteration
+PPX_TOL = 1e-3  # north_star: perplexity trajectory within 1e-3 after N iterations
+
+
+def make_cfg(N=1200, E=9000, K=64, m=64, n=16, seed=4, **kw):
+    cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=0.1, **kw)
+    cfg.set_graph(N, make_edges(N, E, seed))
+    return cfg
+
+
+class OracleLearner:
+    """The reference schedule (learner.cc:214-250) restated over the oracle operators; the
+    mini-batches (edges, nodes, weight) are the ones the device Learner is about to consume,
+    everything else -- neighbor sampling, phi/pi, beta/theta, perplexity -- is the oracle's."""
+
+    def __init__(self, orc, cfg, lrn, N, K, n):
+        self.orc, self.cfg, self.N, self.K, self.n = orc, cfg, N, K, n
+        self.p = orc.make_params(N, len(cfg.edges()[0]) + 0, K, n)
+        self.p.E = cfg.params().E
+        tr, he = cfg.edges()
+        self.train_set = orc.set_build(tr)
+        nl = len(he) // 2
+        self.heldout_set = orc.set_build(he[:nl])
+        self.heldout_edges = he
+        self.pi, self.phi, self.beta, self.theta = lrn.read(N, K)
+        self.phi_pool = orc.rng_pool(cfg.max_nodes() * 32, 42, 43)
+        self.beta_pool = orc.rng_pool(K, 44, 45)
+        self.nb_pools = [orc.rng_pool(cfg.max_nodes() * 2 * n, 56, 57) for _ in range(2)]
+        self.phase = 0
+        self.step = 0
+        self.ppx_per_edge = np.zeros(len(he), dtype=np.float32)
+        self.ppx_calls = 0
+
+    def iterate(self, edges, nodes, weight):
+        o = self.orc
+        nbrs, _ = o.neighbor_sample(self.nb_pools[self.phase], nodes, self.N, self.n, 32)
+        self.step += 1
+        vec = o.update_phi(A.MODE_WG, 32, self.p, self.beta, self.pi, self.phi, self.train_set, nodes, nbrs,
+                           self.step, self.phi_pool)
+        o.update_pi(A.MODE_WG, 32, self.K, self.pi, self.phi, vec, nodes)
+        o.update_beta(A.MODE_WG, 32, self.p, self.theta, self.beta, self.pi, self.train_set, edges, weight,
+                      self.step, self.beta_pool)
+        self.phase = 1 - self.phase
+        return nbrs
+
+    def perplexity(self):
+        self.ppx_calls += 1
+        avg, _ = self.orc.perplexity(A.MODE_WG, 32, self.p, self.pi, self.beta, self.heldout_set,
+                                     self.heldout_edges, self.ppx_per_edge, self.ppx_calls)
+        return float(np.exp(np.float32(avg)))
+
+
+def close_enough(got, want, what, frac=2e-3):
+    e = rel_err(got, want)
+    assert np.median(e) < 1e-6, (what, np.median(e))
+    assert float((e > RTOL).mean()) < frac, (what, float((e > RTOL).mean()), e.max())
+
+
+@pytest.mark.parametrize("strategy", ["Node", "BF"])
+def test_learner_iterations_match_oracle(ctx, orc, strategy):
+    N, K, n = 1200, 64, 16
+    cfg = make_cfg(N=N, K=K, n=n, strategy=strategy)
+    lrn = pymcmc.Learner(cfg, 0)
+    ol = OracleLearner(orc, cfg, lrn, N, K, n)
+    # initial state is the reference's: libstdc++ gamma stream for theta, device gamma for pi
+    pi0, phi0 = orc.init_pi(N, K)
+    close_enough(ol.pi, pi0, "init pi")
+    assert np.array_equal(ol.theta, pymcmc.init_theta_host(K))
+    assert abs(lrn.heldout_perplexity() - ol.perplexity()) <= PPX_TOL * ol.perplexity()
+    sizes = []
+    for it in range(40):
+        edges, nodes, nbrs, weight = lrn.peek(n)
+        sizes.append(len(nodes))
+        want_nbrs = ol.iterate(edges, nodes, weight)
+        assert np.array_equal(nbrs, want_nbrs), "iteration %d: neighbor ids differ" % it
+        lrn.run(1)
+        if it in (0, 1, 5, 39):
+            pi, phi, beta, theta = lrn.read(N, K)
+            # per-iteration gate: compare, then continue the oracle from the device state so
+            # that every iteration is judged on its own
+            close_enough(pi[nodes], ol.pi[nodes], "pi it %d" % it)
+            close_enough(phi[nodes], ol.phi[nodes], "phi it %d" % it)
+            close_enough(theta, ol.theta, "theta it %d" % it, frac=2e-2)
+            close_enough(beta, ol.beta, "beta it %d" % it, frac=2e-2)
+    assert len(set(sizes)) > 1 or strategy != "Node"  # both link and non-link mini-batches occurred
+    assert lrn.edges_processed() > 0
+    got, want = lrn.heldout_perplexity(), ol.perplexity()
+    print("perplexity after 40 free-running iterations: device %.6f oracle %.6f" % (got, want))
+    assert abs(got - want) <= PPX_TOL * want
+    lrn.close()
+    cfg.close()
+
+
+def test_learner_perplexity_trajectory(ctx, orc):
+    """free-running (never re-synchronised) 200 iterations: perplexity within 1e-3 throughout"""
+    N, K, n = 800, 32, 8
+    cfg = make_cfg(N=N, E=6000, K=K, m=32, n=n, seed=9)
+    lrn = pymcmc.Learner(cfg, 0)
+    ol = OracleLearner(orc, cfg, lrn, N, K, n)
+    worst = 0.0
+    for block in range(10):
+        for _ in range(20):
+            edges, nodes, _, weight = lrn.peek(n)
+            ol.iterate(edges, nodes, weight)
+            lrn.run(1)
+        got, want = lrn.heldout_perplexity(), ol.perplexity()
+        worst = max(worst, abs(got - want) / want)
+    print("worst perplexity deviation over 200 iterations: %.3e (last %.6f vs %.6f)" % (worst, got, want))
+    assert worst <= PPX_TOL
+    lrn.close()
+    cfg.close()
+
+
+def test_learner_checkpoint_resume_is_bit_exact(ctx):
+    """serialize-test.cc:90-134 EndToEnd: 10 iterations, Serialize, 10 more -> ppx; a fresh
+    Learner Parse()s the file, runs 10 -> ppx2; ASSERT_EQ(ppx, ppx2)."""
+    cfg = make_cfg(N=1024, E=1024 * 4, K=32, m=32, n=8, seed=12)
+    path = os.path.join(tempfile.mkdtemp(), "ckpt.bin")
+    lrn = pymcmc.Learner(cfg, 0)
+    lrn.run(10)
+    lrn.serialize(path)
+    lrn.run(10)
+    ppx = lrn.heldout_perplexity()
+    state = lrn.read(1024, 32)
+    lrn.close()
+    lrn2 = pymcmc.Learner(cfg, 0)
+    lrn2.parse(path)
+    lrn2.run(10)
+    ppx2 = lrn2.heldout_perplexity()
+    state2 = lrn2.read(1024, 32)
+    assert ppx == ppx2
+    for a, b in zip(state, state2):
+        assert np.array_equal(a, b)
+    lrn2.close()
+    cfg.close()
+
+
+@pytest.mark.parametrize("strategy", pymcmc.STRATEGIES)
+def test_learner_runs_every_strategy(ctx, strategy):
+    cfg = make_cfg(N=600, E=5000, K=32, m=32, n=8, seed=2, strategy=strategy)
+    lrn = pymcmc.Learner(cfg, 0)
+    p0 = lrn.heldout_perplexity()
+    lrn.run(25)
+    p1 = lrn.heldout_perplexity()
+    pi, phi, beta, theta = lrn.read(600, 32)
+    assert np.isfinite(p0) and np.isfinite(p1)
+    assert np.allclose(pi.sum(axis=1), 1.0, atol=1e-4) and (pi > 0).all() and (phi > 0).all()
+    assert np.allclose(beta[0::2] + beta[1::2], 1.0, atol=1e-5)
+    lrn.close()
+    cfg.close()
+
+
+def test_learner_phi_modes_agree(ctx):
+    """wg-phi-test.cc:116-158: THREAD vs WG-NAIVE state within 2% with noise disabled."""
+    outs = []
+    for mode in ("THREAD", "WG-NAIVE"):
+        cfg = make_cfg(N=700, E=5000, K=64, m=64, n=8, seed=5, phi_mode=mode, phi_disable_noise=1)
+        lrn = pymcmc.Learner(cfg, 0)
+        for _ in range(3):
+            lrn.peek(8)
+            lrn.run(1)
+        outs.append(lrn.read(700, 64))
+        lrn.close()
+        cfg.close()
+    assert rel_err(outs[0][0], outs[1][0]).max() < 0.02
+    assert rel_err(outs[0][1], outs[1][1]).max() < 0.02
+
+
+def test_cli_runs_on_a_snap_file(ctx, tmp_path):
+    """main.cc: SNAP text in (4 header lines), ppx[...] lines out"""
+    edges = make_edges(500, 4000, 3)
+    f = tmp_path / "g.txt"
+    with open(f, "w") as out:
+        out.write("# a\n# b\n# c\n# d\n")
+        for e in edges:
+            out.write("%d\t%d\n" % (int(e) >> 32, int(e) & 0xffffffff))
+    exe = os.path.join(ROOT, "mcmc-ammsb-gpu_b200", "ammsb-main")
+    r = subprocess.run([exe, "-f", str(f), "-k", "16", "-m", "16", "-n", "8", "-x", "30", "-i", "10"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (r.stdout + r.stderr).count("ppx[") >= 3
