@@ -179,15 +179,30 @@ __global__ void __launch_bounds__(BETA_WARPS * 32)
 // sum_theta (beta.cc:30-37) + the tail of calculate_grads_partial/sum_grads:
 //   g_k0 = A_k (1/theta_k0 - 1/thetaSum_k) - B_k / thetaSum_k
 //   g_k1 = B_k (1/theta_k1 - 1/thetaSum_k) - A_k / thetaSum_k        (beta.cc:130-135)
-__global__ void k_beta_reduce(const float* __restrict__ partial, uint32_t P, uint32_t K,
-                              const float* __restrict__ theta, float* __restrict__ theta_sum,
-                              float* __restrict__ grads) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+#define BETA_RED_PY 16
+__global__ void __launch_bounds__(32 * BETA_RED_PY)
+    k_beta_reduce(const float* __restrict__ partial, uint32_t P, uint32_t K,
+                  const float* __restrict__ theta, float* __restrict__ theta_sum,
+                  float* __restrict__ grads) {
+  // 32 consecutive k per CTA; the P partials are split over BETA_RED_PY rows of threads
+  // (p = py, py + PY, ...), combined in row order: a fixed association for a given P
+  __shared__ float sA[BETA_RED_PY][32], sB[BETA_RED_PY][32];
+  const uint32_t kx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const uint32_t k = blockIdx.x * 32 + kx;
   float A = 0.f, B = 0.f;
-  for (uint32_t p = 0; p < P; ++p) {
-    A += partial[(size_t)p * 2 * K + k];
-    B += partial[(size_t)p * 2 * K + K + k];
+  if (k < K) {
+    for (uint32_t p = py; p < P; p += BETA_RED_PY) {
+      A += partial[(size_t)p * 2 * K + k];
+      B += partial[(size_t)p * 2 * K + K + k];
+    }
+  }
+  sA[py][kx] = A;
+  sB[py][kx] = B;
+  __syncthreads();
+  if (py != 0 || k >= K) return;
+  for (uint32_t r = 1; r < BETA_RED_PY; ++r) {
+    A += sA[r][kx];
+    B += sB[r][kx];
   }
   const float t0 = theta[2 * k], t1 = theta[2 * k + 1];
   const float ts = __fadd_rn(t0, t1);
@@ -273,7 +288,7 @@ extern "C" int ammsb_beta_grads(ammsb_ctx* c, const ammsb_params* p, const float
     }
     AMMSB_LAUNCH_CHECK();
   }
-  k_beta_reduce<<<(K + 127) / 128, 128, 0, c->stream>>>((const float*)d_ws, ctas, K, d_theta,
+  k_beta_reduce<<<(K + 31) / 32, 32 * BETA_RED_PY, 0, c->stream>>>((const float*)d_ws, ctas, K, d_theta,
                                                         d_theta_sum, d_grads);
   AMMSB_LAUNCH_CHECK();
   return 0;

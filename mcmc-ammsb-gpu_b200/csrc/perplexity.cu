@@ -97,13 +97,14 @@ __global__ void __launch_bounds__(PPX_WARPS * 32) k_perplexity(const __grid_cons
   }
 }
 
-__global__ void k_ppx_reduce(const double* partial, uint32_t P, double* sums) {
-  const uint32_t t = threadIdx.x;
-  if (t < 4) {
-    double s = 0.0;
-    for (uint32_t p = 0; p < P; ++p) s += partial[(size_t)p * 4 + t];
-    sums[t] = s;
-  }
+// one warp per quantity: lane-strided partial sums in a fixed order, then the shuffle tree
+__global__ void __launch_bounds__(128) k_ppx_reduce(const double* __restrict__ partial, uint32_t P,
+                                                    double* __restrict__ sums) {
+  const uint32_t q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (uint32_t p = lane; p < P; p += 32) s += partial[(size_t)p * 4 + q];
+  s = warp_sum_d(s);
+  if (lane == 0) sums[q] = s;
 }
 
 static uint32_t ppx_max_ctas(const ammsb_ctx* c) { return (uint32_t)c->sm_count * 8; }
@@ -143,7 +144,7 @@ extern "C" int ammsb_perplexity_partial(ammsb_ctx* c, const ammsb_params* p, amm
     k_perplexity<<<ctas, PPX_WARPS * 32, smem, c->stream>>>(a);
     AMMSB_LAUNCH_CHECK();
   }
-  k_ppx_reduce<<<1, 32, 0, c->stream>>>((const double*)d_ws, ctas, d_sums);
+  k_ppx_reduce<<<1, 128, 0, c->stream>>>((const double*)d_ws, ctas, d_sums);
   AMMSB_LAUNCH_CHECK();
   return 0;
 }

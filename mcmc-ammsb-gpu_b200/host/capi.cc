@@ -209,6 +209,9 @@ int mcmc_learner_read(void* vb, float* pi /* [N,K] or null */, float* phi, float
     if (theta) l->ReadTheta(theta);
   });
 }
+int mcmc_learner_mirror_beta(void* vb, float* pinned_host) {
+  return Guard([&] { static_cast<LearnerBox*>(vb)->learner->MirrorBetaTo(pinned_host); });
+}
 uint64_t mcmc_learner_h2d_bytes(void* vb) { return static_cast<LearnerBox*>(vb)->learner->BytesH2D(); }
 uint64_t mcmc_learner_edges_processed(void* vb) { return static_cast<LearnerBox*>(vb)->learner->EdgesProcessed(); }
 // the mini-batch the next Run() iteration will consume

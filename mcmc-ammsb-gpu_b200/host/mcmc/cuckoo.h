@@ -25,6 +25,22 @@ class Set {
 
   bool SetContents(std::vector<Edge>::const_iterator start, std::vector<Edge>::const_iterator end);
   bool Has(Edge k) const;
+  // Has() split in two so that a caller can hash a batch of keys, prefetch their bins and
+  // only then compare (the host mini-batch sampler does; the answers are those of Has)
+  void Locate(Edge k, size_t bins[NUM_BUCKETS]) const {
+    bins[0] = Bin(k, 0);
+    bins[1] = Bin(k, 1);
+    __builtin_prefetch(Cell(0, bins[0]));
+    __builtin_prefetch(Cell(1, bins[1]));
+  }
+  bool HasAt(Edge k, const size_t bins[NUM_BUCKETS]) const {
+    for (size_t b = 0; b < NUM_BUCKETS; ++b) {
+      const Edge* cell = Cell(b, bins[b]);
+      for (size_t s = 0; s < NUM_SLOTS; ++s)
+        if (cell[s] == k) return true;
+    }
+    return false;
+  }
 
   size_t BinsPerBucket() const { return bins_; }
   size_t Capacity() const { return bins_ * NUM_SLOTS * NUM_BUCKETS; }

@@ -11,6 +11,79 @@ using namespace std::chrono;
 
 namespace mcmc {
 
+SamplerThread::SamplerThread() : thread_(&SamplerThread::Loop, this) {}
+
+SamplerThread::~SamplerThread() {
+  {
+    std::unique_lock<std::mutex> lock(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  thread_.join();
+}
+
+void SamplerThread::Loop() {
+  std::unique_lock<std::mutex> lock(mu_);
+  for (;;) {
+    cv_.wait(lock, [this] { return has_task_ || stop_; });
+    if (has_task_) {
+      std::function<Float()> task = std::move(task_);
+      has_task_ = false;
+      lock.unlock();
+      Float r = 0;
+      std::exception_ptr err;
+      try {
+        r = task();
+      } catch (...) {
+        err = std::current_exception();
+      }
+      lock.lock();
+      result_ = r;
+      error_ = err;
+      done_ = true;
+      cv_.notify_all();
+    } else if (stop_) {
+      return;
+    }
+  }
+}
+
+void SamplerThread::Launch(std::function<Float()> task) {
+  wait();
+  {
+    std::unique_lock<std::mutex> lock(mu_);
+    task_ = std::move(task);
+    has_task_ = true;
+    done_ = false;
+    valid_ = true;
+  }
+  cv_.notify_all();
+}
+
+void SamplerThread::wait() {
+  if (!valid_) return;
+  std::unique_lock<std::mutex> lock(mu_);
+  cv_.wait(lock, [this] { return done_; });
+}
+
+Float SamplerThread::get() {
+  if (!valid_) throw BackendError("SamplerThread::get() without a launched task");
+  wait();
+  valid_ = false;
+  if (error_) {
+    std::exception_ptr e = error_;
+    error_ = nullptr;
+    std::rethrow_exception(e);
+  }
+  return result_;
+}
+
+void SamplerThread::Reset() {
+  wait();
+  valid_ = false;
+  error_ = nullptr;
+}
+
 namespace {
 typedef Float (*SamplerFn)(const Config&, std::vector<Edge>*, unsigned int*);
 SamplerFn PickSampler(SampleStrategy s) {
@@ -54,7 +127,8 @@ Learner::Learner(const Config& cfg, clcuda::Queue queue)
       samples_{Sample(cfg_, queue_), Sample(cfg_, queue_)},
       pendingWeight_{0, 0},
       pendingValid_{false, false},
-      phase_(0) {
+      phase_(0),
+      betaMirror_(nullptr) {
   // phi lives in a Buffer of its own in the reference; the store adopts that memory
   AmmsbCheck(ammsb_store_bind_phi(pi_->Get(), phi_.data()));
   // theta ~ Gamma(eta0, eta1) on the host, fixed seed; beta = theta row-normalised
@@ -92,8 +166,7 @@ Float Learner::DoSample(Sample* sample) {
 }
 
 const Sample& Learner::PeekNextSample() {
-  if (!futures_[phase_].valid() && !pendingValid_[phase_])
-    futures_[phase_] = std::async(std::launch::async, &Learner::DoSample, this, &samples_[phase_]);
+  LaunchSampler(phase_);
   if (!pendingValid_[phase_]) {
     pendingWeight_[phase_] = futures_[phase_].get();
     pendingValid_[phase_] = true;
@@ -108,10 +181,15 @@ Float Learner::HeldoutPerplexity() {
   return std::exp(avg);
 }
 
+void Learner::LaunchSampler(int buffer) {
+  if (futures_[buffer].valid() || pendingValid_[buffer]) return;  // already drawn / being drawn
+  Sample* sample = &samples_[buffer];
+  futures_[buffer].Launch([this, sample] { return DoSample(sample); });
+}
+
 void Learner::Run(uint32_t max_iters, sig_atomic_t* signaled) {
   const auto t1 = high_resolution_clock::now();
-  if (!futures_[phase_].valid() && !pendingValid_[phase_])
-    futures_[phase_] = std::async(std::launch::async, &Learner::DoSample, this, &samples_[phase_]);
+  LaunchSampler(phase_);
   for (uint64_t i = 0; i < max_iters && (signaled == nullptr || !*signaled); ++i, ++stepCount_) {
     const auto ts = high_resolution_clock::now();
     Float weight;
@@ -122,16 +200,25 @@ void Learner::Run(uint32_t max_iters, sig_atomic_t* signaled) {
       weight = futures_[phase_].get();
     }
     // kernels of iteration t still read samples_[phase_]; the other buffer is free
-    futures_[1 - phase_] = std::async(std::launch::async, &Learner::DoSample, this, &samples_[1 - phase_]);
+    // (reference learner.cc:228: mini-batch t+1 is drawn while t is processed)
+    LaunchSampler(1 - phase_);
     samplingTime_ += duration_cast<nanoseconds>(high_resolution_clock::now() - ts).count();
 
     Sample& s = samples_[phase_];
     phiUpdater_(s.dev_nodes, s.neighbor_sampler.GetData(), static_cast<uint32_t>(s.nodes_vec.size()));
     betaUpdater_(&s.dev_edges, static_cast<uint32_t>(s.edges.size()), weight);
     edgesProcessed_ += s.edges.size();
+    if (betaMirror_ != nullptr) beta_.ReadAsync(queue_, 2 * cfg_.K, betaMirror_);
     // the sampler thread reuses this buffer two iterations from now; drain before flipping
     queue_.Finish();
+    const int consumed = phase_;
     phase_ = 1 - phase_;
+    // The two Samples draw from independent seeds and RNG pools and sampling never reads
+    // the model, so mini-batch t+2 can be drawn into the buffer that has just been consumed
+    // while t+1 is still being drawn: same mini-batches, two sampler threads in flight.
+    // Only when iteration t+2 belongs to this Run() call, so that a caller (and Serialize)
+    // always finds the reference's state on return: exactly one mini-batch in flight.
+    if (i + 2 < max_iters && (signaled == nullptr || !*signaled)) LaunchSampler(consumed);
   }
   time_ += duration_cast<nanoseconds>(high_resolution_clock::now() - t1).count();
 }
@@ -159,6 +246,10 @@ void Learner::PrintStats() {
 // beta updater, perplexity, LearnerProperties, sample 0, sample 1.
 bool Learner::Serialize(std::ostream* out) {
   PeekNextSample();  // drain the in-flight sampler so its state is final
+  if (futures_[1 - phase_].valid()) {  // only after a Run() cut short by `signaled`
+    pendingWeight_[1 - phase_] = futures_[1 - phase_].get();
+    pendingValid_[1 - phase_] = true;
+  }
   LearnerProperties props;
   props.stepCount = stepCount_;
   props.time = time_;
@@ -184,8 +275,8 @@ bool Learner::Parse(std::istream* in) {
   samplingTime_ = props.samplingTime;
   phase_ = props.phase;
   if (!(samples_[0].Parse(in) && samples_[1].Parse(in))) return false;
-  futures_[0] = std::future<Float>();
-  futures_[1] = std::future<Float>();
+  futures_[0].Reset();
+  futures_[1].Reset();
   pendingValid_[0] = pendingValid_[1] = false;
   pendingWeight_[phase_] = static_cast<Float>(props.weight);
   pendingValid_[phase_] = true;

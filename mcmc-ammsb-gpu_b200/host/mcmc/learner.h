@@ -9,7 +9,11 @@
 #include <signal.h>
 
 #include <atomic>
-#include <future>
+#include <condition_variable>
+#include <exception>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <ostream>
 
 #include "mcmc/beta.h"
@@ -19,6 +23,31 @@
 #include "mcmc/phi.h"
 
 namespace mcmc {
+
+// One persistent host thread per Sample buffer, with the interface of the std::future the
+// reference gets from std::async (learner.cc:216-229): Launch() = std::async, get()/wait()/
+// valid() as std::future.  Persistent so that the thread-local sampling arena and the CUDA
+// context binding are paid once, not per iteration.
+class SamplerThread {
+ public:
+  SamplerThread();
+  ~SamplerThread();
+  void Launch(std::function<Float()> task);
+  bool valid() const { return valid_; }
+  void wait();
+  Float get();          // waits, rethrows a failure of the task, invalidates
+  void Reset();         // wait and discard
+
+ private:
+  void Loop();
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::function<Float()> task_;
+  bool has_task_ = false, done_ = false, stop_ = false, valid_ = false;
+  Float result_ = 0;
+  std::exception_ptr error_;
+  std::thread thread_;
+};
 
 class Learner {
  public:
@@ -42,12 +71,16 @@ class Learner {
   uint32_t StepCount() const { return stepCount_; }
   uint64_t EdgesProcessed() const { return edgesProcessed_; }
   uint64_t BytesH2D() const { return h2dBytes_; }  // mini-batch edges + nodes copied to the device so far
+  // when set (pinned host memory, 2K floats), every iteration ends with a device->host copy
+  // of beta into it: the per-iteration result a monitoring caller reads
+  void MirrorBetaTo(Float* pinned_host) { betaMirror_ = pinned_host; }
   // the mini-batch the next iteration will consume (joins the sampler thread)
   const Sample& PeekNextSample();
   Float PeekNextWeight() { PeekNextSample(); return pendingWeight_[phase_]; }
 
  private:
   Float SampleMiniBatch(std::vector<Edge>* edges, unsigned int* seed);
+  void LaunchSampler(int buffer);
   Float DoSample(Sample* sample);
 
   const Config& cfg_;
@@ -73,10 +106,11 @@ class Learner {
   uint64_t edgesProcessed_;
   std::atomic<uint64_t> h2dBytes_;
   Sample samples_[2];
-  std::future<Float> futures_[2];
+  SamplerThread futures_[2];
   Float pendingWeight_[2];
   bool pendingValid_[2];
   int phase_;
+  Float* betaMirror_;
 };
 
 }  // namespace mcmc

@@ -11,9 +11,71 @@
 namespace mcmc {
 
 namespace {
+
+// Bump allocator for the short-lived hash sets of one mini-batch.  The allocator of a
+// std::unordered_set changes neither its bucket-count sequence nor its iteration order (the
+// output contract of the strategies); it only removes a malloc/free pair per element and keeps
+// the nodes contiguous.  Memory is recycled per thread when the last set of a scope dies.
+class Arena {
+ public:
+  void* Allocate(size_t bytes) {
+    bytes = (bytes + 15) & ~size_t(15);
+    if (blocks_.empty() || used_ + bytes > blocks_[cur_].size()) NextBlock(bytes);
+    void* p = blocks_[cur_].data() + used_;
+    used_ += bytes;
+    return p;
+  }
+  void Enter() { ++live_; }
+  void Leave() {
+    if (--live_ == 0) {
+      cur_ = 0;
+      used_ = 0;
+    }
+  }
+
+ private:
+  void NextBlock(size_t bytes) {
+    while (!blocks_.empty() && cur_ + 1 < blocks_.size()) {
+      ++cur_;
+      used_ = 0;
+      if (bytes <= blocks_[cur_].size()) return;
+    }
+    blocks_.emplace_back(std::max<size_t>(bytes, size_t(1) << 20));
+    cur_ = blocks_.size() - 1;
+    used_ = 0;
+  }
+  std::vector<std::vector<char>> blocks_;
+  size_t cur_ = 0, used_ = 0;
+  int live_ = 0;
+};
+thread_local Arena t_arena;
+
+struct ArenaScope {
+  ArenaScope() { t_arena.Enter(); }
+  ~ArenaScope() { t_arena.Leave(); }
+};
+
+template <class T>
+struct ArenaAlloc {
+  typedef T value_type;
+  ArenaAlloc() {}
+  template <class U>
+  ArenaAlloc(const ArenaAlloc<U>&) {}
+  T* allocate(size_t n) { return static_cast<T*>(t_arena.Allocate(n * sizeof(T))); }
+  void deallocate(T*, size_t) {}
+  template <class U>
+  bool operator==(const ArenaAlloc<U>&) const { return true; }
+  template <class U>
+  bool operator!=(const ArenaAlloc<U>&) const { return false; }
+};
+// same hash, equality and growth policy as the reference's std::unordered_set<T>
+template <class T>
+using HashSet = std::unordered_set<T, std::hash<T>, std::equal_to<T>, ArenaAlloc<T>>;
+
 inline Edge Canonical(Vertex u, Vertex v) { return MakeEdge(std::min(u, v), std::max(u, v)); }
 inline Vertex DrawVertex(const Config& cfg, unsigned int* seed) { return rand_r(seed) % cfg.N; }
-inline void Emit(const std::unordered_set<Edge>& picked, std::vector<Edge>* edges) {
+template <class SetT>
+inline void Emit(const SetT& picked, std::vector<Edge>* edges) {
   edges->insert(edges->begin(), picked.begin(), picked.end());  // std::unordered_set order is the contract
 }
 bool SameNoCase(const std::string& a, const char* b) {
@@ -36,8 +98,9 @@ uint64_t MaxMiniBatchEdges(const Config& cfg) {
 // Pick unseen vertices u until one has training neighbors; the mini-batch is every training
 // edge of u.  Scale N.
 Float sampleNodeLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed) {
-  std::unordered_set<Vertex> tried;
-  std::unordered_set<Edge> picked;
+  ArenaScope scope;
+  HashSet<Vertex> tried;
+  HashSet<Edge> picked;
   while (picked.empty()) {
     const Vertex u = DrawVertex(cfg, seed);
     if (!tried.insert(u).second) continue;
@@ -50,16 +113,38 @@ Float sampleNodeLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* 
 // One vertex u; draw v until (u,v) is in neither the held-out nor the training set, m
 // distinct pairs.  (u == v is not excluded and no v is ever blacklisted -- kept as is.)
 // Scale 2E/m.
+//
+// The reference consumes one rand_r draw per candidate whatever its fate, so the candidate
+// stream does not depend on the membership answers: candidates are drawn a block at a time,
+// their cuckoo bins hashed and prefetched together, and then examined in draw order.  The
+// seed is rewound to the draw that completed the mini-batch, so the stream position -- and
+// with it every later mini-batch -- is the reference's.
 Float sampleNodeNonLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed) {
-  std::unordered_set<Edge> picked;
+  ArenaScope scope;
+  HashSet<Edge> picked;
   const Vertex u = DrawVertex(cfg, seed);
-  while (picked.size() < cfg.mini_batch_size) {
-    Edge e;
-    do {
-      e = Canonical(u, DrawVertex(cfg, seed));
-    } while (cfg.heldout->Has(e) || cfg.training->Has(e));
-    picked.insert(e);
+  const size_t m = cfg.mini_batch_size;
+  const int kBlock = 32;
+  Edge cand[kBlock];
+  unsigned int after[kBlock];
+  size_t hb[kBlock][2], tb[kBlock][2];
+  unsigned int s = *seed;
+  while (picked.size() < m) {
+    const int take = static_cast<int>(std::min<size_t>(kBlock, m - picked.size()));
+    for (int i = 0; i < take; ++i) {
+      cand[i] = Canonical(u, rand_r(&s) % cfg.N);
+      after[i] = s;
+      cfg.heldout->Locate(cand[i], hb[i]);
+      cfg.training->Locate(cand[i], tb[i]);
+    }
+    // at most `take` insertions can happen, so the block never overshoots m mid-way
+    for (int i = 0; i < take; ++i) {
+      if (cfg.heldout->HasAt(cand[i], hb[i]) || cfg.training->HasAt(cand[i], tb[i])) continue;
+      picked.insert(cand[i]);
+    }
+    s = after[take - 1];
   }
+  *seed = s;
   Emit(picked, edges);
   return (2 * cfg.E) / static_cast<Float>(cfg.mini_batch_size);
 }
@@ -70,9 +155,10 @@ Float sampleNode(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed
 
 // Breadth-first over training links from random roots until m edges.  Scale E/m.
 Float sampleBreadthFirstLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed) {
-  std::unordered_set<Vertex> visited;
+  ArenaScope scope;
+  HashSet<Vertex> visited;
   std::queue<Vertex> frontier;
-  std::unordered_set<Edge> picked;
+  HashSet<Edge> picked;
   while (picked.size() < cfg.mini_batch_size) {
     if (frontier.empty()) {
       Vertex root;
@@ -97,9 +183,10 @@ Float sampleBreadthFirstLink(const Config& cfg, std::vector<Edge>* edges, unsign
 // Breadth-first where each visited vertex contributes up to 32 random non-neighbors.
 // Scale (N(N-1)/2 - E)/m.
 Float sampleBreadthFirstNonLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed) {
-  std::unordered_set<Vertex> visited;
+  ArenaScope scope;
+  HashSet<Vertex> visited;
   std::queue<Vertex> frontier;
-  std::unordered_set<Edge> picked;
+  HashSet<Edge> picked;
   while (picked.size() < cfg.mini_batch_size) {
     if (frontier.empty()) {
       Vertex root;
@@ -130,7 +217,8 @@ Float sampleBreadthFirst(const Config& cfg, std::vector<Edge>* edges, unsigned i
 }
 
 void ExtractNodesFromMiniBatch(const std::vector<Edge>& edges, std::vector<Vertex>* nodes_vec) {
-  std::unordered_set<Vertex> nodes;
+  ArenaScope scope;
+  HashSet<Vertex> nodes;
   for (Edge e : edges) {
     nodes.insert(static_cast<Vertex>(e >> 32));
     nodes.insert(static_cast<Vertex>(e & 0xffffffffu));

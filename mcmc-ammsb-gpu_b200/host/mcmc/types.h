@@ -136,6 +136,9 @@ class Buffer {
   void Read(const Queue& q, size_t n, std::vector<T>& host, size_t offset = 0) const {
     Read(q, n, host.data(), offset);
   }
+  void ReadAsync(const Queue& q, size_t n, T* host, size_t offset = 0) const {
+    AmmsbCheck(ammsb_d2h_async(q(), host, data() + offset, n * sizeof(T)));
+  }
   void Write(const Queue& q, size_t n, const T* host, size_t offset = 0) {
     AmmsbCheck(ammsb_h2d(q(), data() + offset, host, n * sizeof(T)));
   }

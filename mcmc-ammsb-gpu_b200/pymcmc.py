@@ -54,6 +54,7 @@ def lib():
         L.mcmc_learner_print_stats.argtypes = [C.c_void_p]
         L.mcmc_learner_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.mcmc_learner_edges_processed.restype = C.c_uint64
+        L.mcmc_learner_mirror_beta.argtypes = [C.c_void_p, C.c_void_p]
         L.mcmc_learner_h2d_bytes.restype = C.c_uint64
         L.mcmc_learner_h2d_bytes.argtypes = [C.c_void_p]
         L.mcmc_learner_edges_processed.argtypes = [C.c_void_p]
@@ -195,6 +196,10 @@ class Learner:
         beta = np.empty(2 * K, np.float32) if out is None else out
         _ck(lib().mcmc_learner_read(self.h, None, None, _p(beta), None, 0))
         return beta
+
+    def mirror_beta(self, pinned_ptr):
+        """every iteration of run() ends with a D2H copy of beta[2K] into this pinned buffer"""
+        _ck(lib().mcmc_learner_mirror_beta(self.h, C.c_void_p(pinned_ptr)))
 
     def h2d_bytes(self):
         return int(lib().mcmc_learner_h2d_bytes(self.h))
