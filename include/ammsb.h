@@ -64,6 +64,12 @@ typedef struct {
   uint32_t disable_noise; /* PHI_RANDN -> literal 1 (phi.cc:673-677)           */
   uint32_t strict;        /* 1: IEEE, reference-association kernel (slow);
                              0: production kernel (HBM-roofline path)          */
+  /* multi-GPU: this call processes only the mini-batch slots whose RNG unit u (the
+   * reference work-group / work-item that owns the slot, phi.cc:740-747) satisfies
+   * u % part_count == part_index.  part_count 0 or 1 = every slot.  The ownership of
+   * RNG state by rank is therefore static and results do not depend on the GPU count. */
+  uint32_t part_index;
+  uint32_t part_count;
 } ammsb_phi_opts;
 
 const char* ammsb_last_error(void);
@@ -165,6 +171,11 @@ int ammsb_update_phi(ammsb_ctx* ctx, const ammsb_params* p, const ammsb_phi_opts
 int ammsb_update_pi(ammsb_ctx* ctx, uint32_t K, ammsb_store* store,
                     const float* d_phi_vec, const float* d_phi_sum,
                     const uint32_t* d_nodes, uint32_t V);
+/* the slots of one rank only (same partition rule as ammsb_update_phi; rows owned by
+ * another GPU are written with NVLink peer stores) */
+int ammsb_update_pi_part(ammsb_ctx* ctx, uint32_t K, ammsb_store* store,
+                         const float* d_phi_vec, const float* d_phi_sum,
+                         const uint32_t* d_nodes, uint32_t V, const ammsb_phi_opts* opts);
 
 /* ---- BetaUpdater::operator()(edges, E_mb, scale) (beta.h:25, beta.cc:334-384).
  *      ammsb_beta_grads = sum_theta + calculate_grads_partial + sum_grads;

@@ -20,6 +20,7 @@ struct PhiArgs {
   uint32_t V, n, K;
   uint32_t units;      // reference work-items (THREAD) or groups (WG) that own RNG state
   uint32_t mode, wg;   // reference launch being reproduced
+  uint32_t part_index, part_count;  // this rank's share of the units (unit % count == index)
   uint32_t disable_noise;
   float eps_t, alpha, epsilon, Nn;
   ulonglong2* pool;
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(128) k_update_phi_strict(const __grid_constant
   float* s_probs = s_grads + K;
   float* s_aux = s_probs + K;  // max(wg,1)
   const uint32_t vw = a.mode == AMMSB_MODE_THREAD ? 1u : a.wg;
-  for (uint32_t unit = blockIdx.x; unit < a.units && unit < a.V; unit += gridDim.x) {
+  for (uint32_t unit = a.part_index + a.part_count * blockIdx.x; unit < a.units && unit < a.V;
+       unit += a.part_count * gridDim.x) {
     for (uint32_t slot = unit; slot < a.V; slot += a.units) {
       const uint32_t node = a.nodes[slot];
       const float* pi = store_row(a.sv, node);
@@ -166,7 +168,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 
   const uint32_t gwarp = blockIdx.x * WARPS + wib;
   const uint32_t total_warps = gridDim.x * WARPS;
-  for (uint32_t unit = gwarp; unit < a.units && unit < a.V; unit += total_warps) {
+  for (uint32_t unit = a.part_index + a.part_count * gwarp; unit < a.units && unit < a.V;
+       unit += a.part_count * total_warps) {
     Rng st;
     if (fast_noise && !a.disable_noise) st = rng_load(a.pool, (uint64_t)unit * 32 + lane);
     for (uint32_t slot = unit; slot < a.V; slot += a.units) {
@@ -307,6 +310,12 @@ __global__ void __launch_bounds__(WARPS * 32)
   }
 }
 
+// number of units (and so of concurrently useful warps / CTAs) this rank owns
+static uint32_t my_units(const PhiArgs& a) {
+  const uint32_t active = a.units < a.V ? a.units : a.V;
+  return active > a.part_index ? (active - a.part_index + a.part_count - 1) / a.part_count : 0;
+}
+
 template <int KPL, int STAGES, int WARPS>
 static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   const size_t smem = (size_t)WARPS * (STAGES + 1) * a.K * 4 + (size_t)WARPS * (STAGES + 1) * 8;
@@ -317,13 +326,24 @@ static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   int occ = 0;
   AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
   AMMSB_REQUIRE(occ > 0, "update_phi: kernel does not fit on an SM");
-  const uint32_t active = a.units < a.V ? a.units : a.V;
+  const uint32_t active = my_units(a);
+  if (active == 0) return 0;
   uint32_t blocks = (active + WARPS - 1) / WARPS;
   const uint32_t resident = (uint32_t)occ * c->sm_count;
   if (blocks > resident) blocks = resident;  // persistent: one wave, warps stride over units
   kern<<<blocks, WARPS * 32, smem, c->stream>>>(a);
   AMMSB_LAUNCH_CHECK();
   return 0;
+}
+
+// work-items (THREAD) or work-groups (WG) of the reference launch, phi.cc:740-747
+static uint32_t phi_units(uint32_t mode, uint32_t wg, uint32_t V) {
+  if (mode == AMMSB_MODE_THREAD) {
+    uint32_t g = V / wg + (V % wg ? 1 : 0);
+    if (g > 65535u) g = 65535u;
+    return g * wg;
+  }
+  return V < 65535u ? V : 65535u;
 }
 
 extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb_phi_opts* o,
@@ -348,15 +368,15 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
   a.mode = o->mode;
   a.wg = o->wg;
   a.disable_noise = o->disable_noise;
+  a.part_count = o->part_count ? o->part_count : 1;
+  a.part_index = o->part_index;
+  AMMSB_REQUIRE(a.part_index < a.part_count, "part_index out of range");
   // phi.cc:740-747 launch geometry
   uint64_t states;
+  a.units = phi_units(o->mode, o->wg, V);
   if (o->mode == AMMSB_MODE_THREAD) {
-    uint32_t g = V / o->wg + (V % o->wg ? 1 : 0);
-    if (g > 65535u) g = 65535u;
-    a.units = g * o->wg;
     states = a.units < V ? a.units : V;
   } else {
-    a.units = V < 65535u ? V : 65535u;
     states = (uint64_t)a.units * o->wg;
   }
   AMMSB_REQUIRE(o->disable_noise || (pool && pool->n >= states),
@@ -383,7 +403,8 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
   AMMSB_REQUIRE(smem <= c->smem_optin, "K too large for the strict update_phi kernel");
   AMMSB_CHECK_CUDA(cudaFuncSetAttribute(k_update_phi_strict,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  uint32_t blocks = a.units < V ? a.units : V;
+  uint32_t blocks = my_units(a);
+  if (blocks == 0) return 0;
   const uint32_t cap = (uint32_t)c->sm_count * 8;
   if (blocks > cap) blocks = cap;
   k_update_phi_strict<<<blocks, 128, smem, c->stream>>>(a);
@@ -398,12 +419,14 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
 // the launch mode; the division is IEEE.
 __global__ void __launch_bounds__(256)
     k_update_pi(StoreView sv, const float* __restrict__ phi_vec, const float* __restrict__ phi_sum,
-                const uint32_t* __restrict__ nodes, uint32_t V) {
+                const uint32_t* __restrict__ nodes, uint32_t V, uint32_t units, uint32_t part_index,
+                uint32_t part_count) {
   const uint32_t lane = threadIdx.x & 31;
   uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t K = sv.K;
   for (; warp < V; warp += nwarps) {
+    if (part_count > 1 && (warp % units) % part_count != part_index) continue;  // another rank's slot
     const uint32_t node = __ldg(&nodes[warp]);
     const float* src = phi_vec + (size_t)warp * K;
     float* dst = store_row(sv, node);
@@ -431,15 +454,32 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-extern "C" int ammsb_update_pi(ammsb_ctx* c, uint32_t K, ammsb_store* store, const float* d_phi_vec,
-                               const float* d_phi_sum, const uint32_t* d_nodes, uint32_t V) {
+static int update_pi_impl(ammsb_ctx* c, uint32_t K, ammsb_store* store, const float* d_phi_vec,
+                          const float* d_phi_sum, const uint32_t* d_nodes, uint32_t V, uint32_t units,
+                          uint32_t part_index, uint32_t part_count) {
   AMMSB_REQUIRE(V > 0, "mini-batch nodes size = 0!");
   AMMSB_REQUIRE(K == store->K, "K does not match the store");
   AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
   uint32_t blocks = (V + 7) / 8;
   const uint32_t cap = (uint32_t)c->sm_count * 8;
   if (blocks > cap) blocks = cap;
-  k_update_pi<<<blocks, 256, 0, c->stream>>>(store->view(), d_phi_vec, d_phi_sum, d_nodes, V);
+  k_update_pi<<<blocks, 256, 0, c->stream>>>(store->view(), d_phi_vec, d_phi_sum, d_nodes, V, units, part_index,
+                                             part_count);
   AMMSB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ammsb_update_pi(ammsb_ctx* c, uint32_t K, ammsb_store* store, const float* d_phi_vec,
+                               const float* d_phi_sum, const uint32_t* d_nodes, uint32_t V) {
+  return update_pi_impl(c, K, store, d_phi_vec, d_phi_sum, d_nodes, V, V ? V : 1, 0, 1);
+}
+
+extern "C" int ammsb_update_pi_part(ammsb_ctx* c, uint32_t K, ammsb_store* store, const float* d_phi_vec,
+                                    const float* d_phi_sum, const uint32_t* d_nodes, uint32_t V,
+                                    const ammsb_phi_opts* o) {
+  AMMSB_REQUIRE(o->wg > 0, "work-group size must be > 0");
+  const uint32_t pc = o->part_count ? o->part_count : 1;
+  AMMSB_REQUIRE(o->part_index < pc, "part_index out of range");
+  return update_pi_impl(c, K, store, d_phi_vec, d_phi_sum, d_nodes, V, phi_units(o->mode, o->wg, V ? V : 1),
+                        o->part_index, pc);
 }

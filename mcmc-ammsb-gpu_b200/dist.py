@@ -1,0 +1,369 @@
+"""dist.py -- node-partitioned multi-GPU driver of the SG-MCMC iteration (one process per GPU).
+
+The reference is single-device; its only scale mechanism is RowPartitionedMatrix
+(partitioned-alloc.h:14-141).  Here pi/phi are node-partitioned over the G GPUs of one box
+(shard s owns rows [s*ceil(N/G), (s+1)*ceil(N/G)) -- the reference's row -> (block, offset)
+rule with one block per GPU) and every rank maps every peer shard through CUDA IPC, so the
+kernels gather neighbor rows with NVLink peer loads.  torch.distributed (NCCL) is plumbing:
+handle exchange, the [2K] beta-gradient all-reduce, the 4 perplexity sums, and the ordering
+points between phases.
+
+Work split (all static functions of (V, E_mb, H, G), so every rank computes the same plan):
+  update_phi / update_pi  slot i belongs to rank (unit(i) % G), unit(i) = i % min(V, 65535) -- the
+                          reference work-group that owns the slot and its Langevin RNG state
+                          (phi.cc:740-747).  RNG-state ownership is therefore fixed per rank and
+                          the result does not depend on G.
+  beta gradient           mini-batch edges split in G contiguous chunks; partial [2K] gradients
+                          are summed by an all-reduce, then every rank runs the same
+                          update_theta on its replica (same RNG pool) -> replicas stay identical.
+  perplexity              held-out pairs split in G contiguous chunks; 4 sums all-reduced.
+  mini-batch / neighbor sampling  replicated: every rank draws the same mini-batch (same seeds)
+                          and runs the (cheap, integer) neighbor sampler for all slots.
+"""
+import ctypes as C
+import json
+import os
+import queue
+import threading
+import time
+
+import numpy as np
+
+MAX_GROUPS = 65535  # types.cc:537
+
+
+# ------------------------------------------------------------------ the plan --
+def phi_units(V, mode_wg=True, wg=32):
+    """work-groups (WG modes) / work-items (THREAD) of the reference launch, phi.cc:740-747"""
+    if mode_wg:
+        return min(V, MAX_GROUPS)
+    g = min((V + wg - 1) // wg, MAX_GROUPS)
+    return g * wg
+
+
+def slot_ranks(V, world, mode_wg=True, wg=32):
+    """rank that processes each mini-batch slot"""
+    units = phi_units(V, mode_wg, wg)
+    return (np.arange(V, dtype=np.int64) % units) % world
+
+
+def chunk(total, rank, world):
+    """contiguous, balanced [lo, hi) split of `total` work units"""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def exchange(obj, world, group=None):
+    """all-gather of a small python object (IPC handles)"""
+    import torch.distributed as dist
+    out = [None] * world
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+class _Buf:
+    """a device pointer seen as a pyammsb buffer (torch tensor storage or a sub-range)"""
+
+    def __init__(self, ptr, nbytes=0, keep=None):
+        self.ptr, self.nbytes, self.keep = C.c_void_p(ptr), nbytes, keep
+
+
+def tbuf(t):
+    return _Buf(t.data_ptr(), t.numel() * t.element_size(), t)
+
+
+# ---------------------------------------------------------------- the driver --
+class ShardedLearner:
+    """Learner::Run / HeldoutPerplexity over G node-partitioned GPUs.  `cfg` is a pymcmc.Config
+    whose mini_batch_size is the GLOBAL mini-batch."""
+
+    STREAMS = 4  # independent host sampler streams (the reference has 2: its two Samples)
+
+    def __init__(self, cfg, rank, world, local_rank, seed=12345, prefetch=True):
+        import torch
+        import torch.distributed as dist
+        import pyammsb as A
+        import pymcmc
+        self.torch, self.dist, self.A = torch, dist, A
+        self.cfg, self.rank, self.world = cfg, rank, world
+        self.p = cfg.params()
+        self.N, self.K, self.n = int(self.p.N), int(self.p.K), int(self.p.num_neighbors)
+        self.stream = torch.cuda.current_stream()
+        self.ctx = A.Ctx(local_rank)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        dev = torch.device("cuda", local_rank)
+        # ---- node-partitioned store, peers attached by IPC handle ----
+        self.store = A.Store(self.ctx, self.N, self.K, world, rank)
+        if world > 1:
+            handles = exchange(self.store.export_handles(), world)
+            for s, (hp, hf) in enumerate(handles):
+                if s != rank:
+                    self.store.attach(s, hp, hf)
+        self.store.init_pi(float(self.p.eta0), float(self.p.eta1))
+        # ---- replicated: edge sets, theta/beta, RNG pools ----
+        t_tab, t_bins, t_prime = cfg.set_table(0)
+        h_tab, h_bins, h_prime = cfg.set_table(1)
+        self.train = A.DevSet(self.ctx, t_tab, t_bins, t_prime)
+        self.heldout = A.DevSet(self.ctx, h_tab, h_bins, h_prime)
+        theta = pymcmc.init_theta_host(self.K, float(self.p.eta0), float(self.p.eta1))
+        th2 = theta.reshape(self.K, 2)
+        beta = (th2 / (th2[:, :1] + th2[:, 1:])).astype(np.float32).ravel()
+        self.theta = torch.from_numpy(theta).to(dev)
+        self.beta = torch.from_numpy(beta).to(dev)
+        self.Vmax, self.Emax = cfg.max_nodes(), cfg.max_edges()
+        n = self.n
+        self.npools = [A.Rng(self.ctx, self.Vmax * 2 * n, 56, 57) for _ in range(self.STREAMS)]
+        self.ppool = A.Rng(self.ctx, self.Vmax * 32, 42, 43)
+        self.bpool = A.Rng(self.ctx, self.K, 44, 45)
+        # ---- mini-batch buffers ----
+        self.d_nodes = torch.empty(self.Vmax, dtype=torch.int32, device=dev)
+        self.d_edges = torch.empty(self.Emax, dtype=torch.int64, device=dev)
+        self.d_nb = torch.empty(self.Vmax * n, dtype=torch.int32, device=dev)
+        self.d_vec = torch.empty(self.Vmax * self.K, dtype=torch.float32, device=dev)
+        self.d_sum = torch.empty(self.Vmax, dtype=torch.float32, device=dev)
+        self.d_tsum = torch.empty(self.K, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(2 * self.K, dtype=torch.float32, device=dev)
+        self.ws = torch.empty(self.ctx.beta_workspace_bytes(self.K), dtype=torch.uint8, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.h_nodes = torch.empty(self.Vmax, dtype=torch.int32).pin_memory()
+        self.h_edges = torch.empty(self.Emax, dtype=torch.int64).pin_memory()
+        self.h_beta = torch.empty(2 * self.K, dtype=torch.float32).pin_memory()
+        self.opts = A.PhiOpts(A.MODE_WG, 32, 0, 0, rank, world)
+        # ---- held-out pairs: this rank's chunk ----
+        he = cfg.edges()[1]
+        self.H = len(he)
+        lo, hi = chunk(self.H, rank, world)
+        self.H_local = hi - lo
+        self.d_hedges = torch.from_numpy(he[lo:hi].astype(np.int64)).to(dev) if hi > lo else \
+            torch.zeros(1, dtype=torch.int64, device=dev)
+        self.d_ppx = torch.zeros(max(self.H_local, 1), dtype=torch.float32, device=dev)
+        self.pws = torch.empty(self.ctx.perplexity_workspace_bytes(), dtype=torch.uint8, device=dev)
+        self.sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.ppx_calls = 0
+        self.step_count = 0
+        self.edges_processed = 0
+        self.h2d_bytes = 0
+        # ---- host sampler: STREAMS seeds, mini-batch t comes from stream t % STREAMS ----
+        self.seeds = [C.c_uint(seed + 7919 * i) for i in range(self.STREAMS)]
+        self.drawn = 0
+        self.q = None
+        if prefetch:
+            self.q = [queue.Queue(maxsize=2) for _ in range(self.STREAMS)]
+            self.threads = [threading.Thread(target=self._producer, args=(i,), daemon=True)
+                            for i in range(self.STREAMS)]
+            for t in self.threads:
+                t.start()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------- sampling ----
+    def _producer(self, i):
+        while True:
+            self.q[i].put(self.cfg.sample("Node", self.seeds[i]))  # ctypes call releases the GIL
+
+    def next_minibatch(self):
+        """(weight, edges, nodes) of iteration t from sampler stream t % STREAMS"""
+        i = self.drawn % self.STREAMS
+        self.drawn += 1
+        if self.q is not None:
+            return self.q[i].get()
+        return self.cfg.sample("Node", self.seeds[i])
+
+    # --------------------------------------------------------- iteration ----
+    def barrier(self):
+        if self.world > 1:
+            self.dist.all_reduce(self.flag)
+
+    def device_step(self, d_nodes, d_edges, V, E_mb, weight, pool_index, phi_events=None):
+        """one iteration on device-resident mini-batch buffers (pyammsb-style buffers)"""
+        ctx, p, K = self.ctx, self.p, self.K
+        self.step_count += 1
+        ctx.neighbor_sample(self.npools[pool_index], d_nodes, V, self.N, self.n, 32, tbuf(self.d_nb))
+        if phi_events is not None:
+            phi_events[0].record(self.stream)
+        ctx.update_phi(p, self.opts, tbuf(self.beta), self.store, self.train, d_nodes, tbuf(self.d_nb), V,
+                       self.step_count, self.ppool, tbuf(self.d_vec), tbuf(self.d_sum))
+        if phi_events is not None:
+            phi_events[1].record(self.stream)
+        self.barrier()  # every read of the old pi is done before any rank writes
+        ctx.update_pi_part(K, self.store, tbuf(self.d_vec), tbuf(self.d_sum), d_nodes, V, self.opts)
+        self.barrier()  # every write is visible before beta reads pi
+        lo, hi = chunk(E_mb, self.rank, self.world)
+        ctx.beta_grads(p, tbuf(self.theta), tbuf(self.beta), self.store, self.train,
+                       _Buf(d_edges.ptr.value + 8 * lo), hi - lo, tbuf(self.d_tsum), tbuf(self.grads), tbuf(self.ws))
+        if self.world > 1:
+            self.dist.all_reduce(self.grads)
+        ctx.update_theta(p, tbuf(self.theta), tbuf(self.beta), tbuf(self.grads), weight, self.step_count, self.bpool)
+        self.edges_processed += E_mb
+
+    def host_step(self):
+        """one iteration from a HOST mini-batch: sample, H2D, kernels, D2H of beta"""
+        torch = self.torch
+        weight, edges, nodes = self.next_minibatch()
+        V, E_mb = len(nodes), len(edges)
+        self.h_nodes[:V].copy_(torch.from_numpy(nodes.view(np.int32)))
+        self.h_edges[:E_mb].copy_(torch.from_numpy(edges.view(np.int64)))
+        self.d_nodes[:V].copy_(self.h_nodes[:V], non_blocking=True)
+        self.d_edges[:E_mb].copy_(self.h_edges[:E_mb], non_blocking=True)
+        self.h2d_bytes += 4 * V + 8 * E_mb
+        self.device_step(tbuf(self.d_nodes), tbuf(self.d_edges), V, E_mb, weight,
+                         (self.drawn - 1) % self.STREAMS)
+        self.h_beta.copy_(self.beta, non_blocking=True)
+        self.stream.synchronize()  # the pinned staging buffers are reused by the next step
+        return E_mb
+
+    def run(self, iters):
+        for _ in range(iters):
+            self.host_step()
+
+    def heldout_perplexity(self):
+        self.ppx_calls += 1
+        if self.H_local > 0:
+            self.ctx.perplexity_partial(self.p, self.store, tbuf(self.beta), self.heldout, tbuf(self.d_hedges),
+                                        self.H_local, tbuf(self.d_ppx), self.ppx_calls, tbuf(self.sums), tbuf(self.pws))
+        else:
+            self.sums.zero_()
+        if self.world > 1:
+            self.dist.all_reduce(self.sums)
+        s = self.sums.cpu().numpy()
+        avg = (s[0] + s[1]) / (s[2] + s[3]) if (s[2] + s[3]) != 0 else 0.0  # perplexity.cc:264-273
+        return float(np.exp(np.float32(-avg)))
+
+    # ------------------------------------------------------------- state ----
+    def read_local_pi(self):
+        return self.store.read_pi()
+
+    def read_beta(self):
+        return self.beta.cpu().numpy()
+
+
+# ------------------------------------------------------------------ bench ----
+def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_name, ClockSampler,
+                  cpu_reference):
+    """bench.py --gpus N (N > 1): weak scaling, mini-batch = N x m edges on the same graph."""
+    import torch
+    import torch.distributed as dist
+    import pyammsb as A
+    import pymcmc
+    import synth
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N, E, K, n = w["N"], w["E"], w["K"], w["n"]
+    m = w["m"] * world
+    t0 = time.time()
+    keys = synth.make_edges(N, E, 1)
+    cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=w["heldout_ratio"], strategy="Node")
+    cfg.set_graph(N, keys)
+    log("graph + split + sets: %.1fs" % (time.time() - t0))
+    lrn = ShardedLearner(cfg, rank, world, local_rank, prefetch=False)
+    stream = lrn.stream
+    ctx = lrn.ctx
+
+    # ---- value leg: pre-sampled mini-batches resident in HBM ----
+    total = args.warmup + args.steps
+    t0 = time.time()
+    batches = [lrn.next_minibatch() for _ in range(total)]
+    log("host sampler: %d mini-batches of up to %d edges in %.1fs" % (total, m, time.time() - t0))
+    e_off = np.cumsum([0] + [len(b[1]) for b in batches])
+    v_off = np.cumsum([0] + [len(b[2]) for b in batches])
+    d_edges_all = ctx.from_host(np.concatenate([b[1] for b in batches]))
+    d_nodes_all = ctx.from_host(np.concatenate([b[2] for b in batches]))
+
+    def step(i, ev=None):
+        wgt, edges, nodes = batches[i]
+        lrn.device_step(_Buf(d_nodes_all.ptr.value + 4 * int(v_off[i])), _Buf(d_edges_all.ptr.value + 8 * int(e_off[i])),
+                        len(nodes), len(edges), wgt, i % lrn.STREAMS, ev)
+
+    for i in range(args.warmup):
+        step(i)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = A.launch_count()
+    e_start.record(stream)
+    for k in range(args.steps):
+        step(args.warmup + k, evs[k])
+    e_stop.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches = A.launch_count() - launches0
+    t = torch.tensor([e_start.elapsed_time(e_stop), sum(a.elapsed_time(b) for a, b in evs)],
+                     dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+    dev_ms, phi_ms = float(t[0]), float(t[1])
+    clk = clocks.stop() if rank == 0 else None
+    timed = batches[args.warmup:]
+    edges_timed = int(sum(len(b[1]) for b in timed))
+    value = edges_timed / (dev_ms * 1e-3)
+    # NVLink roofline of update_phi: rows that cross the switch into this GPU
+    Vs = [len(b[2]) for b in timed]
+    remote_bytes = float(sum((V / world) * n * 4 * K * (world - 1) / world for V in Vs))
+    local_bytes = float(sum((V / world) * ((n + 2) * 4 * K + 68 * n + 8) for V in Vs))
+    nvlink_peak = 770.0  # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                            "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ideal_ms = max(remote_bytes / nvlink_peak, local_bytes / hbm_peak) / 1e6
+    roofline = {"bound": "nvlink", "kernel": "k_update_phi_fast (peer loads)", "unit": "GB/s",
+                "achieved": round(remote_bytes / (phi_ms * 1e-3) / 1e9, 1), "peak": nvlink_peak,
+                "frac": round(remote_bytes / (phi_ms * 1e-3) / 1e9 / nvlink_peak, 4),
+                "peak_source": "770 GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)",
+                "traffic": None, "inbound_remote_GB_per_gpu_per_step": round(remote_bytes / args.steps / 1e9, 4),
+                "hbm_side_GBps": round(local_bytes / (phi_ms * 1e-3) / 1e9, 1),
+                "ideal_ms_per_step": round(ideal_ms / args.steps, 4), "share_of_step": round(phi_ms / dev_ms, 4)}
+
+    # ---- perplexity (sharded) ----
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    ppx = lrn.heldout_perplexity()
+    torch.cuda.synchronize()
+    ppx_s = time.perf_counter() - t1
+
+    # ---- e2e leg: host mini-batches through the sharded driver ----
+    e2e = None
+    if not args.no_e2e:
+        l2 = ShardedLearner(cfg, rank, world, local_rank, prefetch=True)
+        for _ in range(args.warmup):
+            l2.host_step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        b0, e0 = l2.h2d_bytes, l2.edges_processed
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            l2.host_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt[0])
+        e2e = {"value": (l2.edges_processed - e0) / dt, "unit": UNIT,
+               "h2d_bytes_per_step": (l2.h2d_bytes - b0) / args.steps * world, "d2h_bytes_per_step": 8 * K * world,
+               "iterations_per_s": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
+               "api": "dist.ShardedLearner.host_step(): replicated host mini-batch sampler (prefetch threads), "
+                      "H2D of edges/nodes from pinned memory on every rank, sharded kernels + NCCL, D2H of beta"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(w, world),
+                       "parallelism": "pi/phi node-partitioned over %d GPUs (NVLink peer loads), beta gradient and "
+                                      "perplexity sums all-reduced (NCCL)" % world,
+                       "l2": "inputs larger than L2 (pi %.2f GB, %.2f GB of rows gathered per non-link step)"
+                             % (4.0 * N * K / 1e9, (m + 1) * (n + 2) * 4 * K / 1e9),
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "iterations_per_s": args.steps / (dev_ms * 1e-3), "perplexity_eval_s": ppx_s, "heldout_perplexity": ppx,
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

@@ -63,6 +63,8 @@ ammsb_phi_opts MakePhiOpts(const Config& cfg) {
   o.wg = cfg.phi_wg_size;
   o.disable_noise = cfg.phi_disable_noise ? 1 : 0;
   o.strict = cfg.phi_strict ? 1 : 0;
+  o.part_index = 0;  // single-GPU Learner: every slot
+  o.part_count = 1;
   return o;
 }
 

@@ -24,7 +24,7 @@ class Params(C.Structure):
 
 class PhiOpts(C.Structure):
     _fields_ = [("mode", C.c_uint32), ("wg", C.c_uint32), ("disable_noise", C.c_uint32),
-                ("strict", C.c_uint32)]
+                ("strict", C.c_uint32), ("part_index", C.c_uint32), ("part_count", C.c_uint32)]
 
 
 class AmmsbError(RuntimeError):
@@ -175,6 +175,11 @@ class Ctx:
     def update_pi(self, K, store, d_phi_vec, d_phi_sum, d_nodes, V):
         _ck(lib().ammsb_update_pi(self.h, K, store.h, d_phi_vec.ptr,
                                   d_phi_sum.ptr if d_phi_sum is not None else None, d_nodes.ptr, V))
+
+    def update_pi_part(self, K, store, d_phi_vec, d_phi_sum, d_nodes, V, opts):
+        _ck(lib().ammsb_update_pi_part(self.h, K, store.h, d_phi_vec.ptr,
+                                       d_phi_sum.ptr if d_phi_sum is not None else None, d_nodes.ptr, V,
+                                       C.byref(opts)))
 
     def beta_workspace_bytes(self, K):
         n = C.c_size_t(0)

@@ -359,3 +359,67 @@ def test_row_sum_and_normalize(ctx, orc, length):
     got = d.read().reshape(rows, length)
     assert np.array_equal(got[0], (base / np.float32(want)).astype(np.float32))
     d.free(); d_s.free()
+
+
+# ------------------------------------------------ multi-GPU work partition ----
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+@pytest.mark.parametrize("strict", [0, 1])
+def test_update_phi_partition_is_rank_invariant(ctx, orc, parts, strict):
+    """The slots of each rank (unit % parts == rank), launched one rank after the other on one
+    GPU, reproduce the single-launch phi_vec / RNG pool / pi bit for bit: a unit's Langevin
+    state is owned by exactly one rank, so the result cannot depend on the GPU count."""
+    K, V, n = 128, 203, 8
+    prob = link_heavy_problem(orc, 600, K, n)
+    nodes = prob.minibatch_nodes(V, 4)
+    neighbors, _ = orc.neighbor_sample(orc.rng_pool(V * 2 * n, 56, 57), nodes, prob.N, n, 32)
+    d_nodes, d_nb, d_beta = ctx.from_host(nodes), ctx.from_host(neighbors), ctx.from_host(prob.beta)
+    dset = dev_set(ctx, prob.train_set)
+    outs = []
+    for pc in (1, parts):
+        st = dev_store(ctx, prob)
+        r = A.Rng(ctx, V * 32, 42, 43)
+        d_vec, d_sum = ctx.buf(np.float32, V * K).zero(), ctx.buf(np.float32, V).zero()
+        for pi_ in range(pc):
+            opts = A.PhiOpts(A.MODE_WG, 32, 0, strict, pi_, pc)
+            ctx.update_phi(dev_params(prob.p_orc), opts, d_beta, st, dset, d_nodes, d_nb, V, 2, r, d_vec, d_sum)
+        for pi_ in range(pc):  # every rank's update_phi is done before any update_pi (the barrier)
+            opts = A.PhiOpts(A.MODE_WG, 32, 0, strict, pi_, pc)
+            ctx.update_pi_part(K, st, d_vec, d_sum, d_nodes, V, opts)
+        outs.append((d_vec.read(), d_sum.read(), r.get_state(), st.read_pi(), st.read_phi()))
+        for b in (d_vec, d_sum):
+            b.free()
+        r.free(); st.free()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    for b in (d_nodes, d_nb, d_beta):
+        b.free()
+    dset.free()
+
+
+def test_beta_grads_chunks_sum_to_the_whole(ctx, orc):
+    """per-rank edge chunks + sum (the all-reduce) == one launch, within reduction-order noise"""
+    K, m = 256, 333
+    prob = link_heavy_problem(orc, 500, K, 8)
+    edges = prob.minibatch_edges(m, 3)
+    st, dset = dev_store(ctx, prob), dev_set(ctx, prob.train_set)
+    d_theta, d_beta, d_edges = ctx.from_host(prob.theta), ctx.from_host(prob.beta), ctx.from_host(edges)
+    d_ts, d_g = ctx.buf(np.float32, K), ctx.buf(np.float32, 2 * K)
+    ws = ctx.buf(np.uint8, ctx.beta_workspace_bytes(K))
+    p = dev_params(prob.p_orc)
+    ctx.beta_grads(p, d_theta, d_beta, st, dset, d_edges, m, d_ts, d_g, ws)
+    whole = d_g.read().astype(np.float64)
+    total = np.zeros(2 * K)
+    import dist as D
+    for rank in range(4):
+        lo, hi = D.chunk(m, rank, 4)
+        sub = type("V", (), {"ptr": __import__("ctypes").c_void_p(d_edges.ptr.value + 8 * lo)})()
+        ctx.beta_grads(p, d_theta, d_beta, st, dset, sub, hi - lo, d_ts, d_g, ws)
+        total += d_g.read()
+    err = np.abs(total - whole) / (np.abs(whole) + 1e-12)
+    assert np.median(err) < 1e-6 and err.max() < 1e-3
+    ctx.beta_grads(p, d_theta, d_beta, st, dset, d_edges, 0, d_ts, d_g, ws)  # a rank with no edges
+    assert not d_g.read().any()
+    for b in (d_theta, d_beta, d_edges, d_ts, d_g, ws):
+        b.free()
+    dset.free(); st.free()
