@@ -432,14 +432,15 @@ def run_b200(args, w):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "update_phi_traffic.json")))["dram_bytes_per_launch"]
+    try:  # DRAM bytes per launch = ncu's (dram read + write) / algorithmic ratio of the committed capture
+        ratio = json.load(open(os.path.join(ROOT, "profiles", "update_phi_traffic.json")))["dram_over_algorithmic"]
+        traffic = round(ratio * phi_bytes / args.steps)
     except Exception:
         pass
     achieved = phi_bytes / (phi_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_update_phi_fast", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "launches": args.steps, "share_of_step": round(phi_ms / dev_ms, 4),
+                "launches": args.steps, "algorithmic_bytes_per_launch": round(phi_bytes / args.steps), "share_of_step": round(phi_ms / dev_ms, 4),
                 "canonical_launch": dict(stages["update_phi"], V=Vb, frac=round(stages["update_phi"]["GBps"] / peak, 4))}
     for b in (d_edges_all, d_nodes_all, d_hedges, d_ppx, pws, d_nb, d_vec, d_sum, d_ts, d_g, ws, d_theta, d_beta):
         b.free()

@@ -8,6 +8,8 @@
 #include <sstream>
 
 #include "mcmc/learner.h"
+#include "mcmc/std_order_set.h"
+#include <unordered_set>
 
 using namespace mcmc;
 
@@ -156,6 +158,34 @@ int mcmc_host_set_build(const uint64_t* keys, uint64_t n, uint64_t* table_out, u
   return ok ? 1 : 0;
 }
 uint64_t mcmc_host_set_bins(uint64_t n) { return Set(n).BinsPerBucket(); }
+
+// test hook: iteration order of StdOrderSet vs std::unordered_set for one insert sequence
+// (width 8: Edge keys, width 4: Vertex keys); returns the number of distinct keys
+uint64_t mcmc_test_set_order(const uint64_t* keys, uint64_t n, int width, uint64_t* out_std, uint64_t* out_flat) {
+  std::vector<uint64_t> a, b;
+  if (width == 8) {
+    std::unordered_set<Edge> ref;
+    StdOrderSet<Edge> flat;
+    for (uint64_t i = 0; i < n; ++i) {
+      const bool x = ref.insert(keys[i]).second, y = flat.Insert(keys[i]);
+      if (x != y) return ~0ull;
+    }
+    a.assign(ref.begin(), ref.end());
+    flat.EmitTo(&b);
+  } else {
+    std::unordered_set<Vertex> ref;
+    StdOrderSet<Vertex> flat;
+    for (uint64_t i = 0; i < n; ++i) {
+      const bool x = ref.insert(static_cast<Vertex>(keys[i])).second, y = flat.Insert(static_cast<Vertex>(keys[i]));
+      if (x != y) return ~0ull;
+    }
+    a.assign(ref.begin(), ref.end());
+    flat.EmitTo(&b);
+  }
+  std::memcpy(out_std, a.data(), 8 * a.size());
+  std::memcpy(out_flat, b.data(), 8 * b.size());
+  return a.size() == b.size() ? a.size() : ~0ull;
+}
 
 // theta init stream of Learner::Learner (host mt19937 + gamma_distribution)
 void mcmc_init_theta_host(uint32_t K, float eta0, float eta1, float* theta_out) {

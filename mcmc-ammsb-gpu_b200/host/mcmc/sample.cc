@@ -7,6 +7,7 @@
 
 #include "mcmc/config.h"
 #include "mcmc/serialize.h"
+#include "mcmc/std_order_set.h"
 
 namespace mcmc {
 
@@ -120,8 +121,8 @@ Float sampleNodeLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* 
 // seed is rewound to the draw that completed the mini-batch, so the stream position -- and
 // with it every later mini-batch -- is the reference's.
 Float sampleNodeNonLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed) {
-  ArenaScope scope;
-  HashSet<Edge> picked;
+  thread_local StdOrderSet<Edge> picked;  // std::unordered_set<Edge> order, flat storage
+  picked.Clear();
   const Vertex u = DrawVertex(cfg, seed);
   const size_t m = cfg.mini_batch_size;
   const int kBlock = 32;
@@ -140,12 +141,12 @@ Float sampleNodeNonLink(const Config& cfg, std::vector<Edge>* edges, unsigned in
     // at most `take` insertions can happen, so the block never overshoots m mid-way
     for (int i = 0; i < take; ++i) {
       if (cfg.heldout->HasAt(cand[i], hb[i]) || cfg.training->HasAt(cand[i], tb[i])) continue;
-      picked.insert(cand[i]);
+      picked.Insert(cand[i]);
     }
     s = after[take - 1];
   }
   *seed = s;
-  Emit(picked, edges);
+  picked.EmitTo(edges);
   return (2 * cfg.E) / static_cast<Float>(cfg.mini_batch_size);
 }
 
@@ -217,14 +218,25 @@ Float sampleBreadthFirst(const Config& cfg, std::vector<Edge>* edges, unsigned i
 }
 
 void ExtractNodesFromMiniBatch(const std::vector<Edge>& edges, std::vector<Vertex>* nodes_vec) {
-  ArenaScope scope;
-  HashSet<Vertex> nodes;
+  thread_local StdOrderSet<Vertex> nodes;  // std::unordered_set<Vertex> order (learner.cc:164-172)
+  nodes.Clear();
+  // a vertex that has just been inserted (or found) need not be looked up again: re-inserting
+  // a present key never changes the set.  Node-strategy mini-batches share one endpoint.
+  bool have_last = false;
+  Vertex last = 0;
   for (Edge e : edges) {
-    nodes.insert(static_cast<Vertex>(e >> 32));
-    nodes.insert(static_cast<Vertex>(e & 0xffffffffu));
+    const Vertex ends[2] = {static_cast<Vertex>(e >> 32), static_cast<Vertex>(e & 0xffffffffu)};
+    for (Vertex v : ends) {
+      if (have_last && v == last) continue;
+      nodes.Insert(v);
+    }
+    // the shared endpoint is whichever end repeats; remember the first end, and the second
+    // when the first keeps changing
+    if (!have_last) { last = ends[0]; have_last = true; }
+    else if (ends[0] != last && ends[1] != last) last = ends[0];
   }
   nodes_vec->clear();
-  nodes_vec->insert(nodes_vec->begin(), nodes.begin(), nodes.end());
+  nodes.EmitTo(nodes_vec);
 }
 
 std::istream& operator>>(std::istream& in, SampleStrategy& strategy) {

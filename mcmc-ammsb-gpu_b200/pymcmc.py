@@ -45,6 +45,8 @@ def lib():
                                           C.c_void_p, C.c_void_p]
         L.mcmc_host_set_bins.restype = C.c_uint64
         L.mcmc_host_set_bins.argtypes = [C.c_uint64]
+        L.mcmc_test_set_order.restype = C.c_uint64
+        L.mcmc_test_set_order.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
         L.mcmc_init_theta_host.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_void_p]
         L.mcmc_learner_create.restype = C.c_void_p
         L.mcmc_learner_create.argtypes = [C.c_void_p, C.c_int]
@@ -82,6 +84,16 @@ def host_set_build(keys):
     b, p, s = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
     ok = lib().mcmc_host_set_build(_p(keys), len(keys), _p(table), table.size, C.byref(b), C.byref(p), C.byref(s))
     return bool(ok), table, b.value, p.value, s.value
+
+
+def set_order(keys, width):
+    """(order of std::unordered_set, order of StdOrderSet) for one insert sequence"""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    a, b = np.zeros(len(keys), np.uint64), np.zeros(len(keys), np.uint64)
+    n = lib().mcmc_test_set_order(_p(keys), len(keys), width, _p(a), _p(b))
+    if n == 2 ** 64 - 1:
+        raise AssertionError("StdOrderSet disagrees with std::unordered_set on membership")
+    return a[:n], b[:n]
 
 
 def init_theta_host(K, eta0=1.0, eta1=1.0):

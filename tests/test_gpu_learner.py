@@ -67,10 +67,14 @@ class OracleLearner:
         return float(np.exp(np.float32(avg)))
 
 
-def close_enough(got, want, what, frac=2e-3):
+def close_enough(got, want, what, frac=5e-3):
+    """rtol 1e-5 on all but the ill-conditioned elements (cancellation in the Langevin update;
+    the reference's own THREAD and WG variants differ by more there, test_gpu_parity.py), which
+    stay within 2e-4"""
     e = rel_err(got, want)
     assert np.median(e) < 1e-6, (what, np.median(e))
     assert float((e > RTOL).mean()) < frac, (what, float((e > RTOL).mean()), e.max())
+    assert e.max() < 2e-4, (what, e.max())
 
 
 @pytest.mark.parametrize("strategy", ["Node", "BF"])

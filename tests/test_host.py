@@ -93,3 +93,27 @@ def test_theta_init_is_the_libstdcxx_stream():
     b = pymcmc.init_theta_host(64)
     assert np.array_equal(a, b) and (a > 0).all() and abs(float(a.mean()) - 1.0) < 0.25
     assert np.array_equal(pymcmc.init_theta_host(16), a[:32])
+
+
+@pytest.mark.parametrize("width", [8, 4])
+def test_flat_set_iterates_like_std_unordered_set(width):
+    """the mini-batch strategies emit edges/nodes in std::unordered_set iteration order; the flat
+    container that replaces it in the hot host path must reproduce that order exactly, through
+    every rehash, with duplicates, for 64-bit edge keys and 32-bit vertex ids"""
+    rng = np.random.default_rng(width)
+    for n, span in [(0, 10), (1, 10), (13, 5), (14, 1 << 40), (200, 64), (5000, 1 << 20), (40000, 1 << 33),
+                    (33000, 317080), (150000, 1 << 31)]:
+        hi = span if width == 8 else min(span, 1 << 32)
+        keys = rng.integers(0, hi, size=n, dtype=np.uint64)
+        if n > 100:  # duplicates and clustered keys
+            keys[::7] = keys[0]
+            keys[1::3] = (keys[1::3] // 4096) * 4096
+        a, b = pymcmc.set_order(keys, width)
+        assert len(a) == len(np.unique(keys))
+        assert np.array_equal(a, b)
+    # the non-link mini-batch shape: all edges share one endpoint
+    u = 1234
+    v = rng.integers(0, 317080, size=20000, dtype=np.uint64)
+    keys = (np.minimum(u, v) << np.uint64(32)) | np.maximum(u, v)
+    a, b = pymcmc.set_order(keys, 8)
+    assert np.array_equal(a, b)
