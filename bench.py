@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--m", type=int, default=16384, help="mini-batch edges per GPU")
     ap.add_argument("--n", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--store", default="auto", choices=["auto", "partitioned", "replicated"],
+                    help="multi-GPU pi layout: node-partitioned (NVLink peer loads) or one copy per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -463,6 +465,8 @@ def run_b200(args, w):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         assert float(mirror.sum()) > 0
+        if rank == 0:
+            lrn.print_stats()  # stage breakdown of the host path, to stderr
         e_edges = lrn.edges_processed() - e0
         t1 = time.perf_counter()
         ppx = lrn.heldout_perplexity()

@@ -138,6 +138,11 @@ int ammsb_store_export(ammsb_store* store, uint8_t* pi_handle /* [64] */, uint8_
 int ammsb_store_attach(ammsb_store* store, uint32_t shard, const uint8_t* pi_handle, const uint8_t* phi_handle);
 /* single-process multi-device: attach another store's shard by direct peer access */
 int ammsb_store_attach_local(ammsb_store* store, uint32_t shard, ammsb_store* peer);
+/* Replicated mode (pi fits on every GPU): each GPU holds a full copy (num_shards = 1) and
+ * registers the other GPUs' copies as mirrors; reads stay in local HBM and ammsb_update_pi*
+ * writes every updated row to the local copy and to all mirrors (NVLink peer stores). */
+int ammsb_store_add_mirror(ammsb_store* store, const uint8_t* pi_handle, const uint8_t* phi_handle);
+int ammsb_store_add_mirror_local(ammsb_store* store, ammsb_store* peer);
 int ammsb_store_rows(const ammsb_store* store, uint64_t* first_row, uint64_t* num_rows);
 int ammsb_store_local_ptrs(ammsb_store* store, float** d_pi, float** d_phi);
 /* make the local shard use caller-owned memory for phi (>= rows_per_shard floats): the

@@ -82,6 +82,10 @@ struct StoreView {
   uint32_t num_shards;
   uint32_t K;
   uint32_t N;
+  // replicated mode: full copies on other GPUs that receive every row update
+  float* mirror_pi[AMMSB_MAX_SHARDS];
+  float* mirror_phi[AMMSB_MAX_SHARDS];
+  uint32_t num_mirrors;
 };
 
 struct ammsb_store {
@@ -96,6 +100,10 @@ struct ammsb_store {
   float* peer_phi[AMMSB_MAX_SHARDS] = {nullptr};
   bool peer_is_ipc[AMMSB_MAX_SHARDS] = {false};
   bool owns_phi = true;
+  float* mirror_pi[AMMSB_MAX_SHARDS] = {nullptr};
+  float* mirror_phi[AMMSB_MAX_SHARDS] = {nullptr};
+  bool mirror_is_ipc[AMMSB_MAX_SHARDS] = {false};
+  uint32_t num_mirrors = 0;
   StoreView view() const;
 };
 

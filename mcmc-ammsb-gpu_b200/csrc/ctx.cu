@@ -216,6 +216,11 @@ StoreView ammsb_store::view() const {
   v.num_shards = num_shards;
   v.K = K;
   v.N = (uint32_t)N;
+  for (int i = 0; i < AMMSB_MAX_SHARDS; ++i) {
+    v.mirror_pi[i] = mirror_pi[i];
+    v.mirror_phi[i] = mirror_phi[i];
+  }
+  v.num_mirrors = num_mirrors;
   return v;
 }
 
@@ -253,6 +258,12 @@ extern "C" int ammsb_store_destroy(ammsb_store* s) {
     if (i != s->shard_id && s->peer_is_ipc[i]) {
       if (s->peer_pi[i]) cudaIpcCloseMemHandle(s->peer_pi[i]);
       if (s->peer_phi[i]) cudaIpcCloseMemHandle(s->peer_phi[i]);
+    }
+  }
+  for (uint32_t i = 0; i < s->num_mirrors; ++i) {
+    if (s->mirror_is_ipc[i]) {
+      cudaIpcCloseMemHandle(s->mirror_pi[i]);
+      cudaIpcCloseMemHandle(s->mirror_phi[i]);
     }
   }
   cudaFree(s->d_pi);
@@ -311,6 +322,46 @@ extern "C" int ammsb_store_attach_local(ammsb_store* s, uint32_t shard, ammsb_st
   return 0;
 }
 
+extern "C" int ammsb_store_add_mirror(ammsb_store* s, const uint8_t* pi_handle, const uint8_t* phi_handle) {
+  AMMSB_REQUIRE(s->num_shards == 1, "mirrors belong to a replicated (num_shards = 1) store");
+  AMMSB_REQUIRE(s->num_mirrors < AMMSB_MAX_SHARDS - 1, "too many mirrors");
+  AMMSB_CHECK_CUDA(cudaSetDevice(s->ctx->device));
+  cudaIpcMemHandle_t h;
+  void* p = nullptr;
+  memcpy(&h, pi_handle, sizeof h);
+  AMMSB_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  s->mirror_pi[s->num_mirrors] = (float*)p;
+  memcpy(&h, phi_handle, sizeof h);
+  AMMSB_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  s->mirror_phi[s->num_mirrors] = (float*)p;
+  s->mirror_is_ipc[s->num_mirrors] = true;
+  ++s->num_mirrors;
+  return 0;
+}
+
+extern "C" int ammsb_store_add_mirror_local(ammsb_store* s, ammsb_store* peer) {
+  AMMSB_REQUIRE(s->num_shards == 1 && peer->num_shards == 1 && peer->N == s->N && peer->K == s->K && peer != s,
+                "mirror must be another full copy of the same shape");
+  AMMSB_REQUIRE(s->num_mirrors < AMMSB_MAX_SHARDS - 1, "too many mirrors");
+  AMMSB_CHECK_CUDA(cudaSetDevice(s->ctx->device));
+  if (peer->ctx->device != s->ctx->device) {
+    int can = 0;
+    AMMSB_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, s->ctx->device, peer->ctx->device));
+    AMMSB_REQUIRE(can, "devices are not peer-accessible");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->ctx->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+    } else {
+      AMMSB_CHECK_CUDA(e);
+    }
+  }
+  s->mirror_pi[s->num_mirrors] = peer->d_pi;
+  s->mirror_phi[s->num_mirrors] = peer->d_phi;
+  s->mirror_is_ipc[s->num_mirrors] = false;
+  ++s->num_mirrors;
+  return 0;
+}
+
 extern "C" int ammsb_store_rows(const ammsb_store* s, uint64_t* first_row, uint64_t* num_rows) {
   *first_row = s->first_row;
   *num_rows = s->local_rows;
@@ -325,6 +376,7 @@ extern "C" int ammsb_store_local_ptrs(ammsb_store* s, float** d_pi, float** d_ph
 
 extern "C" int ammsb_store_bind_phi(ammsb_store* s, float* d_phi) {
   AMMSB_REQUIRE(d_phi != nullptr, "null phi");
+  AMMSB_REQUIRE(s->num_shards == 1 && s->num_mirrors == 0, "bind_phi is for a single, unmirrored store");
   AMMSB_CHECK_CUDA(cudaSetDevice(s->ctx->device));
   if (s->owns_phi) {
     AMMSB_CHECK_CUDA(cudaMemcpyAsync(d_phi, s->d_phi, sizeof(float) * s->local_rows, cudaMemcpyDeviceToDevice,

@@ -418,7 +418,7 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
 // phi[node] = sum.  The row sum was produced by update_phi in the association of
 // the launch mode; the division is IEEE.
 __global__ void __launch_bounds__(256)
-    k_update_pi(StoreView sv, const float* __restrict__ phi_vec, const float* __restrict__ phi_sum,
+    k_update_pi(const __grid_constant__ StoreView sv, const float* __restrict__ phi_vec, const float* __restrict__ phi_sum,
                 const uint32_t* __restrict__ nodes, uint32_t V, uint32_t units, uint32_t part_index,
                 uint32_t part_count) {
   const uint32_t lane = threadIdx.x & 31;
@@ -446,10 +446,18 @@ __global__ void __launch_bounds__(256)
         v.z = __fdiv_rn(v.z, sum);
         v.w = __fdiv_rn(v.w, sum);
         *reinterpret_cast<float4*>(dst + k) = v;
+        for (uint32_t r = 0; r < sv.num_mirrors; ++r)  // replicated mode: NVLink peer stores
+          *reinterpret_cast<float4*>(sv.mirror_pi[r] + (size_t)node * K + k) = v;
       }
     } else {
-      for (uint32_t k = lane; k < K; k += 32) dst[k] = __fdiv_rn(src[k], sum);
+      for (uint32_t k = lane; k < K; k += 32) {
+        const float v = __fdiv_rn(src[k], sum);
+        dst[k] = v;
+        for (uint32_t r = 0; r < sv.num_mirrors; ++r) sv.mirror_pi[r][(size_t)node * K + k] = v;
+      }
     }
+    if (lane == 0)
+      for (uint32_t r = 0; r < sv.num_mirrors; ++r) sv.mirror_phi[r][node] = sum;
     if (lane == 0) *store_phi(sv, node) = sum;
   }
 }

@@ -1,4 +1,7 @@
-"""dist.py -- node-partitioned multi-GPU driver of the SG-MCMC iteration (one process per GPU).
+"""dist.py -- multi-GPU driver of the SG-MCMC iteration (one process per GPU); pi/phi either
+node-partitioned over the GPUs (store_mode "partitioned", the layout for graphs that need the
+memory of G GPUs) or held as one full copy per GPU ("replicated", when N*K*4 bytes fit: every
+read is local HBM and only the updated rows cross NVLink).
 
 The reference is single-device; its only scale mechanism is RowPartitionedMatrix
 (partitioned-alloc.h:14-141).  Here pi/phi are node-partitioned over the G GPUs of one box
@@ -80,7 +83,7 @@ class ShardedLearner:
 
     STREAMS = 4  # independent host sampler streams (the reference has 2: its two Samples)
 
-    def __init__(self, cfg, rank, world, local_rank, seed=12345, prefetch=True):
+    def __init__(self, cfg, rank, world, local_rank, seed=12345, prefetch=True, store_mode="partitioned"):
         import torch
         import torch.distributed as dist
         import pyammsb as A
@@ -93,13 +96,24 @@ class ShardedLearner:
         self.ctx = A.Ctx(local_rank)
         self.ctx.set_stream(self.stream.cuda_stream)
         dev = torch.device("cuda", local_rank)
-        # ---- node-partitioned store, peers attached by IPC handle ----
-        self.store = A.Store(self.ctx, self.N, self.K, world, rank)
-        if world > 1:
-            handles = exchange(self.store.export_handles(), world)
-            for s, (hp, hf) in enumerate(handles):
+        # ---- pi/phi store; peers attached by IPC handle ----
+        #   partitioned: shard `rank` of a node-partitioned matrix, neighbor rows of other
+        #                shards are read over NVLink (the layout for graphs that need G GPUs)
+        #   replicated:  a full copy per GPU (when N*K*4 fits), reads are local HBM and every
+        #                updated row is written to all copies over NVLink
+        assert store_mode in ("partitioned", "replicated")
+        self.store_mode = store_mode if world > 1 else "partitioned"
+        if self.store_mode == "replicated":
+            self.store = A.Store(self.ctx, self.N, self.K, 1, 0)
+            for s, (hp, hf) in enumerate(exchange(self.store.export_handles(), world)):
                 if s != rank:
-                    self.store.attach(s, hp, hf)
+                    self.store.add_mirror(hp, hf)
+        else:
+            self.store = A.Store(self.ctx, self.N, self.K, world, rank)
+            if world > 1:
+                for s, (hp, hf) in enumerate(exchange(self.store.export_handles(), world)):
+                    if s != rank:
+                        self.store.attach(s, hp, hf)
         self.store.init_pi(float(self.p.eta0), float(self.p.eta1))
         # ---- replicated: edge sets, theta/beta, RNG pools ----
         t_tab, t_bins, t_prime = cfg.set_table(0)
@@ -231,7 +245,11 @@ class ShardedLearner:
 
     # ------------------------------------------------------------- state ----
     def read_local_pi(self):
+        """rows this rank holds: its shard (partitioned) or the whole matrix (replicated)"""
         return self.store.read_pi()
+
+    def local_rows(self):
+        return self.store.first_row, self.store.first_row + self.store.local_rows
 
     def read_beta(self):
         return self.beta.cpu().numpy()
@@ -255,7 +273,10 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=w["heldout_ratio"], strategy="Node")
     cfg.set_graph(N, keys)
     log("graph + split + sets: %.1fs" % (time.time() - t0))
-    lrn = ShardedLearner(cfg, rank, world, local_rank, prefetch=False)
+    mode = getattr(args, "store", "auto")
+    if mode == "auto":  # replicate while a full copy (plus mini-batch buffers) is a small part of 180 GB
+        mode = "replicated" if 4.0 * N * K <= 48e9 else "partitioned"
+    lrn = ShardedLearner(cfg, rank, world, local_rank, prefetch=False, store_mode=mode)
     stream = lrn.stream
     ctx = lrn.ctx
 
@@ -300,10 +321,7 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     timed = batches[args.warmup:]
     edges_timed = int(sum(len(b[1]) for b in timed))
     value = edges_timed / (dev_ms * 1e-3)
-    # NVLink roofline of update_phi: rows that cross the switch into this GPU
     Vs = [len(b[2]) for b in timed]
-    remote_bytes = float(sum((V / world) * n * 4 * K * (world - 1) / world for V in Vs))
-    local_bytes = float(sum((V / world) * ((n + 2) * 4 * K + 68 * n + 8) for V in Vs))
     nvlink_peak = 770.0  # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
     peaks = {}
     try:
@@ -312,14 +330,27 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    ideal_ms = max(remote_bytes / nvlink_peak, local_bytes / hbm_peak) / 1e6
-    roofline = {"bound": "nvlink", "kernel": "k_update_phi_fast (peer loads)", "unit": "GB/s",
-                "achieved": round(remote_bytes / (phi_ms * 1e-3) / 1e9, 1), "peak": nvlink_peak,
-                "frac": round(remote_bytes / (phi_ms * 1e-3) / 1e9 / nvlink_peak, 4),
-                "peak_source": "770 GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)",
-                "traffic": None, "inbound_remote_GB_per_gpu_per_step": round(remote_bytes / args.steps / 1e9, 4),
-                "hbm_side_GBps": round(local_bytes / (phi_ms * 1e-3) / 1e9, 1),
-                "ideal_ms_per_step": round(ideal_ms / args.steps, 4), "share_of_step": round(phi_ms / dev_ms, 4)}
+    local_bytes = float(sum((V / world) * ((n + 2) * 4 * K + 68 * n + 8) for V in Vs))  # per GPU
+    if mode == "partitioned":
+        # update_phi is bound by the neighbor rows that cross the switch into each GPU
+        remote_bytes = float(sum((V / world) * n * 4 * K * (world - 1) / world for V in Vs))
+        ach = remote_bytes / (phi_ms * 1e-3) / 1e9
+        roofline = {"bound": "nvlink", "kernel": "k_update_phi_fast (NVLink peer loads of neighbor rows)",
+                    "unit": "GB/s", "achieved": round(ach, 1), "peak": nvlink_peak, "frac": round(ach / nvlink_peak, 4),
+                    "peak_source": "770 GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)",
+                    "traffic": None, "inbound_remote_GB_per_gpu_per_step": round(remote_bytes / args.steps / 1e9, 4),
+                    "hbm_side_GBps": round(local_bytes / (phi_ms * 1e-3) / 1e9, 1),
+                    "share_of_step": round(phi_ms / dev_ms, 4)}
+    else:
+        # every read is local HBM; NVLink only carries the updated rows (update_pi peer stores)
+        ach = local_bytes / (phi_ms * 1e-3) / 1e9
+        out_bytes = float(sum((V / world) * (world - 1) * (4 * K + 4) for V in Vs))
+        roofline = {"bound": "hbm", "kernel": "k_update_phi_fast (per GPU, replicated pi)", "unit": "GB/s",
+                    "achieved": round(ach, 1), "peak": hbm_peak, "frac": round(ach / hbm_peak, 4),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)", "traffic": None,
+                    "share_of_step": round(phi_ms / dev_ms, 4),
+                    "nvlink_outbound_GB_per_gpu_per_step": round(out_bytes / args.steps / 1e9, 4)}
+    roofline["store"] = mode
 
     # ---- perplexity (sharded) ----
     torch.cuda.synchronize()
@@ -331,7 +362,7 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     # ---- e2e leg: host mini-batches through the sharded driver ----
     e2e = None
     if not args.no_e2e:
-        l2 = ShardedLearner(cfg, rank, world, local_rank, prefetch=True)
+        l2 = ShardedLearner(cfg, rank, world, local_rank, prefetch=True, store_mode=mode)
         for _ in range(args.warmup):
             l2.host_step()
         dist.barrier()
@@ -356,8 +387,12 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w, world),
-                       "parallelism": "pi/phi node-partitioned over %d GPUs (NVLink peer loads), beta gradient and "
-                                      "perplexity sums all-reduced (NCCL)" % world,
+                       "parallelism": ("pi/phi node-partitioned over %d GPUs (NVLink peer loads), " % world
+                                       if mode == "partitioned" else
+                                       "pi/phi replicated on %d GPUs (fits: %.1f GB), mini-batch slots split over "
+                                       "GPUs, updated rows written to every copy by NVLink peer stores, "
+                                       % (world, 4.0 * N * K / 1e9)) +
+                                      "beta gradient and perplexity sums all-reduced (NCCL)",
                        "l2": "inputs larger than L2 (pi %.2f GB, %.2f GB of rows gathered per non-link step)"
                              % (4.0 * N * K / 1e9, (m + 1) * (n + 2) * 4 * K / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},

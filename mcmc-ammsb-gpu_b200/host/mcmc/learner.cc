@@ -151,9 +151,12 @@ Float Learner::SampleMiniBatch(std::vector<Edge>* edges, unsigned int* seed) { r
 // host mini-batch -> device copies -> neighbor sampling, all on the Sample's own queue so
 // that it overlaps the previous iteration's kernels (reference learner.cc:175-194)
 Float Learner::DoSample(Sample* sample) {
+  const auto t0 = high_resolution_clock::now();
   sample->edges.clear();
   const Float weight = SampleMiniBatch(&sample->edges, &sample->seed);
+  const auto t1 = high_resolution_clock::now();
   ExtractNodesFromMiniBatch(sample->edges, &sample->nodes_vec);
+  const auto t2 = high_resolution_clock::now();
   if (sample->nodes_vec.empty()) throw BackendError("mini-batch size = 0!");
   if (sample->edges.size() > sample->dev_edges.GetSize() / sizeof(Edge) ||
       sample->nodes_vec.size() > sample->dev_nodes.GetSize() / sizeof(Vertex))
@@ -161,7 +164,13 @@ Float Learner::DoSample(Sample* sample) {
   sample->dev_edges.Write(sample->queue, sample->edges.size(), sample->edges.data());
   sample->dev_nodes.Write(sample->queue, sample->nodes_vec.size(), sample->nodes_vec.data());
   h2dBytes_ += sample->edges.size() * sizeof(Edge) + sample->nodes_vec.size() * sizeof(Vertex);
+  const auto t3 = high_resolution_clock::now();
   sample->neighbor_sampler(static_cast<uint32_t>(sample->nodes_vec.size()), &sample->dev_nodes);
+  const auto t4 = high_resolution_clock::now();
+  tStrategy_ += duration_cast<nanoseconds>(t1 - t0).count();
+  tExtract_ += duration_cast<nanoseconds>(t2 - t1).count();
+  tCopy_ += duration_cast<nanoseconds>(t3 - t2).count();
+  tNeighbor_ += duration_cast<nanoseconds>(t4 - t3).count();
   return weight;
 }
 
@@ -204,13 +213,17 @@ void Learner::Run(uint32_t max_iters, sig_atomic_t* signaled) {
     LaunchSampler(1 - phase_);
     samplingTime_ += duration_cast<nanoseconds>(high_resolution_clock::now() - ts).count();
 
+    const auto tk = high_resolution_clock::now();
     Sample& s = samples_[phase_];
     phiUpdater_(s.dev_nodes, s.neighbor_sampler.GetData(), static_cast<uint32_t>(s.nodes_vec.size()));
     betaUpdater_(&s.dev_edges, static_cast<uint32_t>(s.edges.size()), weight);
     edgesProcessed_ += s.edges.size();
     if (betaMirror_ != nullptr) beta_.ReadAsync(queue_, 2 * cfg_.K, betaMirror_);
     // the sampler thread reuses this buffer two iterations from now; drain before flipping
+    const auto td = high_resolution_clock::now();
     queue_.Finish();
+    tKernelsHost_ += duration_cast<nanoseconds>(td - tk).count();
+    tDrain_ += duration_cast<nanoseconds>(high_resolution_clock::now() - td).count();
     const int consumed = phase_;
     phase_ = 1 - phase_;
     // The two Samples draw from independent seeds and RNG pools and sampling never reads
@@ -239,6 +252,12 @@ void Learner::PrintStats() {
   line("GRADS SUM   : ", betaUpdater_.GradsSumTime() / 1.0e3);
   line("UPDATE THETA: ", betaUpdater_.UpdateThetaTime() / 1.0e3);
   line("NORM THETA  : ", betaUpdater_.NormalizeTime() / 1.0e3);
+  line("  sampler threads: strategy ", tStrategy_ / 1.0e9);
+  line("  sampler threads: extract  ", tExtract_ / 1.0e9);
+  line("  sampler threads: H2D      ", tCopy_ / 1.0e9);
+  line("  sampler threads: neighbors", tNeighbor_ / 1.0e9);
+  line("  main thread: launches     ", tKernelsHost_ / 1.0e9);
+  line("  main thread: drain        ", tDrain_ / 1.0e9);
   std::cerr << "ITERATIONS  : " << (stepCount_ - 1) << ", MINI-BATCH EDGES: " << edgesProcessed_ << std::endl;
 }
 

@@ -105,6 +105,8 @@ class Learner {
   uint64_t samplingTime_;
   uint64_t edgesProcessed_;
   std::atomic<uint64_t> h2dBytes_;
+  // sampler-thread time by stage, ns (host strategy, node extraction, H2D copies, neighbor kernel)
+  std::atomic<uint64_t> tStrategy_{0}, tExtract_{0}, tCopy_{0}, tNeighbor_{0}, tKernelsHost_{0}, tDrain_{0};
   Sample samples_[2];
   SamplerThread futures_[2];
   Float pendingWeight_[2];

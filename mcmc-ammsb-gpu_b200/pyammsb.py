@@ -338,6 +338,14 @@ class Store:
         b = (C.c_uint8 * 64).from_buffer_copy(phi_handle)
         _ck(lib().ammsb_store_attach(self.h, shard, a, b))
 
+    def add_mirror(self, pi_handle, phi_handle):
+        a = (C.c_uint8 * 64).from_buffer_copy(pi_handle)
+        b = (C.c_uint8 * 64).from_buffer_copy(phi_handle)
+        _ck(lib().ammsb_store_add_mirror(self.h, a, b))
+
+    def add_mirror_local(self, peer):
+        _ck(lib().ammsb_store_add_mirror_local(self.h, peer.h))
+
     def attach_local(self, shard, peer):
         _ck(lib().ammsb_store_attach_local(self.h, shard, peer.h))
 

@@ -29,10 +29,10 @@ def main():
     N, K, n, m = 3000, 256, 16, 512
     cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=0.1, strategy="Node")
     cfg.set_graph(N, make_edges(N, 30000, 3))
-    sharded = D.ShardedLearner(cfg, rank, world, local, prefetch=False)
+    mode = sys.argv[1] if len(sys.argv) > 1 else "partitioned"
+    sharded = D.ShardedLearner(cfg, rank, world, local, prefetch=False, store_mode=mode)
     single = D.ShardedLearner(cfg, 0, 1, local, prefetch=False)
-    single.dist = None
-    lo, hi = sharded.store.first_row, sharded.store.first_row + sharded.store.local_rows
+    lo, hi = sharded.local_rows()
 
     def compare(tag, exact_pi):
         tdist.barrier()
@@ -64,12 +64,12 @@ def main():
     p1, q1 = sharded.heldout_perplexity(), single.heldout_perplexity()
     assert abs(p1 - q1) <= 1e-3 * q1, (p1, q1)
     # the host path (sampler threads + pinned staging) runs too
-    e2e = D.ShardedLearner(cfg, rank, world, local, prefetch=True)
+    e2e = D.ShardedLearner(cfg, rank, world, local, prefetch=True, store_mode=mode)
     e2e.run(6)
     assert np.isfinite(e2e.heldout_perplexity())
     tdist.barrier()
     if rank == 0:
-        print("dist gpu check ok: world %d, perplexity %.5f -> %.5f (single %.5f -> %.5f)" % (world, p0, p1, q0, q1))
+        print("dist gpu check ok (%s): world %d, perplexity %.5f -> %.5f (single %.5f -> %.5f)" % (mode, world, p0, p1, q0, q1))
     tdist.destroy_process_group()
 
 

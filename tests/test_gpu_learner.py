@@ -69,12 +69,14 @@ class OracleLearner:
 
 def close_enough(got, want, what, frac=5e-3):
     """rtol 1e-5 on all but the ill-conditioned elements (cancellation in the Langevin update;
-    the reference's own THREAD and WG variants differ by more there, test_gpu_parity.py), which
-    stay within 2e-4"""
+    the reference's own THREAD and WG variants differ by more there, test_gpu_parity.py); those
+    are bounded in absolute terms: 2e-6 of the largest element of their row / vector"""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     e = rel_err(got, want)
     assert np.median(e) < 1e-6, (what, np.median(e))
     assert float((e > RTOL).mean()) < frac, (what, float((e > RTOL).mean()), e.max())
-    assert e.max() < 2e-4, (what, e.max())
+    scale = np.abs(want).max(axis=-1, keepdims=True)
+    assert (np.abs(got - want) / scale).max() < 2e-6, (what, (np.abs(got - want) / scale).max())
 
 
 @pytest.mark.parametrize("strategy", ["Node", "BF"])

@@ -423,3 +423,24 @@ def test_beta_grads_chunks_sum_to_the_whole(ctx, orc):
     for b in (d_theta, d_beta, d_edges, d_ts, d_g, ws):
         b.free()
     dset.free(); st.free()
+
+
+def test_update_pi_writes_every_mirror(ctx, orc):
+    """replicated mode: update_pi stores each updated row in the local copy and in all mirrors"""
+    K, V = 64, 50
+    prob = link_heavy_problem(orc, 300, K, 8)
+    stores = [dev_store(ctx, prob) for _ in range(3)]
+    stores[0].add_mirror_local(stores[1])
+    stores[0].add_mirror_local(stores[2])
+    nodes = prob.minibatch_nodes(V, 9)
+    vec = np.random.default_rng(1).gamma(1.0, 1.0, size=(V, K)).astype(np.float32)
+    d_nodes, d_vec, d_sum = ctx.from_host(nodes), ctx.from_host(vec), ctx.from_host(vec.sum(axis=1, dtype=np.float32))
+    ctx.update_pi(K, stores[0], d_vec, d_sum, d_nodes, V)
+    pis, phis = [s.read_pi() for s in stores], [s.read_phi() for s in stores]
+    assert np.array_equal(pis[0], pis[1]) and np.array_equal(pis[0], pis[2])
+    assert np.array_equal(phis[0], phis[1]) and np.array_equal(phis[0], phis[2])
+    assert not np.array_equal(pis[0][nodes], prob.pi[nodes])
+    for b in (d_nodes, d_vec, d_sum):
+        b.free()
+    for s in stores:
+        s.free()
