@@ -310,6 +310,205 @@ __global__ void __launch_bounds__(WARPS * 32)
   }
 }
 
+// ------------------------------------------------------------------ team ---
+//
+// K > 1024: a slot is processed by a TEAM of T warps (T = 2 or 4).  Warp w owns the column
+// segment [w*KS, (w+1)*KS), KS = K/T <= 1024, and stages only that segment of every row, so the
+// per-warp register budget and the bytes in flight per SM are those of the K = 1024 kernel.
+// The one cross-warp dependency per neighbor -- sum_k probs_k -- goes through shared memory and
+// a named barrier of the team (partials added in warp order: a fixed association).
+// Langevin noise: a unit's RNG stream is sequential over all K columns, so a single warp must
+// draw it.  To keep the team busy the T warps first draw the noise of T *different* upcoming
+// slots in parallel, parking it in the slot's (not yet written) phi_vec row in global memory
+// (it is read back, mostly from L2, when the slot is finalised), then process those T slots as
+// a team.  One slot per unit only (V <= 65535); larger V falls back to the strict kernel.
+__device__ __forceinline__ void team_barrier(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int KPL, int STAGES, int T, bool EXACT>
+__global__ void __launch_bounds__(128) k_update_phi_team(const __grid_constant__ PhiArgs a) {
+  constexpr int WARPS = 4;
+  constexpr int TEAMS = WARPS / T;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const uint32_t K = a.K, KS = K / T;
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t team = wib / T, w = wib % T;
+  const uint32_t seg = w * KS;           // first column of this warp's segment
+  const uint32_t seg_bytes = KS * 4;
+  float* s_own = reinterpret_cast<float*>(s_raw) + (size_t)wib * (STAGES + 1) * KS;
+  float* s_stage = s_own + KS;
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(s_raw + (size_t)WARPS * (STAGES + 1) * seg_bytes) + wib * (STAGES + 1);
+  float* s_part = reinterpret_cast<float*>(s_raw + (size_t)WARPS * (STAGES + 1) * seg_bytes +
+                                           (size_t)WARPS * (STAGES + 1) * 8) + team * 3 * T;  // [2][T] + [T]
+  if (lane == 0) {
+    for (int s = 0; s <= STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+  const uint32_t bar_id = 1 + team, bar_threads = T * 32;
+
+  float fb[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const uint32_t kk = lane + 32 * i;
+    fb[i] = (EXACT || kk < KS) ? __ldg(&a.beta[2 * (seg + kk) + 1]) - a.epsilon : 0.f;
+  }
+  const float e_link = a.epsilon, e_non = 1.0f - a.epsilon;
+  const float half_eps = a.eps_t / 2;
+  const bool fast_noise = (a.mode == AMMSB_MODE_WG && a.wg == 32);
+  const uint32_t vw = a.mode == AMMSB_MODE_THREAD ? 1u : a.wg;
+  const uint32_t active = a.units < a.V ? a.units : a.V;
+  const uint32_t gteam = blockIdx.x * TEAMS + team;
+  const uint32_t total_teams = gridDim.x * TEAMS;
+
+  for (uint32_t j0 = 0;; j0 += T) {
+    if (a.part_index + a.part_count * (gteam + j0 * total_teams) >= active) break;  // team-uniform
+    // ---- phase A: warp w draws the noise of the (j0+w)-th slot of this team ----
+    if (!a.disable_noise) {
+      const uint32_t unit = a.part_index + a.part_count * (gteam + (j0 + w) * total_teams);
+      if (unit < active) {
+        float* park = a.phi_vec + (size_t)unit * K;  // slot == unit
+        if (fast_noise) {
+          Rng st = rng_load(a.pool, (uint64_t)unit * 32 + lane);
+          for (uint32_t k = lane; k < K; k += 32) park[k] = rng_randn(st);
+          rng_store(a.pool, (uint64_t)unit * 32 + lane, st);
+        } else {
+          for (uint32_t vl = lane; vl < vw; vl += 32) {
+            Rng vs = rng_load(a.pool, (uint64_t)unit * vw + vl);
+            for (uint32_t k = vl; k < K; k += vw) park[k] = rng_randn(vs);
+            rng_store(a.pool, (uint64_t)unit * vw + vl, vs);
+          }
+        }
+      }
+    }
+    team_barrier(bar_id, bar_threads);  // parked noise is visible to the whole team
+    // ---- phase B: the T slots, one after the other, all warps on each ----
+    for (uint32_t jj = 0; jj < T; ++jj) {
+      const uint32_t slot = a.part_index + a.part_count * (gteam + (j0 + jj) * total_teams);
+      if (slot >= active) break;  // team-uniform
+      const uint32_t node = __ldg(&a.nodes[slot]);
+      const float phi_sum = *store_phi(a.sv, node);
+      const float rphi = 1.0f / phi_sum;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&bars[STAGES], seg_bytes);
+        bulk_g2s(s_own, store_row(a.sv, node) + seg, seg_bytes, &bars[STAGES]);
+      }
+      const uint32_t* nbr = a.neighbors + (size_t)slot * a.n;
+      const float* cur_ptr = nullptr;
+      const float* nxt_ptr = nullptr;
+      uint32_t cur_mask = 0, nxt_mask = 0;
+      {
+        bool y = false;
+        if (lane < a.n) {
+          const uint32_t nb = __ldg(&nbr[lane]);
+          cur_ptr = store_row(a.sv, nb) + seg;
+          if (lane < STAGES) {
+            mbar_expect_tx(&bars[lane], seg_bytes);
+            bulk_g2s(s_stage + (size_t)lane * KS, cur_ptr, seg_bytes, &bars[lane]);
+          }
+          y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+        }
+        cur_mask = __ballot_sync(FULL_MASK, y);
+        y = false;
+        if (32 + lane < a.n) {
+          const uint32_t nb = __ldg(&nbr[32 + lane]);
+          nxt_ptr = store_row(a.sv, nb) + seg;
+          y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+        }
+        nxt_mask = __ballot_sync(FULL_MASK, y);
+      }
+      float g[KPL];
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) g[i] = 0.f;
+      mbar_wait(&bars[STAGES], (phase >> STAGES) & 1);
+      phase ^= 1u << STAGES;
+
+      for (uint32_t j = 0; j < a.n; ++j) {
+        const uint32_t q32 = j & 31;
+        if (q32 == 0 && j > 0) {
+          cur_ptr = nxt_ptr;
+          cur_mask = nxt_mask;
+          bool y = false;
+          nxt_ptr = nullptr;
+          if (j + 32 + lane < a.n) {
+            const uint32_t nb = __ldg(&nbr[j + 32 + lane]);
+            nxt_ptr = store_row(a.sv, nb) + seg;
+            y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+          }
+          nxt_mask = __ballot_sync(FULL_MASK, y);
+        }
+        const uint32_t s = j % STAGES;
+        const bool y = (cur_mask >> q32) & 1;
+        const float e = y ? e_link : e_non;
+        const float sgn = y ? 1.0f : -1.0f;
+        mbar_wait(&bars[s], (phase >> s) & 1);
+        phase ^= 1u << s;
+        const float* row = s_stage + (size_t)s * KS;
+        float t[KPL];
+        float S = 0.f;
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+          const uint32_t kk = lane + 32 * i;
+          if (EXACT || kk < KS) {
+            t[i] = fmaf(row[kk], sgn * fb[i], e);
+            S = fmaf(s_own[kk], t[i], S);
+          } else {
+            t[i] = 0.f;
+          }
+        }
+        __syncwarp();
+        {
+          const uint32_t q = j + STAGES;
+          if (q < a.n && lane == (q & 31)) {
+            const float* src = ((q >> 5) == (j >> 5)) ? cur_ptr : nxt_ptr;
+            mbar_expect_tx(&bars[s], seg_bytes);
+            bulk_g2s(s_stage + (size_t)s * KS, src, seg_bytes, &bars[s]);
+          }
+        }
+        S = warp_sum(S);
+        float* part = s_part + (j & 1) * T;
+        if (lane == 0) part[w] = S;
+        team_barrier(bar_id, bar_threads);
+        S = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < T; ++ww) S += part[ww];
+        const float inv = 1.0f / (S * phi_sum);
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) g[i] += fmaf(t[i], inv, -rphi);
+      }
+
+      float* out = a.phi_vec + (size_t)slot * K + seg;
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const uint32_t kk = lane + 32 * i;
+        if (EXACT || kk < KS) {
+          const float noise = a.disable_noise ? 1.0f : out[kk];
+          const float phi_k = s_own[kk] * phi_sum;
+          float v = fabsf(phi_k + half_eps * (a.alpha - phi_k + a.Nn * g[i]) + sqrtf(a.eps_t * phi_k) * noise);
+          v = fmaxf(v, 1e-24f);
+          out[kk] = v;
+          lsum += v;
+        }
+      }
+      lsum = warp_sum(lsum);
+      float* part = s_part + 2 * T;
+      if (lane == 0) part[w] = lsum;
+      team_barrier(bar_id, bar_threads);
+      if (w == 0 && lane == 0) {
+        float tot = 0.f;
+        for (int ww = 0; ww < T; ++ww) tot += part[ww];
+        a.phi_sum[slot] = tot;
+      }
+      // `part` is rewritten only after the next slot's first in-loop barrier pair: safe
+    }
+  }
+}
+
 // number of units (and so of concurrently useful warps / CTAs) this rank owns
 static uint32_t my_units(const PhiArgs& a) {
   const uint32_t active = a.units < a.V ? a.units : a.V;
@@ -332,6 +531,27 @@ static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   const uint32_t resident = (uint32_t)occ * c->sm_count;
   if (blocks > resident) blocks = resident;  // persistent: one wave, warps stride over units
   kern<<<blocks, WARPS * 32, smem, c->stream>>>(a);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int KPL, int STAGES, int T>
+static int launch_team(ammsb_ctx* c, const PhiArgs& a) {
+  const uint32_t KS = a.K / T;
+  const size_t smem = (size_t)4 * (STAGES + 1) * KS * 4 + (size_t)4 * (STAGES + 1) * 8 + (size_t)(4 / T) * 3 * T * 4;
+  const bool exact = (KS == 32u * KPL);
+  auto kern = exact ? k_update_phi_team<KPL, STAGES, T, true> : k_update_phi_team<KPL, STAGES, T, false>;
+  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));
+  AMMSB_REQUIRE(occ > 0, "update_phi: team kernel does not fit on an SM");
+  const uint32_t active = my_units(a);
+  if (active == 0) return 0;
+  const uint32_t teams_per_cta = 4 / T;
+  uint32_t blocks = (active + teams_per_cta - 1) / teams_per_cta;
+  const uint32_t resident = (uint32_t)occ * c->sm_count;
+  if (blocks > resident) blocks = resident;
+  kern<<<blocks, 128, smem, c->stream>>>(a);
   AMMSB_LAUNCH_CHECK();
   return 0;
 }
@@ -397,6 +617,11 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
     if (kpl <= 8) return launch_fast<8, 6, 4>(c, a);
     if (kpl <= 16) return launch_fast<16, 4, 4>(c, a);
     return launch_fast<32, 3, 4>(c, a);
+  }
+  // K in (1024, 4096]: teams of 2 or 4 warps per slot (one slot per unit, i.e. V <= 65535)
+  if (!o->strict && V <= a.units && p->K > 1024 && p->K <= 4096) {
+    if (p->K <= 2048 && p->K % 8 == 0) return launch_team<32, 3, 2>(c, a);
+    if (p->K % 16 == 0) return launch_team<32, 3, 4>(c, a);
   }
   const uint32_t vw = o->mode == AMMSB_MODE_THREAD ? 1u : o->wg;
   const size_t smem = sizeof(float) * (3 * (size_t)p->K + vw);

@@ -197,7 +197,7 @@ def phi_scale(prob, r, step=3):
     return np.abs(r["want"]) + phi_old + g_scale + np.abs(r["want"] - phi_old)
 
 
-@pytest.mark.parametrize("K", [64, 96, 256, 1024])
+@pytest.mark.parametrize("K", [64, 96, 256, 1024, 1536, 2048, 4096])
 @pytest.mark.parametrize("noise", [False, True])
 def test_update_phi_fast_vs_oracle(ctx, orc, K, noise):
     prob = link_heavy_problem(orc, 600, K, 32)
@@ -369,7 +369,7 @@ def test_update_phi_partition_is_rank_invariant(ctx, orc, parts, strict):
     """The slots of each rank (unit % parts == rank), launched one rank after the other on one
     GPU, reproduce the single-launch phi_vec / RNG pool / pi bit for bit: a unit's Langevin
     state is owned by exactly one rank, so the result cannot depend on the GPU count."""
-    K, V, n = 128, 203, 8
+    K, V, n = (128 if parts != 3 else 2048), 203, 8
     prob = link_heavy_problem(orc, 600, K, n)
     nodes = prob.minibatch_nodes(V, 4)
     neighbors, _ = orc.neighbor_sample(orc.rng_pool(V * 2 * n, 56, 57), nodes, prob.N, n, 32)
