@@ -136,7 +136,11 @@ __global__ void __launch_bounds__(128) k_update_phi_strict(const __grid_constant
 
 // -------------------------------------------------------------------- fast ---
 
-template <int KPL, int STAGES, int WARPS, bool EXACT>
+// NB = neighbors per loop trip.  For short rows (K <= 512) the per-neighbor fixed cost (barrier
+// wait, shuffle tree, reciprocal, refill) dominates the issue slots; NB = 2 interleaves two
+// neighbors (two shuffle trees in flight, own row kept in registers) without changing any
+// result: every sum is formed in the same order as with NB = 1.
+template <int KPL, int STAGES, int WARPS, bool EXACT, int NB>
 __global__ void __launch_bounds__(WARPS * 32)
     k_update_phi_fast(const __grid_constant__ PhiArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
@@ -213,7 +217,15 @@ __global__ void __launch_bounds__(WARPS * 32)
       mbar_wait(&bars[STAGES], (phase >> STAGES) & 1);
       phase ^= 1u << STAGES;
 
-      for (uint32_t j = 0; j < a.n; ++j) {
+      float own[NB == 2 ? KPL : 1];
+      if (NB == 2) {
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+          const uint32_t k = lane + 32 * i;
+          own[NB == 2 ? i : 0] = (EXACT || k < K) ? s_own[k] : 0.f;
+        }
+      }
+      for (uint32_t j = 0; j < a.n; j += NB) {
         const uint32_t jj = j & 31;
         if (jj == 0 && j > 0) {
           cur_ptr = nxt_ptr;
@@ -227,51 +239,73 @@ __global__ void __launch_bounds__(WARPS * 32)
           }
           nxt_mask = __ballot_sync(FULL_MASK, y);
         }
-        const uint32_t s = j % STAGES;
-        const bool y = (cur_mask >> jj) & 1;
-        const float e = y ? e_link : e_non;
-        mbar_wait(&bars[s], (phase >> s) & 1);
-        phase ^= 1u << s;
-        const float* row = s_stage + (size_t)s * K;
-        float t[KPL];
-        float S = 0.f;
-        if (y) {
+        float t[NB][KPL];
+        float S[NB];
+        bool live[NB];
 #pragma unroll
-          for (int i = 0; i < KPL; ++i) {
-            const uint32_t k = lane + 32 * i;
-            if (EXACT || k < K) {
-              t[i] = fmaf(row[k], fb[i], e);
-              S = fmaf(s_own[k], t[i], S);
-            } else {
-              t[i] = 0.f;
-            }
-          }
-        } else {
+        for (int u = 0; u < NB; ++u) {
+          live[u] = (u == 0) || (j + u < a.n);
+          S[u] = 0.f;
+          if (live[u]) {
+            const uint32_t s = (j + u) % STAGES;
+            const bool y = (cur_mask >> (jj + u)) & 1;
+            const float e = y ? e_link : e_non;
+            mbar_wait(&bars[s], (phase >> s) & 1);
+            phase ^= 1u << s;
+            const float* row = s_stage + (size_t)s * K;
+            if (y) {  // warp-uniform: the sign of f_k folds into the FMA
 #pragma unroll
-          for (int i = 0; i < KPL; ++i) {
-            const uint32_t k = lane + 32 * i;
-            if (EXACT || k < K) {
-              t[i] = fmaf(row[k], -fb[i], e);
-              S = fmaf(s_own[k], t[i], S);
+              for (int i = 0; i < KPL; ++i) {
+                const uint32_t k = lane + 32 * i;
+                if (EXACT || k < K) {
+                  t[u][i] = fmaf(row[k], fb[i], e);
+                  S[u] = fmaf(NB == 2 ? own[NB == 2 ? i : 0] : s_own[k], t[u][i], S[u]);
+                } else {
+                  t[u][i] = 0.f;
+                }
+              }
             } else {
-              t[i] = 0.f;
+#pragma unroll
+              for (int i = 0; i < KPL; ++i) {
+                const uint32_t k = lane + 32 * i;
+                if (EXACT || k < K) {
+                  t[u][i] = fmaf(row[k], -fb[i], e);
+                  S[u] = fmaf(NB == 2 ? own[NB == 2 ? i : 0] : s_own[k], t[u][i], S[u]);
+                } else {
+                  t[u][i] = 0.f;
+                }
+              }
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) t[u][i] = 0.f;
           }
         }
-        __syncwarp();  // every lane has consumed the stage -> refill it
-        {
-          const uint32_t q = j + STAGES;
-          if (q < a.n && lane == (q & 31)) {
+        __syncwarp();  // every lane has consumed the stage(s) -> refill
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const uint32_t q = j + u + STAGES;
+          if (live[u] && q < a.n && lane == (q & 31)) {
+            const uint32_t s = (j + u) % STAGES;
             const float* src = ((q >> 5) == (j >> 5)) ? cur_ptr : nxt_ptr;
             mbar_expect_tx(&bars[s], row_bytes);
             bulk_g2s(s_stage + (size_t)s * K, src, row_bytes, &bars[s]);
           }
         }
-        S = warp_sum(S);
-        // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
-        const float inv = 1.0f / (S * phi_sum);
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) g[i] += fmaf(t[i], inv, -rphi);
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < NB; ++u) S[u] += __shfl_xor_sync(FULL_MASK, S[u], o);
+        }
+        // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          if (live[u]) {
+            const float inv = 1.0f / (S[u] * phi_sum);
+#pragma unroll
+            for (int i = 0; i < KPL; ++i) g[i] += fmaf(t[u][i], inv, -rphi);
+          }
+        }
       }
 
       // Langevin noise (phi.cc:266-274) in the reference's per-state draw order
@@ -515,12 +549,12 @@ static uint32_t my_units(const PhiArgs& a) {
   return active > a.part_index ? (active - a.part_index + a.part_count - 1) / a.part_count : 0;
 }
 
-template <int KPL, int STAGES, int WARPS>
+template <int KPL, int STAGES, int WARPS, int NB = 1>
 static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   const size_t smem = (size_t)WARPS * (STAGES + 1) * a.K * 4 + (size_t)WARPS * (STAGES + 1) * 8;
   const bool exact = (a.K == 32u * KPL);
-  auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true>
-                    : k_update_phi_fast<KPL, STAGES, WARPS, false>;
+  auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB>
+                    : k_update_phi_fast<KPL, STAGES, WARPS, false, NB>;
   AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
@@ -612,10 +646,10 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
   const bool fast_ok = !o->strict && (p->K % 4 == 0) && p->K <= 1024;
   if (fast_ok) {
     const uint32_t kpl = (p->K + 31) / 32;
-    if (kpl <= 2) return launch_fast<2, 8, 4>(c, a);
-    if (kpl <= 4) return launch_fast<4, 8, 4>(c, a);
-    if (kpl <= 8) return launch_fast<8, 6, 4>(c, a);
-    if (kpl <= 16) return launch_fast<16, 4, 4>(c, a);
+    if (kpl <= 2) return launch_fast<2, 8, 4, 2>(c, a);
+    if (kpl <= 4) return launch_fast<4, 8, 4, 2>(c, a);
+    if (kpl <= 8) return launch_fast<8, 6, 4, 2>(c, a);
+    if (kpl <= 16) return launch_fast<16, 4, 4>(c, a);  // NB = 2 costs occupancy here (measured -6%)
     return launch_fast<32, 3, 4>(c, a);
   }
   // K in (1024, 4096]: teams of 2 or 4 warps per slot (one slot per unit, i.e. V <= 65535)
