@@ -103,6 +103,15 @@ int ammsb_host_free(void* h_ptr);
 int ammsb_timer_start(ammsb_ctx* ctx);
 int ammsb_timer_stop_ms(ammsb_ctx* ctx, float* ms); /* waits for the stop event */
 
+/* ---- completion markers: clcuda::Event as a synchronisation point (Kernel::Launch's last
+ *      argument).  record = "everything enqueued on ctx so far"; sync waits for it on the host
+ *      without draining later work, which lets a caller keep the stream fed. ---- */
+typedef struct ammsb_event ammsb_event;
+int ammsb_event_create(ammsb_ctx* ctx, ammsb_event** out);
+int ammsb_event_record(ammsb_ctx* ctx, ammsb_event* ev);
+int ammsb_event_sync(ammsb_event* ev);
+int ammsb_event_destroy(ammsb_event* ev);
+
 /* ---- RNG pool: OpenClRandomFactory::CreateRandom(size, seed) (random.h:44-58),
  *      RandomInit kernel (random.cc:31-44): state[i] = (seed_x + i, seed_y + i) ---- */
 int ammsb_rng_create(ammsb_ctx* ctx, uint64_t num_states, uint64_t seed_x,

@@ -164,6 +164,35 @@ extern "C" int ammsb_timer_stop_ms(ammsb_ctx* c, float* ms) {
   return 0;
 }
 
+struct ammsb_event {
+  int device;
+  cudaEvent_t ev;
+};
+extern "C" int ammsb_event_create(ammsb_ctx* c, ammsb_event** out) {
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ammsb_event* e = new ammsb_event();
+  e->device = c->device;
+  AMMSB_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming));
+  *out = e;
+  return 0;
+}
+extern "C" int ammsb_event_record(ammsb_ctx* c, ammsb_event* e) {
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  AMMSB_CHECK_CUDA(cudaEventRecord(e->ev, c->stream));
+  return 0;
+}
+extern "C" int ammsb_event_sync(ammsb_event* e) {
+  AMMSB_CHECK_CUDA(cudaEventSynchronize(e->ev));
+  return 0;
+}
+extern "C" int ammsb_event_destroy(ammsb_event* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaEventDestroy(e->ev);
+  delete e;
+  return 0;
+}
+
 // ---- cuckoo set ----
 static const uint64_t kSetPrimes[4][2] = {  // cuckoo.cc:30-35
     {15485807ull, 920429591ull},

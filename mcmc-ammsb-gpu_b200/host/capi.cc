@@ -249,14 +249,13 @@ int mcmc_learner_peek(void* vb, uint64_t* edges, uint64_t* n_edges, uint32_t* no
                       uint32_t* neighbors /* [n_nodes, n] */, uint32_t n, float* weight) {
   return Guard([&] {
     LearnerBox* b = static_cast<LearnerBox*>(vb);
-    const Sample& s = b->learner->PeekNextSample();
-    *weight = b->learner->PeekNextWeight();
+    const SampleSlot& s = b->learner->PeekNextSample();
+    *weight = s.weight;
     *n_edges = s.edges.size();
     *n_nodes = s.nodes_vec.size();
     std::memcpy(edges, s.edges.data(), 8 * s.edges.size());
     std::memcpy(nodes, s.nodes_vec.data(), 4 * s.nodes_vec.size());
-    Sample& ms = const_cast<Sample&>(s);
-    ms.neighbor_sampler.GetData().Read(ms.queue, s.nodes_vec.size() * n, neighbors);
+    s.neighbors.Read(b->queue, s.nodes_vec.size() * n, neighbors);
   });
 }
 int mcmc_learner_serialize(void* vb, const char* path) {

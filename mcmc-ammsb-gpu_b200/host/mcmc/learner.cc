@@ -11,79 +11,6 @@ using namespace std::chrono;
 
 namespace mcmc {
 
-SamplerThread::SamplerThread() : thread_(&SamplerThread::Loop, this) {}
-
-SamplerThread::~SamplerThread() {
-  {
-    std::unique_lock<std::mutex> lock(mu_);
-    stop_ = true;
-  }
-  cv_.notify_all();
-  thread_.join();
-}
-
-void SamplerThread::Loop() {
-  std::unique_lock<std::mutex> lock(mu_);
-  for (;;) {
-    cv_.wait(lock, [this] { return has_task_ || stop_; });
-    if (has_task_) {
-      std::function<Float()> task = std::move(task_);
-      has_task_ = false;
-      lock.unlock();
-      Float r = 0;
-      std::exception_ptr err;
-      try {
-        r = task();
-      } catch (...) {
-        err = std::current_exception();
-      }
-      lock.lock();
-      result_ = r;
-      error_ = err;
-      done_ = true;
-      cv_.notify_all();
-    } else if (stop_) {
-      return;
-    }
-  }
-}
-
-void SamplerThread::Launch(std::function<Float()> task) {
-  wait();
-  {
-    std::unique_lock<std::mutex> lock(mu_);
-    task_ = std::move(task);
-    has_task_ = true;
-    done_ = false;
-    valid_ = true;
-  }
-  cv_.notify_all();
-}
-
-void SamplerThread::wait() {
-  if (!valid_) return;
-  std::unique_lock<std::mutex> lock(mu_);
-  cv_.wait(lock, [this] { return done_; });
-}
-
-Float SamplerThread::get() {
-  if (!valid_) throw BackendError("SamplerThread::get() without a launched task");
-  wait();
-  valid_ = false;
-  if (error_) {
-    std::exception_ptr e = error_;
-    error_ = nullptr;
-    std::rethrow_exception(e);
-  }
-  return result_;
-}
-
-void SamplerThread::Reset() {
-  wait();
-  valid_ = false;
-  error_ = nullptr;
-}
-
 namespace {
 typedef Float (*SamplerFn)(const Config&, std::vector<Edge>*, unsigned int*);
 SamplerFn PickSampler(SampleStrategy s) {
@@ -123,12 +50,13 @@ Learner::Learner(const Config& cfg, clcuda::Queue queue)
       time_(0),
       samplingTime_(0),
       edgesProcessed_(0),
-      h2dBytes_(0),
-      samples_{Sample(cfg_, queue_), Sample(cfg_, queue_)},
-      pendingWeight_{0, 0},
-      pendingValid_{false, false},
       phase_(0),
       betaMirror_(nullptr) {
+  for (auto& ev : iterDone_) AmmsbCheck(ammsb_event_create(queue_(), &ev));
+  for (auto& sample : samples_) {
+    sample.reset(new Sample(cfg_, queue_));  // seed = rand(), as in the reference (sample.cc:132)
+    sample->Start(sampler_, &stats_);
+  }
   // phi lives in a Buffer of its own in the reference; the store adopts that memory
   AmmsbCheck(ammsb_store_bind_phi(pi_->Get(), phi_.data()));
   // theta ~ Gamma(eta0, eta1) on the host, fixed seed; beta = theta row-normalised
@@ -142,46 +70,22 @@ Learner::Learner(const Config& cfg, clcuda::Queue queue)
 }
 
 Learner::~Learner() {
-  for (auto& f : futures_)
-    if (f.valid()) f.wait();
+  for (auto& ev : iterDone_) ammsb_event_destroy(ev);
 }
 
 Float Learner::SampleMiniBatch(std::vector<Edge>* edges, unsigned int* seed) { return sampler_(cfg_, edges, seed); }
 
-// host mini-batch -> device copies -> neighbor sampling, all on the Sample's own queue so
-// that it overlaps the previous iteration's kernels (reference learner.cc:175-194)
-Float Learner::DoSample(Sample* sample) {
-  const auto t0 = high_resolution_clock::now();
-  sample->edges.clear();
-  const Float weight = SampleMiniBatch(&sample->edges, &sample->seed);
-  const auto t1 = high_resolution_clock::now();
-  ExtractNodesFromMiniBatch(sample->edges, &sample->nodes_vec);
-  const auto t2 = high_resolution_clock::now();
-  if (sample->nodes_vec.empty()) throw BackendError("mini-batch size = 0!");
-  if (sample->edges.size() > sample->dev_edges.GetSize() / sizeof(Edge) ||
-      sample->nodes_vec.size() > sample->dev_nodes.GetSize() / sizeof(Vertex))
-    throw BackendError("mini-batch exceeds the device buffers");
-  sample->dev_edges.Write(sample->queue, sample->edges.size(), sample->edges.data());
-  sample->dev_nodes.Write(sample->queue, sample->nodes_vec.size(), sample->nodes_vec.data());
-  h2dBytes_ += sample->edges.size() * sizeof(Edge) + sample->nodes_vec.size() * sizeof(Vertex);
-  const auto t3 = high_resolution_clock::now();
-  sample->neighbor_sampler(static_cast<uint32_t>(sample->nodes_vec.size()), &sample->dev_nodes);
-  const auto t4 = high_resolution_clock::now();
-  tStrategy_ += duration_cast<nanoseconds>(t1 - t0).count();
-  tExtract_ += duration_cast<nanoseconds>(t2 - t1).count();
-  tCopy_ += duration_cast<nanoseconds>(t3 - t2).count();
-  tNeighbor_ += duration_cast<nanoseconds>(t4 - t3).count();
-  return weight;
-}
+const SampleSlot& Learner::PeekNextSample() { return samples_[phase_]->WaitReady(); }
 
-const Sample& Learner::PeekNextSample() {
-  LaunchSampler(phase_);
-  if (!pendingValid_[phase_]) {
-    pendingWeight_[phase_] = futures_[phase_].get();
-    pendingValid_[phase_] = true;
-  }
-  return samples_[phase_];
+namespace {
+// mini-batches of `stream` that are launched but not yet retired
+uint64_t CountInFlight(Sample* const* owner, uint64_t launched, uint64_t retired, const Sample* stream) {
+  uint64_t n = 0;
+  for (uint64_t k = retired; k < launched; ++k)
+    if (owner[k % 3] == stream) ++n;
+  return n;
 }
+}  // namespace
 
 Float Learner::HeldoutPerplexity() {
   const auto t1 = high_resolution_clock::now();
@@ -190,49 +94,47 @@ Float Learner::HeldoutPerplexity() {
   return std::exp(avg);
 }
 
-void Learner::LaunchSampler(int buffer) {
-  if (futures_[buffer].valid() || pendingValid_[buffer]) return;  // already drawn / being drawn
-  Sample* sample = &samples_[buffer];
-  futures_[buffer].Launch([this, sample] { return DoSample(sample); });
-}
-
 void Learner::Run(uint32_t max_iters, sig_atomic_t* signaled) {
   const auto t1 = high_resolution_clock::now();
-  LaunchSampler(phase_);
+  // This call consumes max_iters mini-batches, alternating between the two streams starting
+  // with `phase_`, and -- like the reference, which always has the next one in flight
+  // (learner.cc:228) -- leaves exactly one more drawn.  That is all the streams may draw.
+  const uint64_t total = static_cast<uint64_t>(max_iters) + 1;
+  samples_[phase_]->Allow((total + 1) / 2);
+  samples_[1 - phase_]->Allow(total / 2);
+  // The stream stays fed: up to kInFlight iterations are enqueued before the host waits for the
+  // oldest one (the reference drains the queue after every kernel).  A slot returns to its
+  // sampler stream when the iteration that read it has completed.
+  Sample* owner[kInFlight] = {nullptr};
+  uint64_t launched = 0, retired = 0;
+  auto retire_oldest = [&]() {
+    const auto td = high_resolution_clock::now();
+    AmmsbCheck(ammsb_event_sync(iterDone_[retired % kInFlight]));
+    tDrain_ += duration_cast<nanoseconds>(high_resolution_clock::now() - td).count();
+    owner[retired % kInFlight]->Release();
+    ++retired;
+  };
   for (uint64_t i = 0; i < max_iters && (signaled == nullptr || !*signaled); ++i, ++stepCount_) {
     const auto ts = high_resolution_clock::now();
-    Float weight;
-    if (pendingValid_[phase_]) {
-      weight = pendingWeight_[phase_];
-      pendingValid_[phase_] = false;
-    } else {
-      weight = futures_[phase_].get();
-    }
-    // kernels of iteration t still read samples_[phase_]; the other buffer is free
-    // (reference learner.cc:228: mini-batch t+1 is drawn while t is processed)
-    LaunchSampler(1 - phase_);
-    samplingTime_ += duration_cast<nanoseconds>(high_resolution_clock::now() - ts).count();
-
+    Sample& stream = *samples_[phase_];
+    // WaitReady() returns the oldest unreleased mini-batch of the stream: the ones still in
+    // flight on the GPU must be retired first if they belong to this stream's ring position
+    while (launched - retired >= static_cast<uint64_t>(kInFlight - 1)) retire_oldest();
+    SampleSlot& s = stream.WaitReady(/*skip=*/CountInFlight(owner, launched, retired, &stream));
     const auto tk = high_resolution_clock::now();
-    Sample& s = samples_[phase_];
-    phiUpdater_(s.dev_nodes, s.neighbor_sampler.GetData(), static_cast<uint32_t>(s.nodes_vec.size()));
-    betaUpdater_(&s.dev_edges, static_cast<uint32_t>(s.edges.size()), weight);
+    samplingTime_ += duration_cast<nanoseconds>(tk - ts).count();
+
+    phiUpdater_(s.dev_nodes, s.neighbors, static_cast<uint32_t>(s.nodes_vec.size()));
+    betaUpdater_(&s.dev_edges, static_cast<uint32_t>(s.edges.size()), s.weight);
     edgesProcessed_ += s.edges.size();
     if (betaMirror_ != nullptr) beta_.ReadAsync(queue_, 2 * cfg_.K, betaMirror_);
-    // the sampler thread reuses this buffer two iterations from now; drain before flipping
-    const auto td = high_resolution_clock::now();
-    queue_.Finish();
-    tKernelsHost_ += duration_cast<nanoseconds>(td - tk).count();
-    tDrain_ += duration_cast<nanoseconds>(high_resolution_clock::now() - td).count();
-    const int consumed = phase_;
+    AmmsbCheck(ammsb_event_record(queue_(), iterDone_[launched % kInFlight]));
+    owner[launched % kInFlight] = &stream;
+    ++launched;
+    tKernelsHost_ += duration_cast<nanoseconds>(high_resolution_clock::now() - tk).count();
     phase_ = 1 - phase_;
-    // The two Samples draw from independent seeds and RNG pools and sampling never reads
-    // the model, so mini-batch t+2 can be drawn into the buffer that has just been consumed
-    // while t+1 is still being drawn: same mini-batches, two sampler threads in flight.
-    // Only when iteration t+2 belongs to this Run() call, so that a caller (and Serialize)
-    // always finds the reference's state on return: exactly one mini-batch in flight.
-    if (i + 2 < max_iters && (signaled == nullptr || !*signaled)) LaunchSampler(consumed);
   }
+  while (retired < launched) retire_oldest();
   time_ += duration_cast<nanoseconds>(high_resolution_clock::now() - t1).count();
 }
 
@@ -252,10 +154,10 @@ void Learner::PrintStats() {
   line("GRADS SUM   : ", betaUpdater_.GradsSumTime() / 1.0e3);
   line("UPDATE THETA: ", betaUpdater_.UpdateThetaTime() / 1.0e3);
   line("NORM THETA  : ", betaUpdater_.NormalizeTime() / 1.0e3);
-  line("  sampler threads: strategy ", tStrategy_ / 1.0e9);
-  line("  sampler threads: extract  ", tExtract_ / 1.0e9);
-  line("  sampler threads: H2D      ", tCopy_ / 1.0e9);
-  line("  sampler threads: neighbors", tNeighbor_ / 1.0e9);
+  line("  sampler threads: strategy ", stats_.strategy / 1.0e9);
+  line("  sampler threads: extract  ", stats_.extract / 1.0e9);
+  line("  sampler threads: H2D      ", stats_.copy / 1.0e9);
+  line("  sampler threads: neighbors", stats_.neighbors / 1.0e9);
   line("  main thread: launches     ", tKernelsHost_ / 1.0e9);
   line("  main thread: drain        ", tDrain_ / 1.0e9);
   std::cerr << "ITERATIONS  : " << (stepCount_ - 1) << ", MINI-BATCH EDGES: " << edgesProcessed_ << std::endl;
@@ -264,26 +166,27 @@ void Learner::PrintStats() {
 // Record order of the reference (learner.cc:301-361): beta, theta, pi, phi, phi updater,
 // beta updater, perplexity, LearnerProperties, sample 0, sample 1.
 bool Learner::Serialize(std::ostream* out) {
-  PeekNextSample();  // drain the in-flight sampler so its state is final
-  if (futures_[1 - phase_].valid()) {  // only after a Run() cut short by `signaled`
-    pendingWeight_[1 - phase_] = futures_[1 - phase_].get();
-    pendingValid_[1 - phase_] = true;
-  }
+  // Drain the sampler streams.  After a Run() that ran to completion the state is the
+  // reference's: the next mini-batch (stream `phase_`) drawn and pending, the other stream's
+  // latest mini-batch consumed.  (A Run() cut short by `signaled` may leave more mini-batches
+  // drawn than the reference's format can carry; those are redrawn differently after Parse.)
+  samples_[phase_]->Allow(1);
+  samples_[phase_]->WaitReady();
+  samples_[0]->Quiesce();
+  samples_[1]->Quiesce();
   LearnerProperties props;
   props.stepCount = stepCount_;
   props.time = time_;
   props.samplingTime = samplingTime_;
   props.phase = phase_;
-  props.weight = pendingWeight_[phase_];
+  props.weight = samples_[phase_]->WaitReady().weight;
   return ::mcmc::Serialize(out, &beta_, &queue_) && ::mcmc::Serialize(out, &theta_, &queue_) &&
          SerializeRpm(out, pi_.get()) && ::mcmc::Serialize(out, &phi_, &queue_) && phiUpdater_.Serialize(out) &&
          betaUpdater_.Serialize(out) && heldoutPerplexity_.Serialize(out) && SerializeMessage(out, props) &&
-         samples_[0].Serialize(out) && samples_[1].Serialize(out);
+         samples_[0]->Serialize(out) && samples_[1]->Serialize(out);
 }
 
 bool Learner::Parse(std::istream* in) {
-  for (auto& f : futures_)
-    if (f.valid()) f.wait();
   LearnerProperties props;
   if (!(::mcmc::Parse(in, &beta_, &queue_) && ::mcmc::Parse(in, &theta_, &queue_) && ParseRpm(in, pi_.get()) &&
         ::mcmc::Parse(in, &phi_, &queue_) && phiUpdater_.Parse(in) && betaUpdater_.Parse(in) &&
@@ -293,12 +196,9 @@ bool Learner::Parse(std::istream* in) {
   time_ = props.time;
   samplingTime_ = props.samplingTime;
   phase_ = props.phase;
-  if (!(samples_[0].Parse(in) && samples_[1].Parse(in))) return false;
-  futures_[0].Reset();
-  futures_[1].Reset();
-  pendingValid_[0] = pendingValid_[1] = false;
-  pendingWeight_[phase_] = static_cast<Float>(props.weight);
-  pendingValid_[phase_] = true;
+  // the stream of `phase_` holds the pending next mini-batch, the other one a consumed one
+  if (!(samples_[0]->Parse(in, phase_ == 0) && samples_[1]->Parse(in, phase_ == 1))) return false;
+  samples_[phase_]->WaitReady().weight = static_cast<Float>(props.weight);
   return true;
 }
 

@@ -24,31 +24,6 @@
 
 namespace mcmc {
 
-// One persistent host thread per Sample buffer, with the interface of the std::future the
-// reference gets from std::async (learner.cc:216-229): Launch() = std::async, get()/wait()/
-// valid() as std::future.  Persistent so that the thread-local sampling arena and the CUDA
-// context binding are paid once, not per iteration.
-class SamplerThread {
- public:
-  SamplerThread();
-  ~SamplerThread();
-  void Launch(std::function<Float()> task);
-  bool valid() const { return valid_; }
-  void wait();
-  Float get();          // waits, rethrows a failure of the task, invalidates
-  void Reset();         // wait and discard
-
- private:
-  void Loop();
-  std::mutex mu_;
-  std::condition_variable cv_;
-  std::function<Float()> task_;
-  bool has_task_ = false, done_ = false, stop_ = false, valid_ = false;
-  Float result_ = 0;
-  std::exception_ptr error_;
-  std::thread thread_;
-};
-
 class Learner {
  public:
   // cfg is held by reference (as in the reference): it must outlive the Learner
@@ -70,18 +45,17 @@ class Learner {
   void ReadTheta(Float* host) { theta_.Read(queue_, 2 * cfg_.K, host); }
   uint32_t StepCount() const { return stepCount_; }
   uint64_t EdgesProcessed() const { return edgesProcessed_; }
-  uint64_t BytesH2D() const { return h2dBytes_; }  // mini-batch edges + nodes copied to the device so far
+  uint64_t BytesH2D() const { return stats_.h2d_bytes; }  // mini-batch edges + nodes copied to the device so far
   // when set (pinned host memory, 2K floats), every iteration ends with a device->host copy
   // of beta into it: the per-iteration result a monitoring caller reads
   void MirrorBetaTo(Float* pinned_host) { betaMirror_ = pinned_host; }
   // the mini-batch the next iteration will consume (joins the sampler thread)
-  const Sample& PeekNextSample();
-  Float PeekNextWeight() { PeekNextSample(); return pendingWeight_[phase_]; }
+  const SampleSlot& PeekNextSample();
+  Float PeekNextWeight() { return PeekNextSample().weight; }
+  Sample& SampleStream(int i) { return *samples_[i]; }
 
  private:
   Float SampleMiniBatch(std::vector<Edge>* edges, unsigned int* seed);
-  void LaunchSampler(int buffer);
-  Float DoSample(Sample* sample);
 
   const Config& cfg_;
   clcuda::Queue queue_;
@@ -104,13 +78,11 @@ class Learner {
   uint64_t time_;
   uint64_t samplingTime_;
   uint64_t edgesProcessed_;
-  std::atomic<uint64_t> h2dBytes_;
-  // sampler-thread time by stage, ns (host strategy, node extraction, H2D copies, neighbor kernel)
-  std::atomic<uint64_t> tStrategy_{0}, tExtract_{0}, tCopy_{0}, tNeighbor_{0}, tKernelsHost_{0}, tDrain_{0};
-  Sample samples_[2];
-  SamplerThread futures_[2];
-  Float pendingWeight_[2];
-  bool pendingValid_[2];
+  SamplerStats stats_;  // sampler-thread time by stage, bytes copied
+  uint64_t tKernelsHost_ = 0, tDrain_ = 0;  // main thread: launching / waiting for the GPU (ns)
+  std::unique_ptr<Sample> samples_[2];  // two sampler streams, alternating (learner.h:64)
+  static const int kInFlight = 3;       // iterations enqueued before the host waits for the oldest
+  ammsb_event* iterDone_[kInFlight];
   int phase_;
   Float* betaMirror_;
 };

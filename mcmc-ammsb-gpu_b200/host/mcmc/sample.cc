@@ -1,6 +1,7 @@
 #include "mcmc/sample.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cctype>
 #include <queue>
 #include <unordered_set>
@@ -293,32 +294,187 @@ bool NeighborSampler::Serialize(std::ostream* out) {
 }
 bool NeighborSampler::Parse(std::istream* in) { return rand_->Parse(in) && ::mcmc::Parse(in, &data_, &queue_); }
 
-Sample::Sample(const Config& cfg, clcuda::Queue q)
-    : queue(q.GetContext(), q.GetDevice()),
-      dev_edges(q.GetContext(), MaxMiniBatchEdges(cfg)),
-      dev_nodes(q.GetContext(), MaxMiniBatchNodes(cfg)),
-      seed(rand()),
-      neighbor_sampler(cfg, clcuda::Queue(q.GetContext(), q.GetDevice())) {}
-
-bool Sample::Serialize(std::ostream* out) {
-  SampleStorage s;
-  s.edges.assign(reinterpret_cast<const char*>(edges.data()), edges.size() * sizeof(Edge));
-  s.nodes_vec.assign(reinterpret_cast<const char*>(nodes_vec.data()), nodes_vec.size() * sizeof(Vertex));
-  s.seed = seed;
-  return SerializeMessage(out, s) && ::mcmc::Serialize(out, &dev_edges, &queue) &&
-         ::mcmc::Serialize(out, &dev_nodes, &queue) && neighbor_sampler.Serialize(out);
+void NeighborSampler::operator()(uint32_t num_samples, clcuda::Buffer<Vertex>* nodes, clcuda::Buffer<Vertex>* out) {
+  AmmsbCheck(ammsb_neighbor_sample(queue_(), rand_->Get(), nodes->data(), num_samples,
+                                   static_cast<uint32_t>(cfg_.N), static_cast<uint32_t>(cfg_.num_node_sample),
+                                   local_, data_.data(), export_hash_ ? hash_.data() : nullptr));
+  data_.CopyTo(queue_, static_cast<size_t>(num_samples) * cfg_.num_node_sample, *out);
+  queue_.Finish();
 }
 
-bool Sample::Parse(std::istream* in) {
+SampleSlot::SampleSlot(const Config& cfg, const clcuda::Context& ctx)
+    : dev_edges(ctx, MaxMiniBatchEdges(cfg)),
+      dev_nodes(ctx, MaxMiniBatchNodes(cfg)),
+      neighbors(ctx, MaxMiniBatchNodes(cfg) * cfg.num_node_sample) {}
+
+Sample::Sample(const Config& cfg, clcuda::Queue q)
+    : queue(q.GetContext(), q.GetDevice()),
+      seed(rand()),
+      neighbor_sampler(cfg, clcuda::Queue(q.GetContext(), q.GetDevice())),
+      cfg_(cfg) {
+  for (uint64_t i = 0; i < kRing; ++i) ring.emplace_back(new SampleSlot(cfg, q.GetContext()));
+}
+
+Sample::~Sample() {
+  {
+    std::unique_lock<std::mutex> lock(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  if (a_.joinable()) a_.join();
+  if (b_.joinable()) b_.join();
+}
+
+void Sample::Start(Strategy strategy, SamplerStats* stats) {
+  strategy_ = strategy;
+  stats_ = stats;
+  a_ = std::thread(&Sample::StageA, this);
+  b_ = std::thread(&Sample::StageB, this);
+}
+
+namespace {
+inline uint64_t NowNs() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+}  // namespace
+
+// stage A: the host strategy (sample.cc:177-302 of the reference), the only consumer of `seed`
+void Sample::StageA() {
+  std::unique_lock<std::mutex> lock(mu_);
+  for (;;) {
+    cv_.wait(lock, [this] { return stop_ || (drawn_ < allowed_ && drawn_ - consumed_ < kRing && !error_); });
+    if (stop_) return;
+    SampleSlot& slot = *ring[drawn_ % kRing];
+    a_busy_ = true;
+    lock.unlock();
+    std::exception_ptr err;
+    const uint64_t t0 = NowNs();
+    try {
+      slot.edges.clear();
+      slot.weight = strategy_(cfg_, &slot.edges, &seed);
+    } catch (...) {
+      err = std::current_exception();
+    }
+    stats_->strategy += NowNs() - t0;
+    lock.lock();
+    a_busy_ = false;
+    if (err) error_ = err; else ++drawn_;
+    cv_.notify_all();
+  }
+}
+
+// stage B: ExtractNodesFromMiniBatch + Buffer::Write x2 + NeighborSampler (learner.cc:175-194)
+void Sample::StageB() {
+  std::unique_lock<std::mutex> lock(mu_);
+  for (;;) {
+    cv_.wait(lock, [this] { return stop_ || (ready_ < drawn_ && !error_); });
+    if (stop_) return;
+    SampleSlot& slot = *ring[ready_ % kRing];
+    lock.unlock();
+    std::exception_ptr err;
+    try {
+      const uint64_t t0 = NowNs();
+      ExtractNodesFromMiniBatch(slot.edges, &slot.nodes_vec);
+      const uint64_t t1 = NowNs();
+      if (slot.nodes_vec.empty()) throw BackendError("mini-batch size = 0!");
+      if (slot.edges.size() > slot.dev_edges.GetSize() / sizeof(Edge) ||
+          slot.nodes_vec.size() > slot.dev_nodes.GetSize() / sizeof(Vertex))
+        throw BackendError("mini-batch exceeds the device buffers");
+      slot.dev_edges.Write(queue, slot.edges.size(), slot.edges.data());
+      slot.dev_nodes.Write(queue, slot.nodes_vec.size(), slot.nodes_vec.data());
+      const uint64_t t2 = NowNs();
+      neighbor_sampler(static_cast<uint32_t>(slot.nodes_vec.size()), &slot.dev_nodes, &slot.neighbors);
+      const uint64_t t3 = NowNs();
+      stats_->extract += t1 - t0;
+      stats_->copy += t2 - t1;
+      stats_->neighbors += t3 - t2;
+      stats_->h2d_bytes += slot.edges.size() * sizeof(Edge) + slot.nodes_vec.size() * sizeof(Vertex);
+    } catch (...) {
+      err = std::current_exception();
+    }
+    lock.lock();
+    if (err) error_ = err; else ++ready_;
+    cv_.notify_all();
+  }
+}
+
+void Sample::Allow(uint64_t more) {
+  std::unique_lock<std::mutex> lock(mu_);
+  if (consumed_ + more > allowed_) allowed_ = consumed_ + more;
+  cv_.notify_all();
+}
+
+SampleSlot& Sample::WaitReady(uint64_t skip) {
+  std::unique_lock<std::mutex> lock(mu_);
+  const uint64_t want = consumed_ + skip;  // index of the mini-batch to hand out
+  if (allowed_ < want + 1) {
+    allowed_ = want + 1;
+    cv_.notify_all();
+  }
+  cv_.wait(lock, [&] { return ready_ > want || error_; });
+  if (ready_ <= want) {
+    std::exception_ptr e = error_;
+    error_ = nullptr;
+    std::rethrow_exception(e);
+  }
+  return *ring[want % kRing];
+}
+
+void Sample::Release() {
+  std::unique_lock<std::mutex> lock(mu_);
+  ++consumed_;
+  cv_.notify_all();
+}
+
+uint64_t Sample::Quiesce() {
+  std::unique_lock<std::mutex> lock(mu_);
+  // a draw that stage A has already started cannot be cancelled: let it land, start no other
+  allowed_ = std::min(allowed_, drawn_ + (a_busy_ ? 1 : 0));
+  cv_.wait(lock, [this] { return error_ || (!a_busy_ && ready_ == drawn_); });
+  allowed_ = drawn_;
+  return ready_ - consumed_;
+}
+
+SampleSlot& Sample::Latest() {
+  std::unique_lock<std::mutex> lock(mu_);
+  return *ring[(drawn_ + kRing - 1) % kRing];
+}
+
+// The reference's record for a Sample (sample.h:62-75): SampleStorage{edges, nodes_vec, seed},
+// dev_edges, dev_nodes, then the NeighborSampler (RNG pool, neighbor data) -- of the most
+// recently drawn mini-batch of this stream.  Call Quiesce() first.
+bool Sample::Serialize(std::ostream* out) {
+  SampleSlot& slot = Latest();
   SampleStorage s;
-  if (!(ParseMessage(in, &s) && ::mcmc::Parse(in, &dev_edges, &queue) && ::mcmc::Parse(in, &dev_nodes, &queue) &&
-        neighbor_sampler.Parse(in)))
+  s.edges.assign(reinterpret_cast<const char*>(slot.edges.data()), slot.edges.size() * sizeof(Edge));
+  s.nodes_vec.assign(reinterpret_cast<const char*>(slot.nodes_vec.data()), slot.nodes_vec.size() * sizeof(Vertex));
+  s.seed = seed;
+  return SerializeMessage(out, s) && ::mcmc::Serialize(out, &slot.dev_edges, &queue) &&
+         ::mcmc::Serialize(out, &slot.dev_nodes, &queue) && neighbor_sampler.Serialize(out);
+}
+
+bool Sample::Parse(std::istream* in, bool pending) {
+  Quiesce();
+  std::unique_lock<std::mutex> lock(mu_);
+  // restart the counters: the parsed mini-batch lands in slot 0
+  drawn_ = ready_ = 1;
+  consumed_ = pending ? 0 : 1;
+  allowed_ = drawn_;
+  SampleSlot& slot = *ring[0];
+  SampleStorage s;
+  if (!(ParseMessage(in, &s) && ::mcmc::Parse(in, &slot.dev_edges, &queue) &&
+        ::mcmc::Parse(in, &slot.dev_nodes, &queue) && neighbor_sampler.Parse(in)))
     return false;
-  edges.resize(s.edges.size() / sizeof(Edge));
-  std::memcpy(edges.data(), s.edges.data(), edges.size() * sizeof(Edge));
-  nodes_vec.resize(s.nodes_vec.size() / sizeof(Vertex));
-  std::memcpy(nodes_vec.data(), s.nodes_vec.data(), nodes_vec.size() * sizeof(Vertex));
+  slot.edges.resize(s.edges.size() / sizeof(Edge));
+  std::memcpy(slot.edges.data(), s.edges.data(), slot.edges.size() * sizeof(Edge));
+  slot.nodes_vec.resize(s.nodes_vec.size() / sizeof(Vertex));
+  std::memcpy(slot.nodes_vec.data(), s.nodes_vec.data(), slot.nodes_vec.size() * sizeof(Vertex));
   seed = s.seed;
+  // neighbor data of the parsed mini-batch: the sampler's buffer holds it (sample.h:30-36)
+  neighbor_sampler.GetData().CopyTo(queue, slot.nodes_vec.size() * neighbor_sampler.DataSizePerSample(),
+                                    slot.neighbors);
+  queue.Finish();
   return true;
 }
 

@@ -6,8 +6,13 @@
 #ifndef MCMC_B200_SAMPLE_H_
 #define MCMC_B200_SAMPLE_H_
 
+#include <atomic>
+#include <condition_variable>
+#include <exception>
 #include <iostream>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -43,6 +48,8 @@ class NeighborSampler {
 
   // draws cfg.num_node_sample distinct neighbors != node for the first num_samples nodes
   void operator()(uint32_t num_samples, clcuda::Buffer<Vertex>* nodes);
+  // same, and a copy of the result into `out` (a ring slot); GetData() keeps the latest result
+  void operator()(uint32_t num_samples, clcuda::Buffer<Vertex>* nodes, clcuda::Buffer<Vertex>* out);
 
   clcuda::Buffer<Vertex>& GetHash() { return hash_; }
   clcuda::Buffer<Vertex>& GetData() { return data_; }
@@ -67,19 +74,72 @@ class NeighborSampler {
   bool export_hash_ = false;
 };
 
-// one in-flight mini-batch: host vectors, device copies, its own queue and sampler
-struct Sample {
-  clcuda::Queue queue;
+// host time spent by the sampler threads, by stage (ns), and bytes copied to the device
+struct SamplerStats {
+  std::atomic<uint64_t> strategy{0}, extract{0}, copy{0}, neighbors{0}, h2d_bytes{0};
+};
+
+// one drawn mini-batch: host vectors and their device copies
+struct SampleSlot {
   std::vector<Edge> edges;
-  clcuda::Buffer<Edge> dev_edges;
   std::vector<Vertex> nodes_vec;
+  clcuda::Buffer<Edge> dev_edges;
   clcuda::Buffer<Vertex> dev_nodes;
+  clcuda::Buffer<Vertex> neighbors;  // [nodes, num_node_sample]
+  Float weight = 0;
+  SampleSlot(const Config& cfg, const clcuda::Context& ctx);
+};
+
+// One sampler stream (the reference's struct Sample, sample.h:51-92: its own seed, queue and
+// NeighborSampler with its own RNG pool).  The Learner alternates between two of them.
+//
+// The reference draws mini-batch t+1 on one std::async thread while t is processed
+// (learner.cc:216-232).  Here each stream is a two-stage pipeline over a small ring of slots,
+//   stage A (thread): host strategy with the stream's seed           -> slot.edges, weight
+//   stage B (thread): node extraction, H2D copies, neighbor sampling -> device buffers
+// so several mini-batches of a stream are in flight.  Nothing in either stage reads the model,
+// and each stage handles the stream's mini-batches strictly in order (seed and RNG pool advance
+// exactly as in the reference), so the mini-batches are the same; only how far ahead they are
+// drawn differs.  `Allow()` bounds that: a Run(n) call lets the streams draw only the n
+// mini-batches it consumes plus the one the reference leaves in flight, so the state seen by
+// Serialize() on return is the reference's.
+struct Sample {
+  typedef Float (*Strategy)(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed);
+  static const uint64_t kRing = 4;
+
+  clcuda::Queue queue;
+  std::vector<std::unique_ptr<SampleSlot>> ring;
   unsigned int seed;
   NeighborSampler neighbor_sampler;
 
   Sample(const Config& cfg, clcuda::Queue queue);
+  ~Sample();
+  void Start(Strategy strategy, SamplerStats* stats);
+  // let the stream draw until `more` mini-batches beyond the consumed ones exist
+  void Allow(uint64_t more);
+  // the oldest drawn-but-unconsumed mini-batch, fully on the device (blocks; rethrows a failure);
+  // skip = mini-batches handed out earlier and not yet Release()d (still read by the GPU)
+  SampleSlot& WaitReady(uint64_t skip = 0);
+  void Release();  // the mini-batch returned by WaitReady() has been consumed
+  // stop drawing and wait for the stages to drain; returns the number of pending mini-batches
+  uint64_t Quiesce();
+  SampleSlot& Latest();  // most recently drawn mini-batch (the reference's Sample contents)
   bool Serialize(std::ostream* out);
-  bool Parse(std::istream* in);
+  // pending: the parsed mini-batch is the next one to consume (else it was already consumed)
+  bool Parse(std::istream* in, bool pending);
+
+ private:
+  void StageA();
+  void StageB();
+  const Config& cfg_;
+  Strategy strategy_ = nullptr;
+  SamplerStats* stats_ = nullptr;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  uint64_t drawn_ = 0, ready_ = 0, consumed_ = 0, allowed_ = 0;  // mini-batches of this stream
+  bool stop_ = false, a_busy_ = false;
+  std::exception_ptr error_;
+  std::thread a_, b_;
 };
 
 }  // namespace mcmc
