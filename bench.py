@@ -503,10 +503,16 @@ def run_b200(args, w):
 def main():
     args = parse_args()
     w = workload(args)
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner)
+    # are sent to stderr; print() keeps writing to the real stdout through sys.stdout
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args, w)
     else:
         run_b200(args, w)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":

@@ -9,6 +9,8 @@
 //   k_update_phi_strict  any K / wg / mode; evaluates every expression in the
 //                        reference's order with IEEE round-to-nearest ops and no FMA
 //                        contraction.  It is the on-device twin of the CPU oracle.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 struct PhiArgs {
@@ -136,27 +138,114 @@ __global__ void __launch_bounds__(128) k_update_phi_strict(const __grid_constant
 
 // -------------------------------------------------------------------- fast ---
 
+// ---- Langevin-noise producer warps (warp specialisation) ----
+//
+// A unit's noise stream is sequential (ziggurat over xorshift128+, ~32 dependent draws per lane
+// and slot) and touches no memory: when the warp that gathers rows draws it itself it has no
+// loads in flight for ~12% of its time.  With NW > 0 the CTA carries NW extra warps that only
+// draw noise: producer p serves compute warps p, p+NW, ..., walks exactly their unit/slot
+// sequences (so state i is advanced by the same draws as in the reference launch), and hands
+// each slot's K normals over through a shared-memory row guarded by a full/empty mbarrier pair.
+// The compute warps then never stall on the RNG and keep their TMA ring busy.
+template <int WARPS, int NW>
+__device__ __forceinline__ void noise_producer(const PhiArgs& a, uint32_t p, float* s_nz, uint64_t* full,
+                                               uint64_t* empty, uint32_t lane) {
+  constexpr int PER = WARPS / NW;  // compute warps served by this producer
+  const uint32_t K = a.K;
+  const bool fast_noise = (a.mode == AMMSB_MODE_WG && a.wg == 32);
+  const uint32_t vw = a.mode == AMMSB_MODE_THREAD ? 1u : a.wg;
+  const uint32_t active = a.units < a.V ? a.units : a.V;
+  const uint32_t total_warps = gridDim.x * WARPS;
+  uint32_t unit[PER], slot[PER], item[PER];
+  Rng st[PER];
+  bool open[PER];  // a unit is in progress (its state is live in st)
+#pragma unroll
+  for (int c = 0; c < PER; ++c) {
+    const uint32_t w = p + c * NW;
+    unit[c] = a.part_index + a.part_count * (blockIdx.x * WARPS + w);
+    slot[c] = unit[c];
+    item[c] = 0;
+    open[c] = false;
+  }
+  for (;;) {
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < PER; ++c) {
+      if (unit[c] >= active) continue;
+      any = true;
+      const uint32_t w = p + c * NW;
+      float* out = s_nz + (size_t)w * K;
+      mbar_wait(&empty[w], (item[c] & 1) ^ 1);  // the consumer is done with the previous row
+      if (fast_noise) {
+        if (!open[c]) {
+          st[c] = rng_load(a.pool, (uint64_t)unit[c] * 32 + lane);
+          open[c] = true;
+        }
+        for (uint32_t k = lane; k < K; k += 32) out[k] = rng_randn(st[c]);
+      } else {
+        for (uint32_t vl = lane; vl < vw; vl += 32) {
+          Rng vs = rng_load(a.pool, (uint64_t)unit[c] * vw + vl);
+          for (uint32_t k = vl; k < K; k += vw) out[k] = rng_randn(vs);
+          rng_store(a.pool, (uint64_t)unit[c] * vw + vl, vs);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[w]);  // release: the row is visible to the consumer
+      ++item[c];
+      slot[c] += a.units;
+      if (slot[c] >= a.V) {  // unit finished: persist its state, move to the warp's next unit
+        if (fast_noise) rng_store(a.pool, (uint64_t)unit[c] * 32 + lane, st[c]);
+        open[c] = false;
+        unit[c] += a.part_count * total_warps;
+        slot[c] = unit[c];
+      }
+    }
+    if (!any) break;
+  }
+}
+
 // NB = neighbors per loop trip.  For short rows (K <= 512) the per-neighbor fixed cost (barrier
 // wait, shuffle tree, reciprocal, refill) dominates the issue slots; NB = 2 interleaves two
 // neighbors (two shuffle trees in flight, own row kept in registers) without changing any
 // result: every sum is formed in the same order as with NB = 1.
-template <int KPL, int STAGES, int WARPS, bool EXACT, int NB>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int KPL, int STAGES, int WARPS, bool EXACT, int NB, int NW>
+__global__ void __launch_bounds__((WARPS + NW) * 32)
     k_update_phi_fast(const __grid_constant__ PhiArgs a) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   const uint32_t K = a.K;
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t row_bytes = K * 4;
+  // layout: [WARPS][(own + STAGES rows)] | NW ? [WARPS][noise row] | [WARPS][STAGES+1] stage
+  // barriers | NW ? full[WARPS], empty[WARPS]
+  float* s_nz = reinterpret_cast<float*>(s_raw) + (size_t)WARPS * (STAGES + 1) * K;
+  uint64_t* bar_base = reinterpret_cast<uint64_t*>(s_raw + ((size_t)WARPS * (STAGES + 1) + (NW ? WARPS : 0)) * row_bytes);
+  uint64_t* nz_full = bar_base + WARPS * (STAGES + 1);
+  uint64_t* nz_empty = nz_full + WARPS;
+  const bool ws_noise = NW > 0 && !a.disable_noise;
+  if (NW > 0) {
+    if (threadIdx.x == 0) {
+      for (int w = 0; w < WARPS; ++w) {
+        mbar_init(&nz_full[w], 1);
+        mbar_init(&nz_empty[w], 1);
+      }
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (wib >= WARPS) {  // producer warps: noise only, no row traffic
+      if (ws_noise) noise_producer<WARPS, (NW > 0 ? NW : 1)>(a, wib - WARPS, s_nz, nz_full, nz_empty, lane);
+      return;
+    }
+  }
   float* s_own = reinterpret_cast<float*>(s_raw) + (size_t)wib * (STAGES + 1) * K;
   float* s_stage = s_own + K;
-  uint64_t* bars =
-      reinterpret_cast<uint64_t*>(s_raw + (size_t)WARPS * (STAGES + 1) * row_bytes) + wib * (STAGES + 1);
+  uint64_t* bars = bar_base + wib * (STAGES + 1);
   if (lane == 0) {
     for (int s = 0; s <= STAGES; ++s) mbar_init(&bars[s], 1);
     mbar_fence_init();
   }
   __syncwarp();
   uint32_t phase = 0;  // bit s: parity to wait on for barrier s (bit STAGES = own row)
+  uint32_t nz_item = 0;  // noise rows consumed so far (parity of the full barrier)
 
   // f_k = beta_k - epsilon for the lane's k (phi.cc:237-239); the non-link factor is -f_k
   float fb[KPL];
@@ -175,7 +264,7 @@ __global__ void __launch_bounds__(WARPS * 32)
   for (uint32_t unit = a.part_index + a.part_count * gwarp; unit < a.units && unit < a.V;
        unit += a.part_count * total_warps) {
     Rng st;
-    if (fast_noise && !a.disable_noise) st = rng_load(a.pool, (uint64_t)unit * 32 + lane);
+    if (NW == 0 && fast_noise && !a.disable_noise) st = rng_load(a.pool, (uint64_t)unit * 32 + lane);
     for (uint32_t slot = unit; slot < a.V; slot += a.units) {
       const uint32_t node = __ldg(&a.nodes[slot]);
       const float phi_sum = *store_phi(a.sv, node);
@@ -309,8 +398,10 @@ __global__ void __launch_bounds__(WARPS * 32)
       }
 
       // Langevin noise (phi.cc:266-274) in the reference's per-state draw order
-      float* s_noise = s_stage;  // all stages are drained here
-      if (!a.disable_noise) {
+      float* s_noise = NW > 0 ? s_nz + (size_t)wib * K : s_stage;  // NW == 0: all stages are drained here
+      if (NW > 0) {
+        if (ws_noise) mbar_wait(&nz_full[wib], nz_item & 1);  // the producer's row for this slot
+      } else if (!a.disable_noise) {
         if (fast_noise) {
           for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn(st);
         } else {
@@ -336,6 +427,11 @@ __global__ void __launch_bounds__(WARPS * 32)
           out[k] = v;
           lsum += v;
         }
+      }
+      if (NW > 0 && ws_noise) {
+        __syncwarp();  // every lane has read the noise row
+        if (lane == 0) mbar_arrive(&nz_empty[wib]);
+        ++nz_item;
       }
       lsum = warp_sum(lsum);
       if (lane == 0) a.phi_sum[slot] = lsum;
@@ -549,22 +645,23 @@ static uint32_t my_units(const PhiArgs& a) {
   return active > a.part_index ? (active - a.part_index + a.part_count - 1) / a.part_count : 0;
 }
 
-template <int KPL, int STAGES, int WARPS, int NB = 1>
+template <int KPL, int STAGES, int WARPS, int NB = 1, int NW = 0>
 static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
-  const size_t smem = (size_t)WARPS * (STAGES + 1) * a.K * 4 + (size_t)WARPS * (STAGES + 1) * 8;
+  const size_t smem = ((size_t)WARPS * (STAGES + 1) + (NW ? WARPS : 0)) * a.K * 4 +
+                      (size_t)WARPS * (STAGES + 1) * 8 + (NW ? 2 * WARPS * 8 : 0);
   const bool exact = (a.K == 32u * KPL);
-  auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB>
-                    : k_update_phi_fast<KPL, STAGES, WARPS, false, NB>;
+  auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB, NW>
+                    : k_update_phi_fast<KPL, STAGES, WARPS, false, NB, NW>;
   AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (WARPS + NW) * 32, smem));
   AMMSB_REQUIRE(occ > 0, "update_phi: kernel does not fit on an SM");
   const uint32_t active = my_units(a);
   if (active == 0) return 0;
   uint32_t blocks = (active + WARPS - 1) / WARPS;
   const uint32_t resident = (uint32_t)occ * c->sm_count;
   if (blocks > resident) blocks = resident;  // persistent: one wave, warps stride over units
-  kern<<<blocks, WARPS * 32, smem, c->stream>>>(a);
+  kern<<<blocks, (WARPS + NW) * 32, smem, c->stream>>>(a);
   AMMSB_LAUNCH_CHECK();
   return 0;
 }
@@ -649,8 +746,16 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
     if (kpl <= 2) return launch_fast<2, 8, 4, 2>(c, a);
     if (kpl <= 4) return launch_fast<4, 8, 4, 2>(c, a);
     if (kpl <= 8) return launch_fast<8, 6, 4, 2>(c, a);
-    if (kpl <= 16) return launch_fast<16, 4, 4>(c, a);  // NB = 2 costs occupancy here (measured -6%)
-    return launch_fast<32, 3, 4>(c, a);
+    if (kpl <= 16) {
+      if (getenv("AMMSB_PHI_WS16A")) return launch_fast<16, 4, 4, 1, 2>(c, a);  // experiments
+      if (getenv("AMMSB_PHI_WS16B")) return launch_fast<16, 6, 4, 1, 2>(c, a);
+      if (getenv("AMMSB_PHI_WS16C")) return launch_fast<16, 8, 4, 1, 2>(c, a);
+      return launch_fast<16, 4, 4>(c, a);  // NB = 2 costs occupancy here (measured -6%)
+    }
+    // 4 gather warps x 4 stages + 2 noise-producer warps, 2 CTAs/SM: 6.10 TB/s at K = 1024
+    // (the all-in-one <32,3,4> kernel: 5.66 TB/s; without noise both reach 6.3 TB/s)
+    if (getenv("AMMSB_PHI_NOWS")) return launch_fast<32, 3, 4>(c, a);
+    return launch_fast<32, 4, 4, 1, 2>(c, a);
   }
   // K in (1024, 4096]: teams of 2 or 4 warps per slot (one slot per unit, i.e. V <= 65535)
   if (!o->strict && V <= a.units && p->K > 1024 && p->K <= 4096) {
