@@ -350,17 +350,41 @@ def run_b200(args, w):
     d_edges_all = ctx.from_host(np.concatenate([b[1] for b in batches]))
     d_nodes_all = ctx.from_host(np.concatenate([b[2] for b in batches]))
 
+    # Neighbor sampling of mini-batch i+1 runs on a second stream while mini-batch i is processed
+    # -- the schedule of Learner::Run (reference learner.cc:216-232: the next Sample is prepared
+    # concurrently on its own queue); double-buffered neighbor lists, ordered by events.
+    side = torch.cuda.Stream()
+    ctx_side = A.Ctx(local_rank)
+    ctx_side.set_stream(side.cuda_stream)
+    d_nbs = [d_nb, ctx.buf(np.uint32, Vmax * n)]
+    ns_done = [torch.cuda.Event(), torch.cuda.Event()]
+    phi_done = [torch.cuda.Event(), torch.cuda.Event()]
+    sampled = [-1]
+
+    def sample_neighbors(i):
+        if i >= total or sampled[0] >= i:
+            return
+        nodes = batches[i][2]
+        side.wait_event(phi_done[i & 1])  # update_phi of mini-batch i-2 has released this buffer
+        ctx_side.neighbor_sample(npools[i & 1], View(d_nodes_all.ptr.value + 4 * int(v_off[i])), len(nodes), N, n, 32,
+                                 d_nbs[i & 1])
+        ns_done[i & 1].record(side)
+        sampled[0] = i
+
     def device_step(i, step_no, ev=None):
         wgt, edges, nodes = batches[i]
         V, Emb = len(nodes), len(edges)
         dn = View(d_nodes_all.ptr.value + 4 * int(v_off[i]))
         de = View(d_edges_all.ptr.value + 8 * int(e_off[i]))
-        ctx.neighbor_sample(npools[i & 1], dn, V, N, n, 32, d_nb)
+        sample_neighbors(i)
+        stream.wait_event(ns_done[i & 1])
         if ev is not None:
             ev[0].record(stream)
-        ctx.update_phi(p, opts, d_beta, store, dts, dn, d_nb, V, step_no, ppool, d_vec, d_sum)
+        ctx.update_phi(p, opts, d_beta, store, dts, dn, d_nbs[i & 1], V, step_no, ppool, d_vec, d_sum)
         if ev is not None:
             ev[1].record(stream)
+        phi_done[i & 1].record(stream)
+        sample_neighbors(i + 1)
         ctx.update_pi(K, store, d_vec, d_sum, dn, V)
         ctx.update_beta(p, d_theta, d_beta, store, dts, de, Emb, wgt, step_no, bpool, d_ts, d_g, ws)
 
@@ -444,7 +468,7 @@ def run_b200(args, w):
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "launches": args.steps, "algorithmic_bytes_per_launch": round(phi_bytes / args.steps), "share_of_step": round(phi_ms / dev_ms, 4),
                 "canonical_launch": dict(stages["update_phi"], V=Vb, frac=round(stages["update_phi"]["GBps"] / peak, 4))}
-    for b in (d_edges_all, d_nodes_all, d_hedges, d_ppx, pws, d_nb, d_vec, d_sum, d_ts, d_g, ws, d_theta, d_beta):
+    for b in (d_edges_all, d_nodes_all, d_hedges, d_ppx, pws, d_nb, d_nbs[1], d_vec, d_sum, d_ts, d_g, ws, d_theta, d_beta):
         b.free()
     for r in npools + [ppool, bpool]:
         r.free()
@@ -491,7 +515,9 @@ def run_b200(args, w):
         "config": {"workload": workload_name(w, 1),
                    "l2": "inputs larger than L2: pi is %.2f GB and every non-link step gathers %.2f GB of rows"
                          % (4.0 * N * K / 1e9, bytes_phi(Vb, n, K) / 1e9),
-                   "timing": "CUDA events on the launching stream; steps are whole iterations in stream order"},
+                   "timing": "CUDA events on the launching stream; steps are whole iterations in stream order; "
+                             "neighbor sampling of the next mini-batch overlaps on a second stream (the "
+                             "Learner::Run schedule)"},
         "iterations_per_s": args.steps / (dev_ms * 1e-3),
         "perplexity_eval_s": stages["perplexity"]["ms"] * 1e-3,
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -56,6 +56,8 @@ int mcmc_config_set(void* vc, const char* key, double v) {
   else if (k == "strategy") c->strategy = static_cast<SampleStrategy>(static_cast<int>(v));
   else if (k == "phi_mode") c->phi_mode = static_cast<PhiUpdaterMode>(static_cast<int>(v));
   else if (k == "phi_strict") c->phi_strict = v != 0;
+  else if (k == "calc_train_ppx") c->calc_train_ppx = v != 0;
+  else if (k == "training_ppx_ratio") c->training_ppx_ratio = v;
   else if (k == "stage_timers") c->stage_timers = v != 0;
   else { g_err = "unknown config key " + k; return 1; }
   return 0;
@@ -225,6 +227,14 @@ int mcmc_learner_run(void* vb, uint32_t iters) {
 }
 int mcmc_learner_heldout_perplexity(void* vb, float* out) {
   return Guard([&] { *out = static_cast<LearnerBox*>(vb)->learner->HeldoutPerplexity(); });
+}
+int mcmc_learner_training_perplexity(void* vb, float* out) {
+  return Guard([&] { *out = static_cast<LearnerBox*>(vb)->learner->TrainingPerplexity(); });
+}
+uint64_t mcmc_learner_train_ppx_edges(void* vb, uint64_t* out) {
+  const std::vector<Edge>& e = static_cast<LearnerBox*>(vb)->learner->TrainingPerplexityEdges();
+  if (out) std::memcpy(out, e.data(), 8 * e.size());
+  return e.size();
 }
 int mcmc_learner_print_stats(void* vb) {
   return Guard([&] { static_cast<LearnerBox*>(vb)->learner->PrintStats(); });

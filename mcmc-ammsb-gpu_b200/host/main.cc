@@ -90,6 +90,8 @@ int main(int argc, char** argv) {
   Take(args, "--beta-sum-grads-vwidth", &cfg.sum_grads_vector_width);
   Take(args, "--phi-disable-noise", &cfg.phi_disable_noise);
   Take(args, "--phi-strict", &cfg.phi_strict);
+  Take(args, "--train-ppx", &cfg.calc_train_ppx);
+  Take(args, "--train-ppx-ratio", &cfg.training_ppx_ratio);
   Take(args, "--stage-timers", &cfg.stage_timers);
   Take(args, "--dump-data", &dumpDataset);
   Take(args, "--dump-file", &dumpFile);

@@ -27,6 +27,10 @@ std::string to_string(const PhiUpdaterMode& mode);
 
 struct Config {
   // model
+  // the reference's MCMC_CALC_TRAIN_PPX build option (config.h:26-28) as a run-time switch:
+  // Learner::TrainingPerplexity() over a sampled subset of the training edges
+  bool calc_train_ppx = false;
+  Float training_ppx_ratio = 0.01;
   Float heldout_ratio = 0.01;
   Float alpha = 0.001;
   Float a = 0.0315, b = 1024, c = 0.5;  // step size eps_t = a (1 + t/b)^-c

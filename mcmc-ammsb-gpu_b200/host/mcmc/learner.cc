@@ -12,6 +12,31 @@ using namespace std::chrono;
 namespace mcmc {
 
 namespace {
+// reference learner.cc:47-75: the first ratio*|training| training links, then
+// links * (N(N-1)/2) / E random pairs that are in neither set (libc rand(), as the reference)
+std::vector<Edge> MakeEdgesForTrainingPerplexity(const Config& cfg) {
+  const uint64_t total = (cfg.N * (cfg.N - 1)) / 2;
+  const uint64_t num_links = static_cast<uint64_t>(cfg.training_ppx_ratio * cfg.training_edges.size());
+  const uint64_t num_non_links = static_cast<uint64_t>(num_links * total / static_cast<double>(cfg.E));
+  std::vector<Edge> ret(num_links + num_non_links);
+  std::copy(cfg.training_edges.begin(), cfg.training_edges.begin() + num_links, ret.begin());
+  for (uint64_t i = num_links; i < ret.size(); ++i) {
+    Edge e;
+    do {
+      const Vertex u = rand() % cfg.N;
+      Vertex v;
+      do {
+        v = rand() % cfg.N;
+      } while (u == v);
+      e = MakeEdge(u, v);  // as the reference: not canonicalised (u may exceed v)
+    } while (cfg.training->Has(e) || cfg.heldout->Has(e));
+    ret[i] = e;
+  }
+  return ret;
+}
+}  // namespace
+
+namespace {
 typedef Float (*SamplerFn)(const Config&, std::vector<Edge>*, unsigned int*);
 SamplerFn PickSampler(SampleStrategy s) {
   switch (s) {
@@ -52,6 +77,15 @@ Learner::Learner(const Config& cfg, clcuda::Queue queue)
       edgesProcessed_(0),
       phase_(0),
       betaMirror_(nullptr) {
+  if (cfg_.calc_train_ppx) {  // before the Samples draw their seeds, as in the reference's member order
+    trainingPerplexityEdges_ = MakeEdgesForTrainingPerplexity(cfg_);
+    devTrainingPerplexityEdges_.reset(new clcuda::Buffer<Edge>(queue_.GetContext(), queue_,
+                                                               trainingPerplexityEdges_.begin(),
+                                                               trainingPerplexityEdges_.end()));
+    trainingPerplexity_.reset(new PerplexityCalculator(PerplexityCalculator::EDGE_PER_WORKGROUP, cfg_, queue_, beta_,
+                                                       pi_.get(), *devTrainingPerplexityEdges_, trainingSet_.get(),
+                                                       compileFlags_));
+  }
   for (auto& ev : iterDone_) AmmsbCheck(ammsb_event_create(queue_(), &ev));
   for (auto& sample : samples_) {
     sample.reset(new Sample(cfg_, queue_));  // seed = rand(), as in the reference (sample.cc:132)
@@ -90,6 +124,14 @@ uint64_t CountInFlight(Sample* const* owner, uint64_t launched, uint64_t retired
 Float Learner::HeldoutPerplexity() {
   const auto t1 = high_resolution_clock::now();
   const Float avg = heldoutPerplexity_();
+  time_ += duration_cast<nanoseconds>(high_resolution_clock::now() - t1).count();
+  return std::exp(avg);
+}
+
+Float Learner::TrainingPerplexity() {
+  if (!trainingPerplexity_) throw BackendError("TrainingPerplexity() needs Config::calc_train_ppx");
+  const auto t1 = high_resolution_clock::now();
+  const Float avg = (*trainingPerplexity_)();
   time_ += duration_cast<nanoseconds>(high_resolution_clock::now() - t1).count();
   return std::exp(avg);
 }
@@ -182,7 +224,8 @@ bool Learner::Serialize(std::ostream* out) {
   props.weight = samples_[phase_]->WaitReady().weight;
   return ::mcmc::Serialize(out, &beta_, &queue_) && ::mcmc::Serialize(out, &theta_, &queue_) &&
          SerializeRpm(out, pi_.get()) && ::mcmc::Serialize(out, &phi_, &queue_) && phiUpdater_.Serialize(out) &&
-         betaUpdater_.Serialize(out) && heldoutPerplexity_.Serialize(out) && SerializeMessage(out, props) &&
+         betaUpdater_.Serialize(out) && (!trainingPerplexity_ || trainingPerplexity_->Serialize(out)) &&
+         heldoutPerplexity_.Serialize(out) && SerializeMessage(out, props) &&
          samples_[0]->Serialize(out) && samples_[1]->Serialize(out);
 }
 
@@ -190,7 +233,8 @@ bool Learner::Parse(std::istream* in) {
   LearnerProperties props;
   if (!(::mcmc::Parse(in, &beta_, &queue_) && ::mcmc::Parse(in, &theta_, &queue_) && ParseRpm(in, pi_.get()) &&
         ::mcmc::Parse(in, &phi_, &queue_) && phiUpdater_.Parse(in) && betaUpdater_.Parse(in) &&
-        heldoutPerplexity_.Parse(in) && ParseMessage(in, &props)))
+        (!trainingPerplexity_ || trainingPerplexity_->Parse(in)) && heldoutPerplexity_.Parse(in) &&
+        ParseMessage(in, &props)))
     return false;
   stepCount_ = props.stepCount;
   time_ = props.time;

@@ -32,6 +32,11 @@ class Learner {
 
   void Run(uint32_t max_iters, sig_atomic_t* signaled = nullptr);
   Float HeldoutPerplexity();
+  // exp(-mean log-likelihood) over cfg.training_ppx_ratio of the training links plus the
+  // matching number of random non-links (reference learner.cc:47-75,204-212); needs
+  // cfg.calc_train_ppx
+  Float TrainingPerplexity();
+  const std::vector<Edge>& TrainingPerplexityEdges() const { return trainingPerplexityEdges_; }
   void PrintStats();
   bool Serialize(std::ostream* out);
   bool Parse(std::istream* in);
@@ -70,6 +75,9 @@ class Learner {
   clcuda::Buffer<Edge> trainingEdges_;
   clcuda::Buffer<Edge> heldoutEdges_;
   std::vector<std::string> compileFlags_;
+  std::vector<Edge> trainingPerplexityEdges_;
+  std::unique_ptr<clcuda::Buffer<Edge>> devTrainingPerplexityEdges_;
+  std::unique_ptr<PerplexityCalculator> trainingPerplexity_;
   PerplexityCalculator heldoutPerplexity_;
   PhiUpdater phiUpdater_;
   BetaUpdater betaUpdater_;

@@ -54,6 +54,9 @@ def lib():
         L.mcmc_learner_run.argtypes = [C.c_void_p, C.c_uint32]
         L.mcmc_learner_heldout_perplexity.argtypes = [C.c_void_p, C.c_void_p]
         L.mcmc_learner_print_stats.argtypes = [C.c_void_p]
+        L.mcmc_learner_training_perplexity.argtypes = [C.c_void_p, C.c_void_p]
+        L.mcmc_learner_train_ppx_edges.restype = C.c_uint64
+        L.mcmc_learner_train_ppx_edges.argtypes = [C.c_void_p, C.c_void_p]
         L.mcmc_learner_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.mcmc_learner_edges_processed.restype = C.c_uint64
         L.mcmc_learner_mirror_beta.argtypes = [C.c_void_p, C.c_void_p]
@@ -193,6 +196,17 @@ class Learner:
         out = C.c_float(0)
         _ck(lib().mcmc_learner_heldout_perplexity(self.h, C.byref(out)))
         return out.value
+
+    def training_perplexity(self):
+        out = C.c_float(0)
+        _ck(lib().mcmc_learner_training_perplexity(self.h, C.byref(out)))
+        return out.value
+
+    def training_perplexity_edges(self):
+        n = lib().mcmc_learner_train_ppx_edges(self.h, None)
+        e = np.zeros(n, dtype=np.uint64)
+        lib().mcmc_learner_train_ppx_edges(self.h, _p(e))
+        return e
 
     def print_stats(self):
         _ck(lib().mcmc_learner_print_stats(self.h))

@@ -207,3 +207,24 @@ def test_cli_runs_on_a_snap_file(ctx, tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert (r.stdout + r.stderr).count("ppx[") >= 3
+
+
+def test_training_perplexity_option(ctx, orc):
+    """MCMC_CALC_TRAIN_PPX (learner.cc:47-75,204-212) as a run-time switch"""
+    N, K, n = 900, 32, 8
+    cfg = make_cfg(N=N, E=7000, K=K, m=32, n=n, seed=6, calc_train_ppx=1, training_ppx_ratio=0.05)
+    lrn = pymcmc.Learner(cfg, 0)
+    lrn.run(5)
+    edges = lrn.training_perplexity_edges()
+    tr, he = cfg.edges()
+    n_links = int(0.05 * len(tr))
+    assert np.array_equal(edges[:n_links], tr[:n_links]) and len(edges) > n_links
+    got = lrn.training_perplexity()
+    pi, phi, beta, theta = lrn.read(N, K)
+    ts = orc.set_build(tr)
+    p = orc.make_params(N, int(cfg.params().E), K, n)
+    avg, sums = orc.perplexity(A.MODE_WG, 32, p, pi, beta, ts, edges, np.zeros(len(edges), np.float32), 1)
+    assert sums[2] == n_links
+    assert abs(got - float(np.exp(np.float32(avg)))) <= 1e-5 * got
+    lrn.close()
+    cfg.close()
