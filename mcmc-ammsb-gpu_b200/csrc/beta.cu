@@ -12,7 +12,10 @@
 // reproducible (the reference's serialize-test.cc:132 contract).
 #include "common.cuh"
 
-#define BETA_WARPS 8
+// 4 warps per CTA: k_beta_partial<8> needs 156 registers, so 128-thread CTAs fit 3 per SM
+// (12 warps x 8 KB of row loads in flight); 256-thread CTAs fit only one (measured 53 us -> see
+// profiles/).
+#define BETA_WARPS 4
 
 struct BetaArgs {
   StoreView sv;
@@ -26,7 +29,7 @@ struct BetaArgs {
 
 // KPL4 = number of float4 per lane per row = ceil(K / 128)
 template <int KPL4>
-__global__ void __launch_bounds__(BETA_WARPS * 32)
+__global__ void __launch_bounds__(BETA_WARPS * 32, 3)
     k_beta_partial(const __grid_constant__ BetaArgs a) {
   extern __shared__ __align__(16) float s_mem[];
   const uint32_t K = a.K;
@@ -243,7 +246,7 @@ __global__ void k_update_theta(float* __restrict__ theta, float* __restrict__ be
   beta[2 * k + 1] = __fdiv_rn(t1, sum);
 }
 
-static uint32_t beta_max_ctas(const ammsb_ctx* c) { return (uint32_t)c->sm_count * 2; }
+static uint32_t beta_max_ctas(const ammsb_ctx* c) { return (uint32_t)c->sm_count * 3; }
 
 extern "C" int ammsb_beta_workspace_bytes(ammsb_ctx* c, uint32_t K, size_t* bytes) {
   *bytes = sizeof(float) * 2 * (size_t)K * beta_max_ctas(c);

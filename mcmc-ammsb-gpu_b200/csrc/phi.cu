@@ -847,15 +847,27 @@ __global__ void __launch_bounds__(256)
       sum = warp_sum(ls);
     }
     if ((K & 3) == 0) {
-      for (uint32_t k = lane * 4; k < K; k += 128) {
-        float4 v = *reinterpret_cast<const float4*>(src + k);
-        v.x = __fdiv_rn(v.x, sum);
-        v.y = __fdiv_rn(v.y, sum);
-        v.z = __fdiv_rn(v.z, sum);
-        v.w = __fdiv_rn(v.w, sum);
-        *reinterpret_cast<float4*>(dst + k) = v;
-        for (uint32_t r = 0; r < sv.num_mirrors; ++r)  // replicated mode: NVLink peer stores
-          *reinterpret_cast<float4*>(sv.mirror_pi[r] + (size_t)node * K + k) = v;
+      // four 128-bit loads in flight per lane before the (IEEE) divides and the stores
+      for (uint32_t k0 = lane * 4; k0 < K; k0 += 512) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t k = k0 + 128 * u;
+          if (k < K) v[u] = *reinterpret_cast<const float4*>(src + k);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t k = k0 + 128 * u;
+          if (k < K) {
+            v[u].x = __fdiv_rn(v[u].x, sum);
+            v[u].y = __fdiv_rn(v[u].y, sum);
+            v[u].z = __fdiv_rn(v[u].z, sum);
+            v[u].w = __fdiv_rn(v[u].w, sum);
+            *reinterpret_cast<float4*>(dst + k) = v[u];
+            for (uint32_t r = 0; r < sv.num_mirrors; ++r)  // replicated mode: NVLink peer stores
+              *reinterpret_cast<float4*>(sv.mirror_pi[r] + (size_t)node * K + k) = v[u];
+          }
+        }
       }
     } else {
       for (uint32_t k = lane; k < K; k += 32) {
@@ -877,7 +889,7 @@ static int update_pi_impl(ammsb_ctx* c, uint32_t K, ammsb_store* store, const fl
   AMMSB_REQUIRE(K == store->K, "K does not match the store");
   AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
   uint32_t blocks = (V + 7) / 8;
-  const uint32_t cap = (uint32_t)c->sm_count * 8;
+  const uint32_t cap = (uint32_t)c->sm_count * 16;
   if (blocks > cap) blocks = cap;
   k_update_pi<<<blocks, 256, 0, c->stream>>>(store->view(), d_phi_vec, d_phi_sum, d_nodes, V, units, part_index,
                                              part_count);
