@@ -131,6 +131,110 @@ __global__ void __launch_bounds__(BETA_WARPS * 32, 3)
   for (uint32_t k = threadIdx.x; k < 2 * K; k += blockDim.x) out[k] = s_acc[k];
 }
 
+// K > 1024: one CTA per edge (grid-strided), thread t owns the columns 4t..4t+3 (+1024 i), so
+// the [2][K] accumulators stay in registers (a warp-per-edge layout would need 2K/32 registers
+// per lane).  The two per-edge sums cross the CTA through shared memory, one barrier per edge
+// (double-buffered), added in warp order.  The next edge's rows are loaded before that barrier.
+template <int KPT4>
+__global__ void __launch_bounds__(256) k_beta_partial_cta(const __grid_constant__ BetaArgs a) {
+  __shared__ float s_red[2][2][8];
+  const uint32_t K = a.K, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float4 accA[KPT4], accB[KPT4], bk[KPT4];
+#pragma unroll
+  for (int i = 0; i < KPT4; ++i) {
+    accA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t k = tid * 4 + 1024 * i;
+    bk[i] = k < K ? make_float4(__ldg(&a.beta[2 * k + 1]), __ldg(&a.beta[2 * k + 3]), __ldg(&a.beta[2 * k + 5]),
+                                __ldg(&a.beta[2 * k + 7]))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 q[KPT4], nq[KPT4];
+  auto load_edge = [&](uint32_t e, float4* dst, uint32_t* pu, uint32_t* pv) {
+    const uint64_t edge = __ldg(&a.edges[e]);
+    const uint32_t u = (uint32_t)(edge >> 32), v = (uint32_t)(edge & 0xffffffffu);
+    *pu = u;
+    *pv = v;
+    const float* pa = store_row(a.sv, u);
+    const float* pb = store_row(a.sv, v);
+#pragma unroll
+    for (int i = 0; i < KPT4; ++i) {
+      const uint32_t k = tid * 4 + 1024 * i;
+      if (k < K) {
+        const float4 x = ldg_stream4(pa + k);
+        const float4 z = ldg_stream4(pb + k);
+        dst[i] = make_float4(x.x * z.x, x.y * z.y, x.z * z.z, x.w * z.w);
+      } else {
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  uint32_t u = 0, v = 0, nu = 0, nv = 0, par = 0;
+  uint32_t e = blockIdx.x;
+  if (e < a.E_mb) load_edge(e, q, &u, &v);
+  for (; e < a.E_mb; e += gridDim.x, par ^= 1) {
+    const uint32_t en = e + gridDim.x;
+    if (en < a.E_mb) load_edge(en, nq, &nu, &nv);  // in flight across the reduction below
+    const bool y = set_has(a.set, make_edge(min(u, v), max(u, v)));
+    float pi_sum = 0.f, probs_sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPT4; ++i) {
+      pi_sum += (q[i].x + q[i].y) + (q[i].z + q[i].w);
+      q[i].x *= y ? bk[i].x : 1.0f - bk[i].x;
+      q[i].y *= y ? bk[i].y : 1.0f - bk[i].y;
+      q[i].z *= y ? bk[i].z : 1.0f - bk[i].z;
+      q[i].w *= y ? bk[i].w : 1.0f - bk[i].w;
+      probs_sum += (q[i].x + q[i].y) + (q[i].z + q[i].w);
+    }
+    pi_sum = warp_sum(pi_sum);
+    probs_sum = warp_sum(probs_sum);
+    if (lane == 0) {
+      s_red[par][0][wid] = pi_sum;
+      s_red[par][1][wid] = probs_sum;
+    }
+    __syncthreads();
+    pi_sum = 0.f;
+    probs_sum = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      pi_sum += s_red[par][0][ww];
+      probs_sum += s_red[par][1][ww];
+    }
+    probs_sum += (y ? a.epsilon : 1.0f - a.epsilon) * (1.0f - pi_sum);
+    const float rS = 1.0f / probs_sum;
+    if (y) {
+#pragma unroll
+      for (int i = 0; i < KPT4; ++i) {
+        accB[i].x = fmaf(q[i].x, rS, accB[i].x);
+        accB[i].y = fmaf(q[i].y, rS, accB[i].y);
+        accB[i].z = fmaf(q[i].z, rS, accB[i].z);
+        accB[i].w = fmaf(q[i].w, rS, accB[i].w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KPT4; ++i) {
+        accA[i].x = fmaf(q[i].x, rS, accA[i].x);
+        accA[i].y = fmaf(q[i].y, rS, accA[i].y);
+        accA[i].z = fmaf(q[i].z, rS, accA[i].z);
+        accA[i].w = fmaf(q[i].w, rS, accA[i].w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < KPT4; ++i) q[i] = nq[i];
+    u = nu;
+    v = nv;
+  }
+  float* out = a.partial + (size_t)blockIdx.x * 2 * K;
+#pragma unroll
+  for (int i = 0; i < KPT4; ++i) {
+    const uint32_t k = tid * 4 + 1024 * i;
+    if (k < K) {
+      *reinterpret_cast<float4*>(out + k) = accA[i];
+      *reinterpret_cast<float4*>(out + K + k) = accB[i];
+    }
+  }
+}
+
 // generic-K fallback (K not a multiple of 4 or K > 4096): scalar loads, lane-strided
 __global__ void __launch_bounds__(BETA_WARPS * 32)
     k_beta_partial_generic(const __grid_constant__ BetaArgs a) {
@@ -280,6 +384,12 @@ extern "C" int ammsb_beta_grads(ammsb_ctx* c, const ammsb_params* p, const float
       else if (kpl4 <= 2) k_beta_partial<2><<<ctas, BETA_WARPS * 32, smem, c->stream>>>(a);
       else if (kpl4 <= 4) k_beta_partial<4><<<ctas, BETA_WARPS * 32, smem, c->stream>>>(a);
       else k_beta_partial<8><<<ctas, BETA_WARPS * 32, smem, c->stream>>>(a);
+    } else if ((K % 4) == 0 && K <= 4096) {
+      // one CTA per edge; the grid is capped by the partial-sum workspace like the warp kernel
+      ctas = E_mb < beta_max_ctas(c) ? E_mb : beta_max_ctas(c);
+      AMMSB_REQUIRE(ws_bytes >= sizeof(float) * 2 * (size_t)K * ctas, "beta workspace too small");
+      if (K <= 2048) k_beta_partial_cta<2><<<ctas, 256, 0, c->stream>>>(a);
+      else k_beta_partial_cta<4><<<ctas, 256, 0, c->stream>>>(a);
     } else {
       uint32_t warps = BETA_WARPS;
       while (warps > 1 && sizeof(float) * 2 * (size_t)K * warps > 160 * 1024) warps >>= 1;

@@ -228,3 +228,28 @@ def test_training_perplexity_option(ctx, orc):
     assert abs(got - float(np.exp(np.float32(avg)))) <= 1e-5 * got
     lrn.close()
     cfg.close()
+
+
+def test_learner_grqc_shape_matches_oracle(ctx, orc):
+    """BASELINE.json configs[0]: synthetic ca-GrQc-shaped graph (N=5242, E=14496), K=64,
+    stratified-random-node mini-batches with the reference CLI defaults m=32, n=32, r=0.01"""
+    N, E, K, m, n = 5242, 14496, 64, 32, 32
+    cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=0.01, strategy="Node")
+    cfg.set_graph(N, make_edges(N, E, 1))
+    assert len(cfg.edges()[1]) == 2 * (E - int(np.ceil((1 - 0.01 / 2) * E)))  # data.cc:86-99
+    lrn = pymcmc.Learner(cfg, 0)
+    ol = OracleLearner(orc, cfg, lrn, N, K, n)
+    got, want = lrn.heldout_perplexity(), ol.perplexity()
+    assert abs(got - want) <= PPX_TOL * want
+    for it in range(60):
+        edges, nodes, nbrs, weight = lrn.peek(n)
+        assert np.array_equal(nbrs, ol.iterate(edges, nodes, weight))
+        lrn.run(1)
+    pi, phi, beta, theta = lrn.read(N, K)
+    e = rel_err(pi, ol.pi)
+    assert np.median(e) == 0 or np.median(e) < 1e-6  # most rows untouched, touched rows close
+    got, want = lrn.heldout_perplexity(), ol.perplexity()
+    print("ca-GrQc shape, 60 free-running iterations: device %.6f oracle %.6f" % (got, want))
+    assert abs(got - want) <= PPX_TOL * want
+    lrn.close()
+    cfg.close()

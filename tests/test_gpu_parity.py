@@ -259,7 +259,7 @@ def test_update_phi_fast_nonstandard_wg_stream(ctx, orc):
 
 # ---------------------------------------------------------- update_beta ----
 
-@pytest.mark.parametrize("K,m", [(64, 37), (256, 512), (1024, 300), (100, 64)])
+@pytest.mark.parametrize("K,m", [(64, 37), (256, 512), (1024, 300), (100, 64), (2048, 200), (4096, 333), (1100, 50)])
 def test_update_beta_vs_oracle(ctx, orc, K, m):
     prob = link_heavy_problem(orc, 500, K, 8)
     edges = prob.minibatch_edges(m, 3)
