@@ -269,7 +269,15 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     N, E, K, n = w["N"], w["E"], w["K"], w["n"]
     m = w["m"] * world
     t0 = time.time()
-    keys = synth.make_edges(N, E, 1)
+    # rank 0 generates the synthetic edge list once; the other ranks load it
+    path = os.path.join("/tmp", "ammsb_edges_%d_%d_%d.npy" % (N, E, int(os.environ.get("MASTER_PORT", "0"))))
+    if rank == 0:
+        np.save(path, synth.make_edges(N, E, 1))
+    dist.barrier()
+    keys = np.load(path)
+    dist.barrier()
+    if rank == 0:
+        os.unlink(path)
     cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=w["heldout_ratio"], strategy="Node")
     cfg.set_graph(N, keys)
     log("graph + split + sets: %.1fs" % (time.time() - t0))
