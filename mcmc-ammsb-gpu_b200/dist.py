@@ -158,30 +158,76 @@ class ShardedLearner:
         self.step_count = 0
         self.edges_processed = 0
         self.h2d_bytes = 0
-        # ---- host sampler: STREAMS seeds, mini-batch t comes from stream t % STREAMS ----
+        # ---- host sampler ----
+        # prefetch=False: every rank draws every mini-batch itself (stream t % STREAMS).
+        # prefetch=True (the host path): the drawing is spread over the ranks.  Mini-batch t is
+        # drawn by rank t % world on one of its LOCAL sampler streams (each with its own seed,
+        # each on its own thread), copied to that rank's GPU and broadcast to the others over
+        # NVLink one step ahead of its use.
         self.seeds = [C.c_uint(seed + 7919 * i) for i in range(self.STREAMS)]
         self.drawn = 0
         self.q = None
+        self.t = 0
         if prefetch:
-            self.q = [queue.Queue(maxsize=2) for _ in range(self.STREAMS)]
+            self.local_seeds = [C.c_uint(seed + 7919 * (rank * self.LOCAL + i) + 104729) for i in range(self.LOCAL)]
+            self.q = [queue.Queue(maxsize=2) for _ in range(self.LOCAL)]
             self.threads = [threading.Thread(target=self._producer, args=(i,), daemon=True)
-                            for i in range(self.STREAMS)]
-            for t in self.threads:
-                t.start()
+                            for i in range(self.LOCAL)]
+            for th in self.threads:
+                th.start()
+            self.side = torch.cuda.Stream()
+            self.bgroup = dist.new_group(backend="nccl") if world > 1 else None
+            self.HDR = 32
+            nbytes = self.HDR + 8 * self.Emax + 4 * self.Vmax
+            self.payload = [torch.zeros(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self.staging = [torch.zeros(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self.h_hdr = [torch.zeros(self.HDR, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self.ev_hdr = [torch.cuda.Event() for _ in range(2)]      # header of slot b is on the host
+            self.ev_payload = [torch.cuda.Event() for _ in range(2)]  # payload of slot b is on this GPU
+            self.ev_free = [torch.cuda.Event() for _ in range(2)]     # kernels that read slot b are done
+            self.ev_staged = [torch.cuda.Event() for _ in range(2)]   # H2D out of staging[b] is done
+            self.issued = 0
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------- sampling ----
+    LOCAL = 2  # sampler streams (threads) per rank on the host path
+
     def _producer(self, i):
         while True:
-            self.q[i].put(self.cfg.sample("Node", self.seeds[i]))  # ctypes call releases the GIL
+            self.q[i].put(self.cfg.sample("Node", self.local_seeds[i]))  # ctypes call releases the GIL
 
     def next_minibatch(self):
-        """(weight, edges, nodes) of iteration t from sampler stream t % STREAMS"""
+        """(weight, edges, nodes) of iteration t from sampler stream t % STREAMS (prefetch=False)"""
         i = self.drawn % self.STREAMS
         self.drawn += 1
-        if self.q is not None:
-            return self.q[i].get()
         return self.cfg.sample("Node", self.seeds[i])
+
+    def _issue(self, t):
+        """enqueue, on the side stream, everything that puts mini-batch t on every GPU"""
+        torch = self.torch
+        b = t & 1
+        src = t % self.world
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_free[b])  # kernels of mini-batch t-2 no longer read the slot
+            if self.rank == src:
+                weight, edges, nodes = self.q[(t // self.world) % self.LOCAL].get()
+                self.ev_staged[b].synchronize()  # the previous copy out of this staging buffer is done
+                st = self.staging[b].numpy()
+                V, E_mb = len(nodes), len(edges)
+                st[:self.HDR].view(np.int64)[:2] = (V, E_mb)
+                st[:self.HDR].view(np.float64)[2] = weight
+                st[self.HDR:self.HDR + 8 * E_mb] = edges.view(np.uint8)
+                off = self.HDR + 8 * self.Emax
+                st[off:off + 4 * V] = nodes.view(np.uint8)
+                self.payload[b].copy_(self.staging[b], non_blocking=True)
+                self.ev_staged[b].record(self.side)
+                self.h2d_bytes += self.HDR + 8 * E_mb + 4 * V
+            if self.bgroup is not None:
+                self.dist.broadcast(self.payload[b], src, group=self.bgroup)
+            self.h_hdr[b].copy_(self.payload[b][:self.HDR], non_blocking=True)
+            self.ev_hdr[b].record(self.side)
+            self.ev_payload[b].record(self.side)
+        self.issued = t + 1
 
     # --------------------------------------------------------- iteration ----
     def barrier(self):
@@ -211,19 +257,24 @@ class ShardedLearner:
         self.edges_processed += E_mb
 
     def host_step(self):
-        """one iteration from a HOST mini-batch: sample, H2D, kernels, D2H of beta"""
-        torch = self.torch
-        weight, edges, nodes = self.next_minibatch()
-        V, E_mb = len(nodes), len(edges)
-        self.h_nodes[:V].copy_(torch.from_numpy(nodes.view(np.int32)))
-        self.h_edges[:E_mb].copy_(torch.from_numpy(edges.view(np.int64)))
-        self.d_nodes[:V].copy_(self.h_nodes[:V], non_blocking=True)
-        self.d_edges[:E_mb].copy_(self.h_edges[:E_mb], non_blocking=True)
-        self.h2d_bytes += 4 * V + 8 * E_mb
-        self.device_step(tbuf(self.d_nodes), tbuf(self.d_edges), V, E_mb, weight,
-                         (self.drawn - 1) % self.STREAMS)
+        """one iteration from a HOST mini-batch: sampled on rank t % world, H2D there, broadcast,
+        sharded kernels, D2H of beta; mini-batch t+1 travels while t is processed"""
+        t = self.t
+        b = t & 1
+        if self.issued <= t:
+            self._issue(t)
+        self.ev_hdr[b].synchronize()
+        hdr = self.h_hdr[b].numpy()
+        V, E_mb = (int(x) for x in hdr.view(np.int64)[:2])
+        weight = float(hdr.view(np.float64)[2])
+        self.stream.wait_event(self.ev_payload[b])
+        base = self.payload[b].data_ptr()
+        self.device_step(_Buf(base + self.HDR + 8 * self.Emax), _Buf(base + self.HDR), V, E_mb, weight,
+                         t % self.STREAMS)
+        self.ev_free[b].record(self.stream)
+        self._issue(t + 1)  # travels while the kernels of t run
         self.h_beta.copy_(self.beta, non_blocking=True)
-        self.stream.synchronize()  # the pinned staging buffers are reused by the next step
+        self.t = t + 1
         return E_mb
 
     def run(self, iters):
@@ -384,11 +435,14 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt[0])
+        hb = torch.tensor([l2.h2d_bytes - b0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(hb)  # each rank counts the mini-batches it drew and copied
         e2e = {"value": (l2.edges_processed - e0) / dt, "unit": UNIT,
-               "h2d_bytes_per_step": (l2.h2d_bytes - b0) / args.steps * world, "d2h_bytes_per_step": 8 * K * world,
+               "h2d_bytes_per_step": float(hb[0]) / args.steps, "d2h_bytes_per_step": (8 * K + 32) * world,
                "iterations_per_s": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
-               "api": "dist.ShardedLearner.host_step(): replicated host mini-batch sampler (prefetch threads), "
-                      "H2D of edges/nodes from pinned memory on every rank, sharded kernels + NCCL, D2H of beta"}
+               "api": "dist.ShardedLearner.host_step(): mini-batch t drawn on rank t % N (2 sampler threads per "
+                      "rank), H2D from pinned memory there, NCCL broadcast one step ahead, sharded kernels + "
+                      "all-reduces, D2H of beta"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
