@@ -444,3 +444,36 @@ def test_update_pi_writes_every_mirror(ctx, orc):
         b.free()
     for s in stores:
         s.free()
+
+
+@pytest.mark.parametrize("K,n,V", [(520, 1, 1), (600, 3, 2), (1000, 31, 5), (1024, 33, 300), (1028, 64, 40),
+                                   (2040, 100, 9), (3008, 7, 33), (4096, 32, 70), (64, 5, 1000), (192, 17, 333),
+                                   (512, 2, 64), (36, 9, 11)])
+def test_update_phi_fast_matches_strict_over_shapes(ctx, orc, K, n, V):
+    """production kernels (warp / team, noise-producer warps, 2-neighbor unrolling) against the
+    IEEE reference-association kernel on the same device over awkward shapes: ragged K, n below
+    and above a warp, a single slot.  RNG pool state bit-identical, phi_vec within tolerance."""
+    N = 400
+    prob = link_heavy_problem(orc, N, K, n, seed=K + n)
+    nodes = prob.minibatch_nodes(min(V, N), 3)
+    V = len(nodes)
+    neighbors, _ = orc.neighbor_sample(orc.rng_pool(max(V, 64) * 2 * n, 56, 57), nodes, N, n, 32)
+    d_nodes, d_nb, d_beta = ctx.from_host(nodes), ctx.from_host(neighbors), ctx.from_host(prob.beta)
+    st, dset = dev_store(ctx, prob), dev_set(ctx, prob.train_set)
+    outs = []
+    for strict in (1, 0):
+        r = A.Rng(ctx, V * 32, 42, 43)
+        d_vec, d_sum = ctx.buf(np.float32, V * K).zero(), ctx.buf(np.float32, V).zero()
+        for step in (1, 2):  # two calls: the pool state carries over
+            ctx.update_phi(dev_params(prob.p_orc), A.PhiOpts(A.MODE_WG, 32, 0, strict), d_beta, st, dset, d_nodes,
+                           d_nb, V, step, r, d_vec, d_sum)
+        outs.append((d_vec.read().reshape(V, K), d_sum.read(), r.get_state()))
+        d_vec.free(); d_sum.free(); r.free()
+    (v_s, s_s, st_s), (v_f, s_f, st_f) = outs
+    assert np.array_equal(st_s, st_f), "RNG pool state differs between strict and production kernels"
+    err = rel_err(v_f, v_s)
+    assert np.median(err) < 1e-6 and float((err > RTOL).mean()) < 5e-3, (err.max(), float((err > RTOL).mean()))
+    assert rel_err(s_f, s_s).max() < 1e-5
+    for b in (d_nodes, d_nb, d_beta):
+        b.free()
+    dset.free(); st.free()
