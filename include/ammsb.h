@@ -147,6 +147,18 @@ int ammsb_store_export(ammsb_store* store, uint8_t* pi_handle /* [64] */, uint8_
 int ammsb_store_attach(ammsb_store* store, uint32_t shard, const uint8_t* pi_handle, const uint8_t* phi_handle);
 /* single-process multi-device: attach another store's shard by direct peer access */
 int ammsb_store_attach_local(ammsb_store* store, uint32_t shard, ammsb_store* peer);
+/* Shareable stores.  ammsb_store_create_shareable allocates pi/phi with the CUDA virtual-memory
+ * API so that another process maps them with full-size pages: a cudaIpc import maps peer memory
+ * with small pages, and NVLink row gathers from a multi-GB shard then run at 195 GB/s instead of
+ * 735 GB/s (measured, tools/peer_probe.py).  export_fd yields two POSIX file descriptors (pi,
+ * phi) to be passed to the peer process (SCM_RIGHTS); attach_fd / add_mirror_fd are the
+ * counterparts of ammsb_store_attach / ammsb_store_add_mirror.  The caller closes the fds. */
+int ammsb_store_create_shareable(ammsb_ctx* ctx, uint64_t N, uint32_t K, uint32_t num_shards,
+                                 uint32_t shard_id, ammsb_store** out);
+int ammsb_store_export_fd(ammsb_store* store, int* pi_fd, int* phi_fd);
+int ammsb_store_attach_fd(ammsb_store* store, uint32_t shard, int pi_fd, int phi_fd);
+int ammsb_store_add_mirror_fd(ammsb_store* store, int pi_fd, int phi_fd);
+
 /* Replicated mode (pi fits on every GPU): each GPU holds a full copy (num_shards = 1) and
  * registers the other GPUs' copies as mirrors; reads stay in local HBM and ammsb_update_pi*
  * writes every updated row to the local copy and to all mirrors (NVLink peer stores). */

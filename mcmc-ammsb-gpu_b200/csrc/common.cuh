@@ -10,6 +10,7 @@
 #include <string>
 
 #include "../../include/ammsb.h"
+#include "vmm.h"
 #include "zig_tables.h"
 
 // ---------------------------------------------------------------- host side --
@@ -104,6 +105,11 @@ struct ammsb_store {
   float* mirror_phi[AMMSB_MAX_SHARDS] = {nullptr};
   bool mirror_is_ipc[AMMSB_MAX_SHARDS] = {false};
   uint32_t num_mirrors = 0;
+  // shareable stores (virtual-memory API): own allocations and the peers' imported ones
+  bool shareable = false;
+  VmmAlloc vmm_pi, vmm_phi;
+  VmmAlloc vmm_peer_pi[AMMSB_MAX_SHARDS], vmm_peer_phi[AMMSB_MAX_SHARDS];
+  VmmAlloc vmm_mirror_pi[AMMSB_MAX_SHARDS], vmm_mirror_phi[AMMSB_MAX_SHARDS];
   StoreView view() const;
 };
 

@@ -253,8 +253,8 @@ StoreView ammsb_store::view() const {
   return v;
 }
 
-extern "C" int ammsb_store_create(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t num_shards,
-                                  uint32_t shard_id, ammsb_store** out) {
+static int store_create_impl(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t num_shards, uint32_t shard_id,
+                             bool shareable, ammsb_store** out) {
   AMMSB_REQUIRE(N > 0 && K > 0, "empty store");
   AMMSB_REQUIRE(N < 0xffffffffull, "N must fit a 32-bit Vertex (types.h:32)");
   AMMSB_REQUIRE(num_shards >= 1 && num_shards <= AMMSB_MAX_SHARDS, "num_shards out of range");
@@ -271,12 +271,64 @@ extern "C" int ammsb_store_create(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t
   uint64_t end = s->first_row + s->rows_per_shard;
   if (end > N) end = N;
   s->local_rows = end > s->first_row ? end - s->first_row : 0;
+  s->shareable = shareable;
   // every shard is allocated at the full rows_per_shard so that row addressing is uniform
-  AMMSB_CHECK_CUDA(cudaMalloc((void**)&s->d_pi, sizeof(float) * s->rows_per_shard * K));
-  AMMSB_CHECK_CUDA(cudaMalloc((void**)&s->d_phi, sizeof(float) * s->rows_per_shard));
+  if (shareable) {
+    if (vmm_alloc(c->device, sizeof(float) * s->rows_per_shard * K, &s->vmm_pi) ||
+        vmm_alloc(c->device, sizeof(float) * s->rows_per_shard, &s->vmm_phi)) {
+      delete s;
+      return 1;
+    }
+    s->d_pi = reinterpret_cast<float*>(s->vmm_pi.ptr);
+    s->d_phi = reinterpret_cast<float*>(s->vmm_phi.ptr);
+  } else {
+    AMMSB_CHECK_CUDA(cudaMalloc((void**)&s->d_pi, sizeof(float) * s->rows_per_shard * K));
+    AMMSB_CHECK_CUDA(cudaMalloc((void**)&s->d_phi, sizeof(float) * s->rows_per_shard));
+  }
   s->peer_pi[shard_id] = s->d_pi;
   s->peer_phi[shard_id] = s->d_phi;
   *out = s;
+  return 0;
+}
+
+extern "C" int ammsb_store_create(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t num_shards,
+                                  uint32_t shard_id, ammsb_store** out) {
+  return store_create_impl(c, N, K, num_shards, shard_id, false, out);
+}
+
+extern "C" int ammsb_store_create_shareable(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t num_shards,
+                                            uint32_t shard_id, ammsb_store** out) {
+  return store_create_impl(c, N, K, num_shards, shard_id, true, out);
+}
+
+extern "C" int ammsb_store_export_fd(ammsb_store* s, int* pi_fd, int* phi_fd) {
+  AMMSB_REQUIRE(s->shareable, "store was not created with ammsb_store_create_shareable");
+  if (vmm_export_fd(s->vmm_pi, pi_fd)) return 1;
+  return vmm_export_fd(s->vmm_phi, phi_fd);
+}
+
+extern "C" int ammsb_store_attach_fd(ammsb_store* s, uint32_t shard, int pi_fd, int phi_fd) {
+  AMMSB_REQUIRE(shard < s->num_shards && shard != s->shard_id, "bad peer shard");
+  if (vmm_import_fd(s->ctx->device, pi_fd, sizeof(float) * s->rows_per_shard * s->K, &s->vmm_peer_pi[shard]) ||
+      vmm_import_fd(s->ctx->device, phi_fd, sizeof(float) * s->rows_per_shard, &s->vmm_peer_phi[shard]))
+    return 1;
+  s->peer_pi[shard] = reinterpret_cast<float*>(s->vmm_peer_pi[shard].ptr);
+  s->peer_phi[shard] = reinterpret_cast<float*>(s->vmm_peer_phi[shard].ptr);
+  s->peer_is_ipc[shard] = false;
+  return 0;
+}
+
+extern "C" int ammsb_store_add_mirror_fd(ammsb_store* s, int pi_fd, int phi_fd) {
+  AMMSB_REQUIRE(s->num_shards == 1, "mirrors belong to a replicated (num_shards = 1) store");
+  AMMSB_REQUIRE(s->num_mirrors < AMMSB_MAX_SHARDS - 1, "too many mirrors");
+  const uint32_t i = s->num_mirrors;
+  if (vmm_import_fd(s->ctx->device, pi_fd, sizeof(float) * s->rows_per_shard * s->K, &s->vmm_mirror_pi[i]) ||
+      vmm_import_fd(s->ctx->device, phi_fd, sizeof(float) * s->rows_per_shard, &s->vmm_mirror_phi[i]))
+    return 1;
+  s->mirror_pi[i] = reinterpret_cast<float*>(s->vmm_mirror_pi[i].ptr);
+  s->mirror_phi[i] = reinterpret_cast<float*>(s->vmm_mirror_phi[i].ptr);
+  s->mirror_is_ipc[i] = false;
+  ++s->num_mirrors;
   return 0;
 }
 
@@ -295,8 +347,19 @@ extern "C" int ammsb_store_destroy(ammsb_store* s) {
       cudaIpcCloseMemHandle(s->mirror_phi[i]);
     }
   }
-  cudaFree(s->d_pi);
-  if (s->owns_phi) cudaFree(s->d_phi);
+  for (int i = 0; i < AMMSB_MAX_SHARDS; ++i) {
+    vmm_free(&s->vmm_peer_pi[i]);
+    vmm_free(&s->vmm_peer_phi[i]);
+    vmm_free(&s->vmm_mirror_pi[i]);
+    vmm_free(&s->vmm_mirror_phi[i]);
+  }
+  if (s->shareable) {
+    vmm_free(&s->vmm_pi);
+    vmm_free(&s->vmm_phi);
+  } else {
+    cudaFree(s->d_pi);
+    if (s->owns_phi) cudaFree(s->d_phi);
+  }
   delete s;
   return 0;
 }
@@ -405,7 +468,8 @@ extern "C" int ammsb_store_local_ptrs(ammsb_store* s, float** d_pi, float** d_ph
 
 extern "C" int ammsb_store_bind_phi(ammsb_store* s, float* d_phi) {
   AMMSB_REQUIRE(d_phi != nullptr, "null phi");
-  AMMSB_REQUIRE(s->num_shards == 1 && s->num_mirrors == 0, "bind_phi is for a single, unmirrored store");
+  AMMSB_REQUIRE(s->num_shards == 1 && s->num_mirrors == 0 && !s->shareable,
+                "bind_phi is for a single, unmirrored, non-shareable store");
   AMMSB_CHECK_CUDA(cudaSetDevice(s->ctx->device));
   if (s->owns_phi) {
     AMMSB_CHECK_CUDA(cudaMemcpyAsync(d_phi, s->d_phi, sizeof(float) * s->local_rows, cudaMemcpyDeviceToDevice,

@@ -65,6 +65,55 @@ def exchange(obj, world, group=None):
     return out
 
 
+_fd_round = [0]
+
+
+def exchange_fds(rank, world, fds):
+    """every rank hands its file descriptors to every other rank (SCM_RIGHTS over unix-domain
+    sockets); returns {peer rank: [fds as valid in this process]}.  Collective."""
+    import socket
+    import struct
+    import torch.distributed as dist
+    _fd_round[0] += 1
+    tag = "%s_%d" % (os.environ.get("MASTER_PORT", "0"), _fd_round[0])
+
+    def path(r):
+        return "/tmp/ammsb_fd_%s_%d.sock" % (tag, r)
+    try:
+        os.unlink(path(rank))
+    except FileNotFoundError:
+        pass
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path(rank))
+    srv.listen(world)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            conn.recv(4)
+            socket.send_fds(conn, [b"x"], list(fds))
+            conn.recv(1)  # the peer has the descriptors
+            conn.close()
+    th = threading.Thread(target=serve)
+    th.start()
+    dist.barrier()  # every server is listening
+    out = {}
+    for p in range(world):
+        if p == rank:
+            continue
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.connect(path(p))
+        c.send(struct.pack("i", rank))
+        _, got, _, _ = socket.recv_fds(c, 16, len(fds))
+        c.send(b"k")
+        c.close()
+        out[p] = list(got)
+    th.join()
+    srv.close()
+    os.unlink(path(rank))
+    return out
+
+
 class _Buf:
     """a device pointer seen as a pyammsb buffer (torch tensor storage or a sub-range)"""
 
@@ -96,24 +145,32 @@ class ShardedLearner:
         self.ctx = A.Ctx(local_rank)
         self.ctx.set_stream(self.stream.cuda_stream)
         dev = torch.device("cuda", local_rank)
-        # ---- pi/phi store; peers attached by IPC handle ----
+        # ---- pi/phi store; peers mapped through shared file descriptors ----
         #   partitioned: shard `rank` of a node-partitioned matrix, neighbor rows of other
         #                shards are read over NVLink (the layout for graphs that need G GPUs)
         #   replicated:  a full copy per GPU (when N*K*4 fits), reads are local HBM and every
         #                updated row is written to all copies over NVLink
         assert store_mode in ("partitioned", "replicated")
         self.store_mode = store_mode if world > 1 else "partitioned"
+        # Shards are allocated with the CUDA virtual-memory API and shared as file descriptors:
+        # a cudaIpc import maps peer memory with small pages and NVLink row gathers from a
+        # multi-GB shard drop to 195 GB/s (735 GB/s with full-size pages, tools/peer_probe.py).
+        shareable = world > 1
         if self.store_mode == "replicated":
-            self.store = A.Store(self.ctx, self.N, self.K, 1, 0)
-            for s, (hp, hf) in enumerate(exchange(self.store.export_handles(), world)):
-                if s != rank:
-                    self.store.add_mirror(hp, hf)
+            self.store = A.Store(self.ctx, self.N, self.K, 1, 0, shareable=shareable)
         else:
-            self.store = A.Store(self.ctx, self.N, self.K, world, rank)
-            if world > 1:
-                for s, (hp, hf) in enumerate(exchange(self.store.export_handles(), world)):
-                    if s != rank:
-                        self.store.attach(s, hp, hf)
+            self.store = A.Store(self.ctx, self.N, self.K, world, rank, shareable=shareable)
+        if world > 1:
+            mine = self.store.export_fds()
+            for peer, (fd_pi, fd_phi) in sorted(exchange_fds(rank, world, mine).items()):
+                if self.store_mode == "replicated":
+                    self.store.add_mirror_fds(fd_pi, fd_phi)
+                else:
+                    self.store.attach_fds(peer, fd_pi, fd_phi)
+                os.close(fd_pi)
+                os.close(fd_phi)
+            for fd in mine:
+                os.close(fd)
         self.store.init_pi(float(self.p.eta0), float(self.p.eta1))
         # ---- replicated: edge sets, theta/beta, RNG pools ----
         t_tab, t_bins, t_prime = cfg.set_table(0)

@@ -291,9 +291,10 @@ class DevSet:
 
 
 class Store:
-    def __init__(self, ctx, N, K, num_shards=1, shard_id=0):
+    def __init__(self, ctx, N, K, num_shards=1, shard_id=0, shareable=False):
         h = C.c_void_p()
-        _ck(lib().ammsb_store_create(ctx.h, C.c_uint64(N), K, num_shards, shard_id, C.byref(h)))
+        create = lib().ammsb_store_create_shareable if shareable else lib().ammsb_store_create
+        _ck(create(ctx.h, C.c_uint64(N), K, num_shards, shard_id, C.byref(h)))
         self.h, self.ctx, self.N, self.K = h, ctx, N, K
         self.num_shards, self.shard_id = num_shards, shard_id
         a, b = C.c_uint64(0), C.c_uint64(0)
@@ -337,6 +338,17 @@ class Store:
         a = (C.c_uint8 * 64).from_buffer_copy(pi_handle)
         b = (C.c_uint8 * 64).from_buffer_copy(phi_handle)
         _ck(lib().ammsb_store_attach(self.h, shard, a, b))
+
+    def export_fds(self):
+        a, b = C.c_int(-1), C.c_int(-1)
+        _ck(lib().ammsb_store_export_fd(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def attach_fds(self, shard, pi_fd, phi_fd):
+        _ck(lib().ammsb_store_attach_fd(self.h, shard, pi_fd, phi_fd))
+
+    def add_mirror_fds(self, pi_fd, phi_fd):
+        _ck(lib().ammsb_store_add_mirror_fd(self.h, pi_fd, phi_fd))
 
     def add_mirror(self, pi_handle, phi_handle):
         a = (C.c_uint8 * 64).from_buffer_copy(pi_handle)

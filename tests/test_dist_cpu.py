@@ -62,6 +62,17 @@ def _worker(rank, world, port, out_dir):
     got = D.exchange((rank, bytes([rank]) * 64), world)
     assert [g[0] for g in got] == list(range(world)) and got[rank][1] == bytes([rank]) * 64
 
+    # file-descriptor exchange (how the shareable pi shards travel between processes)
+    import tempfile
+    f = tempfile.TemporaryFile()
+    f.write(b"rank%d" % rank)
+    f.flush()
+    peers = D.exchange_fds(rank, world, [f.fileno()])
+    assert sorted(peers) == [r for r in range(world) if r != rank]
+    for peer, fds in peers.items():
+        assert os.pread(fds[0], 16, 0) == b"rank%d" % peer
+        os.close(fds[0])
+
     # beta gradient: per-rank chunk + all-reduce == whole mini-batch on one device
     edges = prob.minibatch_edges(101, 3)
     scale, step = 12.5, 3
