@@ -268,7 +268,9 @@ def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(w, args.steps, args.warmup, None, log=lambda *a: print(*a, file=sys.stderr))
+    # same workload as the B200 arm at this N: the global mini-batch is N x m edges
+    r = cpu_reference(dict(w, m=w["m"] * args.gpus), args.steps, args.warmup, None,
+                      log=lambda *a: print(*a, file=sys.stderr))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(r["iterations"], 1),

@@ -8,7 +8,9 @@
 // (warp -> CTA -> grid) in double precision.
 #include "common.cuh"
 
-#define PPX_WARPS 8
+// 128-thread CTAs: 91 registers/thread lets 5 of them share an SM (20 warps x 8 KB of row loads in
+// flight); with 256 threads only 2 CTAs (16 warps) fit.
+#define PPX_WARPS 4
 
 struct PpxArgs {
   StoreView sv;
@@ -22,7 +24,7 @@ struct PpxArgs {
   double* partial;  // [gridDim.x][4]
 };
 
-__global__ void __launch_bounds__(PPX_WARPS * 32) k_perplexity(const __grid_constant__ PpxArgs a) {
+__global__ void __launch_bounds__(PPX_WARPS * 32, 5) k_perplexity(const __grid_constant__ PpxArgs a) {
   extern __shared__ __align__(16) float s_beta[];  // [K]
   __shared__ double s_part[PPX_WARPS][4];
   const uint32_t K = a.K;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(128) k_ppx_reduce(const double* __restrict__ p
   if (lane == 0) sums[q] = s;
 }
 
-static uint32_t ppx_max_ctas(const ammsb_ctx* c) { return (uint32_t)c->sm_count * 8; }
+static uint32_t ppx_max_ctas(const ammsb_ctx* c) { return (uint32_t)c->sm_count * 10; }
 
 extern "C" int ammsb_perplexity_workspace_bytes(ammsb_ctx* c, size_t* bytes) {
   *bytes = sizeof(double) * 4 * (size_t)ppx_max_ctas(c) + sizeof(double) * 4;
