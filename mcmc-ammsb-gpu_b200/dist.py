@@ -190,7 +190,13 @@ class ShardedLearner:
         # ---- mini-batch buffers ----
         self.d_nodes = torch.empty(self.Vmax, dtype=torch.int32, device=dev)
         self.d_edges = torch.empty(self.Emax, dtype=torch.int64, device=dev)
-        self.d_nb = torch.empty(self.Vmax * n, dtype=torch.int32, device=dev)
+        self.d_nbs = [torch.empty(self.Vmax * n, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.ns_stream = torch.cuda.Stream()
+        self.ctx_ns = A.Ctx(local_rank)
+        self.ctx_ns.set_stream(self.ns_stream.cuda_stream)
+        self.ev_ns = [torch.cuda.Event() for _ in range(2)]
+        self.ev_phi = [torch.cuda.Event() for _ in range(2)]
+        self.ns_seq = 0
         self.d_vec = torch.empty(self.Vmax * self.K, dtype=torch.float32, device=dev)
         self.d_sum = torch.empty(self.Vmax, dtype=torch.float32, device=dev)
         self.d_tsum = torch.empty(self.K, dtype=torch.float32, device=dev)
@@ -291,17 +297,35 @@ class ShardedLearner:
         if self.world > 1:
             self.dist.all_reduce(self.flag)
 
-    def device_step(self, d_nodes, d_edges, V, E_mb, weight, pool_index, phi_events=None):
+    def enqueue_neighbors(self, d_nodes, V, pool_index, seq, after=None):
+        """neighbor sampling of mini-batch number `seq` on the sampler stream, into neighbor
+        buffer seq & 1 -- concurrent with the kernels of the previous mini-batch, as the
+        reference prepares the next Sample on its own queue (learner.cc:216-232)"""
+        if self.ns_seq >= seq:
+            return
+        b = seq & 1
+        self.ns_stream.wait_event(self.ev_phi[b])  # update_phi of mini-batch seq-2 is done with the buffer
+        if after is not None:
+            self.ns_stream.wait_event(after)  # the nodes are on this GPU
+        self.ctx_ns.neighbor_sample(self.npools[pool_index], d_nodes, V, self.N, self.n, 32, tbuf(self.d_nbs[b]))
+        self.ev_ns[b].record(self.ns_stream)
+        self.ns_seq = seq
+
+    def device_step(self, d_nodes, d_edges, V, E_mb, weight, pool_index, phi_events=None, seq=None):
         """one iteration on device-resident mini-batch buffers (pyammsb-style buffers)"""
         ctx, p, K = self.ctx, self.p, self.K
         self.step_count += 1
-        ctx.neighbor_sample(self.npools[pool_index], d_nodes, V, self.N, self.n, 32, tbuf(self.d_nb))
+        seq = self.step_count if seq is None else seq
+        self.enqueue_neighbors(d_nodes, V, pool_index, seq)  # no-op when it was enqueued ahead
+        d_nb = self.d_nbs[seq & 1]
+        self.stream.wait_event(self.ev_ns[seq & 1])
         if phi_events is not None:
             phi_events[0].record(self.stream)
-        ctx.update_phi(p, self.opts, tbuf(self.beta), self.store, self.train, d_nodes, tbuf(self.d_nb), V,
+        ctx.update_phi(p, self.opts, tbuf(self.beta), self.store, self.train, d_nodes, tbuf(d_nb), V,
                        self.step_count, self.ppool, tbuf(self.d_vec), tbuf(self.d_sum))
         if phi_events is not None:
             phi_events[1].record(self.stream)
+        self.ev_phi[seq & 1].record(self.stream)
         self.barrier()  # every read of the old pi is done before any rank writes
         ctx.update_pi_part(K, self.store, tbuf(self.d_vec), tbuf(self.d_sum), d_nodes, V, self.opts)
         self.barrier()  # every write is visible before beta reads pi
@@ -326,8 +350,9 @@ class ShardedLearner:
         weight = float(hdr.view(np.float64)[2])
         self.stream.wait_event(self.ev_payload[b])
         base = self.payload[b].data_ptr()
-        self.device_step(_Buf(base + self.HDR + 8 * self.Emax), _Buf(base + self.HDR), V, E_mb, weight,
-                         t % self.STREAMS)
+        d_nodes = _Buf(base + self.HDR + 8 * self.Emax)
+        self.enqueue_neighbors(d_nodes, V, t % self.STREAMS, t + 1, after=self.ev_payload[b])
+        self.device_step(d_nodes, _Buf(base + self.HDR), V, E_mb, weight, t % self.STREAMS, seq=t + 1)
         self.ev_free[b].record(self.stream)
         self._issue(t + 1)  # travels while the kernels of t run
         self.h_beta.copy_(self.beta, non_blocking=True)
@@ -406,10 +431,16 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     d_edges_all = ctx.from_host(np.concatenate([b[1] for b in batches]))
     d_nodes_all = ctx.from_host(np.concatenate([b[2] for b in batches]))
 
+    def nodes_of(i):
+        return _Buf(d_nodes_all.ptr.value + 4 * int(v_off[i]))
+
     def step(i, ev=None):
         wgt, edges, nodes = batches[i]
-        lrn.device_step(_Buf(d_nodes_all.ptr.value + 4 * int(v_off[i])), _Buf(d_edges_all.ptr.value + 8 * int(e_off[i])),
-                        len(nodes), len(edges), wgt, i % lrn.STREAMS, ev)
+        lrn.enqueue_neighbors(nodes_of(i), len(nodes), i % lrn.STREAMS, i + 1)
+        if i + 1 < total:  # the next mini-batch's neighbors are drawn while this one is processed
+            lrn.enqueue_neighbors(nodes_of(i + 1), len(batches[i + 1][2]), (i + 1) % lrn.STREAMS, i + 2)
+        lrn.device_step(nodes_of(i), _Buf(d_edges_all.ptr.value + 8 * int(e_off[i])), len(nodes), len(edges), wgt,
+                        i % lrn.STREAMS, ev, seq=i + 1)
 
     for i in range(args.warmup):
         step(i)
