@@ -790,14 +790,16 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
     if (kpl <= 4) return launch_fast<4, 8, 4, 2>(c, a);
     if (kpl <= 8) return launch_fast<8, 6, 4, 2>(c, a);
     if (kpl <= 16) {
-      if (getenv("AMMSB_PHI_WS16A")) return launch_fast<16, 4, 4, 1, 2>(c, a);  // experiments
-      if (getenv("AMMSB_PHI_WS16B")) return launch_fast<16, 6, 4, 1, 2>(c, a);
-      if (getenv("AMMSB_PHI_WS16C")) return launch_fast<16, 8, 4, 1, 2>(c, a);
-      return launch_fast<16, 4, 4>(c, a);  // NB = 2 costs occupancy here (measured -6%)
+      // NB = 2 costs occupancy here (measured -6%); producer warps do not pay either at K = 512
+      // (8 gather warps/SM cannot cover 2 KB rows: 5.28 vs 5.32 TB/s)
+      return launch_fast<16, 4, 4>(c, a);
     }
     // 4 gather warps x 4 stages + 2 noise-producer warps, 2 CTAs/SM: 6.10 TB/s at K = 1024
     // (the all-in-one <32,3,4> kernel: 5.66 TB/s; without noise both reach 6.3 TB/s)
     if (getenv("AMMSB_PHI_NOWS")) return launch_fast<32, 3, 4>(c, a);
+    // few slots (link mini-batches: V = 1 + deg(u)): the launch is a latency chain of row
+    // round trips, not bandwidth -- one gather warp per CTA with 16 rows in flight
+    if (my_units(a) <= (uint32_t)c->sm_count && !getenv("AMMSB_PHI_NOSMALL")) return launch_fast<32, 16, 1, 1, 1>(c, a);
     return launch_fast<32, 4, 4, 1, 2>(c, a);
   }
   // K in (1024, 4096]: teams of 2 or 4 warps per slot (one slot per unit, i.e. V <= 65535)

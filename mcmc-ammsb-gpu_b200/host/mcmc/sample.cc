@@ -122,7 +122,10 @@ Float sampleNodeLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* 
 // seed is rewound to the draw that completed the mini-batch, so the stream position -- and
 // with it every later mini-batch -- is the reference's.
 Float sampleNodeNonLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed) {
-  thread_local StdOrderSet<Edge> picked;  // std::unordered_set<Edge> order, flat storage
+  // std::unordered_set<Edge> order, flat storage; bound to a reference once: in a shared
+  // library every direct use of a thread_local goes through the TLS wrapper
+  thread_local StdOrderSet<Edge> tls_picked;
+  StdOrderSet<Edge>& picked = tls_picked;
   picked.Clear();
   const Vertex u = DrawVertex(cfg, seed);
   const size_t m = cfg.mini_batch_size;
@@ -219,22 +222,21 @@ Float sampleBreadthFirst(const Config& cfg, std::vector<Edge>* edges, unsigned i
 }
 
 void ExtractNodesFromMiniBatch(const std::vector<Edge>& edges, std::vector<Vertex>* nodes_vec) {
-  thread_local StdOrderSet<Vertex> nodes;  // std::unordered_set<Vertex> order (learner.cc:164-172)
+  thread_local StdOrderSet<Vertex> tls_nodes;  // std::unordered_set<Vertex> order (learner.cc:164-172)
+  StdOrderSet<Vertex>& nodes = tls_nodes;
   nodes.Clear();
-  // a vertex that has just been inserted (or found) need not be looked up again: re-inserting
-  // a present key never changes the set.  Node-strategy mini-batches share one endpoint.
-  bool have_last = false;
-  Vertex last = 0;
+  // An endpoint shared with the previous edge is already in the set, and re-inserting a present
+  // key never changes the set: skip it.  Node-strategy mini-batches share one endpoint
+  // throughout, so this halves the lookups.
+  Vertex p0 = 0, p1 = 0;
+  bool have_prev = false;
   for (Edge e : edges) {
-    const Vertex ends[2] = {static_cast<Vertex>(e >> 32), static_cast<Vertex>(e & 0xffffffffu)};
-    for (Vertex v : ends) {
-      if (have_last && v == last) continue;
-      nodes.Insert(v);
-    }
-    // the shared endpoint is whichever end repeats; remember the first end, and the second
-    // when the first keeps changing
-    if (!have_last) { last = ends[0]; have_last = true; }
-    else if (ends[0] != last && ends[1] != last) last = ends[0];
+    const Vertex a = static_cast<Vertex>(e >> 32), b = static_cast<Vertex>(e & 0xffffffffu);
+    if (!(have_prev && (a == p0 || a == p1))) nodes.Insert(a);
+    if (!(have_prev && (b == p0 || b == p1))) nodes.Insert(b);
+    p0 = a;
+    p1 = b;
+    have_prev = true;
   }
   nodes_vec->clear();
   nodes.EmitTo(nodes_vec);
