@@ -11,6 +11,9 @@
 //                        contraction.  It is the on-device twin of the CPU oracle.
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 struct PhiArgs {
@@ -681,6 +684,31 @@ __global__ void __launch_bounds__(192) k_update_phi_team(const __grid_constant__
   }
 }
 
+// cudaFuncSetAttribute + the occupancy query cost microseconds of host time per launch; their
+// result depends only on (kernel, device, block, smem), so it is computed once per combination.
+template <class Kern>
+static int resident_ctas_per_sm(Kern kern, int device, int block, size_t smem, int* occ_out) {
+  struct Entry { const void* fn; int device, block; size_t smem; int occ; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  const void* fn = reinterpret_cast<const void*>(kern);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : cache)
+      if (e.fn == fn && e.device == device && e.block == block && e.smem == smem) {
+        *occ_out = e.occ;
+        return 0;
+      }
+  }
+  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+  std::lock_guard<std::mutex> lock(mu);
+  cache.push_back(Entry{fn, device, block, smem, occ});
+  *occ_out = occ;
+  return 0;
+}
+
 // number of units (and so of concurrently useful warps / CTAs) this rank owns
 static uint32_t my_units(const PhiArgs& a) {
   const uint32_t active = a.units < a.V ? a.units : a.V;
@@ -694,9 +722,8 @@ static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   const bool exact = (a.K == 32u * KPL);
   auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB, NW>
                     : k_update_phi_fast<KPL, STAGES, WARPS, false, NB, NW>;
-  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (WARPS + NW) * 32, smem));
+  if (resident_ctas_per_sm(kern, c->device, (WARPS + NW) * 32, smem, &occ)) return 1;
   AMMSB_REQUIRE(occ > 0, "update_phi: kernel does not fit on an SM");
   const uint32_t active = my_units(a);
   if (active == 0) return 0;
@@ -716,9 +743,8 @@ static int launch_team(ammsb_ctx* c, const PhiArgs& a) {
                       (size_t)4 * (STAGES + 1) * 8 + (size_t)teams_per_cta * 4 * 8 + (size_t)teams_per_cta * 3 * T * 4;
   const bool exact = (KS == 32u * KPL);
   auto kern = exact ? k_update_phi_team<KPL, STAGES, T, true> : k_update_phi_team<KPL, STAGES, T, false>;
-  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 192, smem));
+  if (resident_ctas_per_sm(kern, c->device, 192, smem, &occ)) return 1;
   AMMSB_REQUIRE(occ > 0, "update_phi: team kernel does not fit on an SM");
   const uint32_t active = my_units(a);
   if (active == 0) return 0;
