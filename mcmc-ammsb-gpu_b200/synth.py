@@ -11,6 +11,10 @@ SHAPES = {
     "com-DBLP": (317080, 1049866, 1024, 0.10),
     "com-LiveJournal": (3997962, 34681189, 1024, 0.01),
     "com-Friendster": (65608366, 1806067135, 512, 0.01),
+    # Friendster-sized pi store (N x K = 134 GB) over a graph with a reduced edge count that a
+    # host can build in a minute: exercises the partitioned store and its NVLink gathers at the
+    # Friendster scale without the 1.8 G-edge host-side graph build
+    "com-Friendster-store": (65608366, 20000000, 512, 0.01),
 }
 
 

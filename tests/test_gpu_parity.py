@@ -477,3 +477,65 @@ def test_update_phi_fast_matches_strict_over_shapes(ctx, orc, K, n, V):
     for b in (d_nodes, d_nb, d_beta):
         b.free()
     dset.free(); st.free()
+
+
+def test_shareable_store_fd_roundtrip_matches_plain_store(ctx, orc):
+    """the multi-process path on one GPU: two shards allocated with the virtual-memory API,
+    each attached to the other through exported file descriptors (what dist.exchange_fds moves
+    between ranks), give the same update_phi / update_pi results as a single plain store"""
+    import os
+    K, V, n, N = 256, 120, 8, 601
+    prob = link_heavy_problem(orc, N, K, n)
+    nodes = prob.minibatch_nodes(V, 6)
+    neighbors, _ = orc.neighbor_sample(orc.rng_pool(V * 2 * n, 56, 57), nodes, N, n, 32)
+    d_nodes, d_nb, d_beta = ctx.from_host(nodes), ctx.from_host(neighbors), ctx.from_host(prob.beta)
+    dset = dev_set(ctx, prob.train_set)
+    p = dev_params(prob.p_orc)
+
+    def run(stores_for_rank, ranks):
+        r = A.Rng(ctx, V * 32, 42, 43)
+        d_vec, d_sum = ctx.buf(np.float32, V * K).zero(), ctx.buf(np.float32, V).zero()
+        for rank in range(ranks):
+            ctx.update_phi(p, A.PhiOpts(A.MODE_WG, 32, 0, 0, rank, ranks), d_beta, stores_for_rank[rank], dset, d_nodes,
+                           d_nb, V, 1, r, d_vec, d_sum)
+        for rank in range(ranks):
+            ctx.update_pi_part(K, stores_for_rank[rank], d_vec, d_sum, d_nodes, V,
+                               A.PhiOpts(A.MODE_WG, 32, 0, 0, rank, ranks))
+        out = d_vec.read()
+        d_vec.free(); d_sum.free(); r.free()
+        return out
+
+    plain = dev_store(ctx, prob)
+    want_vec = run([plain], 1)
+    want_pi, want_phi = plain.read_pi(), plain.read_phi()
+    shards = [A.Store(ctx, N, K, 2, s, shareable=True) for s in range(2)]
+    for s in shards:
+        lo, hi = s.first_row, s.first_row + s.local_rows
+        s.write_pi(prob.pi[lo:hi])
+        s.write_phi(prob.phi[lo:hi])
+    for a, b in ((0, 1), (1, 0)):
+        fds = shards[b].export_fds()
+        shards[a].attach_fds(b, *fds)
+        for fd in fds:
+            os.close(fd)
+    got_vec = run(shards, 2)
+    assert np.array_equal(got_vec, want_vec)
+    got_pi = np.concatenate([s.read_pi() for s in shards])
+    got_phi = np.concatenate([s.read_phi() for s in shards])
+    assert np.array_equal(got_pi, want_pi) and np.array_equal(got_phi, want_phi)
+    # replicated layout: a mirror attached by file descriptor receives every updated row
+    reps = [A.Store(ctx, N, K, 1, 0, shareable=True) for _ in range(2)]
+    for s in reps:
+        s.write_pi(prob.pi)
+        s.write_phi(prob.phi)
+    fds = reps[1].export_fds()
+    reps[0].add_mirror_fds(*fds)
+    for fd in fds:
+        os.close(fd)
+    assert np.array_equal(run([reps[0]], 1), want_vec)
+    assert np.array_equal(reps[1].read_pi(), want_pi) and np.array_equal(reps[0].read_pi(), want_pi)
+    for b in (d_nodes, d_nb, d_beta):
+        b.free()
+    for s in shards + reps + [plain]:
+        s.free()
+    dset.free()
