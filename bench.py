@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--store", default="auto", choices=["auto", "partitioned", "replicated"],
                     help="multi-GPU pi layout: node-partitioned (NVLink peer loads) or one copy per GPU")
+    ap.add_argument("--collectives", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU exchange steps: own kernels over NVLink peer memory, or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

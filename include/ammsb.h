@@ -235,6 +235,21 @@ int ammsb_perplexity(ammsb_ctx* ctx, const ammsb_params* p, ammsb_store* store,
                      double* h_sums /* [4], may be NULL */, double* h_avg,
                      void* d_workspace, size_t workspace_bytes);
 
+/* ---- multi-GPU exchange steps as kernels over NVLink peer memory (one process per GPU; the
+ *      reference has no multi-device code).  A mailbox per rank, shared with the peers as a
+ *      file descriptor like the pi shards.  ammsb_peer_barrier: every rank's earlier work on its
+ *      stream is complete and its peer stores are visible.  ammsb_peer_allreduce_*: sum over
+ *      ranks in RANK ORDER (bit-identical on every rank; count * sizeof(T) <= slot_bytes).
+ *      All ranks must issue the same sequence of these calls. ---- */
+typedef struct ammsb_peer ammsb_peer;
+int ammsb_peer_create(ammsb_ctx* ctx, uint32_t world, uint32_t rank, size_t slot_bytes, ammsb_peer** out);
+int ammsb_peer_destroy(ammsb_peer* peer);
+int ammsb_peer_export_fd(ammsb_peer* peer, int* fd);
+int ammsb_peer_attach_fd(ammsb_peer* peer, uint32_t peer_rank, int fd);
+int ammsb_peer_barrier(ammsb_ctx* ctx, ammsb_peer* peer);
+int ammsb_peer_allreduce_f32(ammsb_ctx* ctx, ammsb_peer* peer, float* d_inout, uint32_t count);
+int ammsb_peer_allreduce_f64(ammsb_ctx* ctx, ammsb_peer* peer, double* d_inout, uint32_t count);
+
 /* ---- work-group helpers the reference tests directly (wg-sum-test.cc,
  *      wg-normalize-test.cc): rows of `len` floats, one warp per row, reference
  *      association for wg = 32 (sum.cc:31-42, normalize.cc:13-32). ---- */

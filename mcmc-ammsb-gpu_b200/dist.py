@@ -132,7 +132,8 @@ class ShardedLearner:
 
     STREAMS = 4  # independent host sampler streams (the reference has 2: its two Samples)
 
-    def __init__(self, cfg, rank, world, local_rank, seed=12345, prefetch=True, store_mode="partitioned"):
+    def __init__(self, cfg, rank, world, local_rank, seed=12345, prefetch=True, store_mode="partitioned",
+                 collectives="peer"):
         import torch
         import torch.distributed as dist
         import pyammsb as A
@@ -171,6 +172,19 @@ class ShardedLearner:
                 os.close(fd_phi)
             for fd in mine:
                 os.close(fd)
+        # ---- the exchange steps: kernels over NVLink peer memory (csrc/peer.cu), or NCCL ----
+        #   "peer": cross-GPU barrier and rank-ordered all-reduce as our own kernels on a mailbox
+        #           shared like the shards (deterministic sum order, no library launch latency)
+        #   "nccl": torch.distributed all-reduces (baseline / fallback)
+        assert collectives in ("peer", "nccl")
+        self.peer = None
+        if world > 1 and collectives == "peer":
+            self.peer = A.Peer(self.ctx, world, rank, max(8 * self.K, 64))
+            fd = self.peer.export_fd()
+            for peer_rank, (pfd,) in sorted(exchange_fds(rank, world, [fd]).items()):
+                self.peer.attach_fd(peer_rank, pfd)
+                os.close(pfd)
+            os.close(fd)
         self.store.init_pi(float(self.p.eta0), float(self.p.eta1))
         # ---- replicated: edge sets, theta/beta, RNG pools ----
         t_tab, t_bins, t_prime = cfg.set_table(0)
@@ -294,7 +308,9 @@ class ShardedLearner:
 
     # --------------------------------------------------------- iteration ----
     def barrier(self):
-        if self.world > 1:
+        if self.peer is not None:
+            self.peer.barrier()
+        elif self.world > 1:
             self.dist.all_reduce(self.flag)
 
     def enqueue_neighbors(self, d_nodes, V, pool_index, seq, after=None):
@@ -332,7 +348,9 @@ class ShardedLearner:
         lo, hi = chunk(E_mb, self.rank, self.world)
         ctx.beta_grads(p, tbuf(self.theta), tbuf(self.beta), self.store, self.train,
                        _Buf(d_edges.ptr.value + 8 * lo), hi - lo, tbuf(self.d_tsum), tbuf(self.grads), tbuf(self.ws))
-        if self.world > 1:
+        if self.peer is not None:
+            self.peer.allreduce_f32(tbuf(self.grads), 2 * K)  # summed in rank order on every rank
+        elif self.world > 1:
             self.dist.all_reduce(self.grads)
         ctx.update_theta(p, tbuf(self.theta), tbuf(self.beta), tbuf(self.grads), weight, self.step_count, self.bpool)
         self.edges_processed += E_mb
@@ -370,7 +388,9 @@ class ShardedLearner:
                                         self.H_local, tbuf(self.d_ppx), self.ppx_calls, tbuf(self.sums), tbuf(self.pws))
         else:
             self.sums.zero_()
-        if self.world > 1:
+        if self.peer is not None:
+            self.peer.allreduce_f64(tbuf(self.sums), 4)
+        elif self.world > 1:
             self.dist.all_reduce(self.sums)
         s = self.sums.cpu().numpy()
         avg = (s[0] + s[1]) / (s[2] + s[3]) if (s[2] + s[3]) != 0 else 0.0  # perplexity.cc:264-273
@@ -417,7 +437,8 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     mode = getattr(args, "store", "auto")
     if mode == "auto":  # replicate while a full copy (plus mini-batch buffers) is a small part of 180 GB
         mode = "replicated" if 4.0 * N * K <= 48e9 else "partitioned"
-    lrn = ShardedLearner(cfg, rank, world, local_rank, prefetch=False, store_mode=mode)
+    coll = getattr(args, "collectives", "peer")
+    lrn = ShardedLearner(cfg, rank, world, local_rank, prefetch=False, store_mode=mode, collectives=coll)
     stream = lrn.stream
     ctx = lrn.ctx
 
@@ -509,7 +530,7 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     # ---- e2e leg: host mini-batches through the sharded driver ----
     e2e = None
     if not args.no_e2e:
-        l2 = ShardedLearner(cfg, rank, world, local_rank, prefetch=True, store_mode=mode)
+        l2 = ShardedLearner(cfg, rank, world, local_rank, prefetch=True, store_mode=mode, collectives=coll)
         for _ in range(args.warmup):
             l2.host_step()
         dist.barrier()
@@ -542,7 +563,9 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
                                        "pi/phi replicated on %d GPUs (fits: %.1f GB), mini-batch slots split over "
                                        "GPUs, updated rows written to every copy by NVLink peer stores, "
                                        % (world, 4.0 * N * K / 1e9)) +
-                                      "beta gradient and perplexity sums all-reduced (NCCL)",
+                                      ("beta gradient and perplexity sums all-reduced in rank order and phases ordered "
+                                       "by our own kernels over NVLink peer memory" if coll == "peer" else
+                                       "beta gradient and perplexity sums all-reduced (NCCL)"),
                        "l2": "inputs larger than L2 (pi %.2f GB, %.2f GB of rows gathered per non-link step)"
                              % (4.0 * N * K / 1e9, (m + 1) * (n + 2) * 4 * K / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},

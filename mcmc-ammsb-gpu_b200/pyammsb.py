@@ -290,6 +290,37 @@ class DevSet:
             self.h = None
 
 
+class Peer:
+    """cross-GPU barrier / rank-ordered all-reduce over NVLink peer memory (csrc/peer.cu)"""
+
+    def __init__(self, ctx, world, rank, slot_bytes):
+        h = C.c_void_p()
+        _ck(lib().ammsb_peer_create(ctx.h, world, rank, C.c_size_t(slot_bytes), C.byref(h)))
+        self.h, self.ctx, self.world, self.rank = h, ctx, world, rank
+
+    def export_fd(self):
+        fd = C.c_int(-1)
+        _ck(lib().ammsb_peer_export_fd(self.h, C.byref(fd)))
+        return fd.value
+
+    def attach_fd(self, peer_rank, fd):
+        _ck(lib().ammsb_peer_attach_fd(self.h, peer_rank, fd))
+
+    def barrier(self, ctx=None):
+        _ck(lib().ammsb_peer_barrier((ctx or self.ctx).h, self.h))
+
+    def allreduce_f32(self, d_buf, count, ctx=None):
+        _ck(lib().ammsb_peer_allreduce_f32((ctx or self.ctx).h, self.h, d_buf.ptr, count))
+
+    def allreduce_f64(self, d_buf, count, ctx=None):
+        _ck(lib().ammsb_peer_allreduce_f64((ctx or self.ctx).h, self.h, d_buf.ptr, count))
+
+    def free(self):
+        if self.h is not None:
+            lib().ammsb_peer_destroy(self.h)
+            self.h = None
+
+
 class Store:
     def __init__(self, ctx, N, K, num_shards=1, shard_id=0, shareable=False):
         h = C.c_void_p()

@@ -30,7 +30,8 @@ def main():
     cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=0.1, strategy="Node")
     cfg.set_graph(N, make_edges(N, 30000, 3))
     mode = sys.argv[1] if len(sys.argv) > 1 else "partitioned"
-    sharded = D.ShardedLearner(cfg, rank, world, local, prefetch=False, store_mode=mode)
+    coll = sys.argv[2] if len(sys.argv) > 2 else "peer"
+    sharded = D.ShardedLearner(cfg, rank, world, local, prefetch=False, store_mode=mode, collectives=coll)
     single = D.ShardedLearner(cfg, 0, 1, local, prefetch=False)
     lo, hi = sharded.local_rows()
 
@@ -64,7 +65,12 @@ def main():
     p1, q1 = sharded.heldout_perplexity(), single.heldout_perplexity()
     assert abs(p1 - q1) <= 1e-3 * q1, (p1, q1)
     # the host path (sampler threads + pinned staging) runs too
-    e2e = D.ShardedLearner(cfg, rank, world, local, prefetch=True, store_mode=mode)
+    e2e = D.ShardedLearner(cfg, rank, world, local, prefetch=True, store_mode=mode, collectives=coll)
+    # replicas of theta/beta are bit-identical across ranks (rank-ordered sum / same NCCL result)
+    mine = torch.from_numpy(sharded.read_beta()).cuda()
+    ref = mine.clone()
+    tdist.broadcast(ref, 0)
+    assert torch.equal(mine, ref), "beta replicas differ across ranks"
     e2e.run(6)
     assert np.isfinite(e2e.heldout_perplexity())
     tdist.barrier()
