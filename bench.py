@@ -110,7 +110,10 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            t0 = time.time()
+            while time.time() - t0 < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.02)  # nvidia-smi takes a moment to deliver its first sample
         except Exception:
             self.proc = None
 
@@ -392,14 +395,15 @@ def run_b200(args, w):
         ctx.update_pi(K, store, d_vec, d_sum, dn, V)
         ctx.update_beta(p, d_theta, d_beta, store, dts, de, Emb, wgt, step_no, bpool, d_ts, d_g, ws)
 
+    # clocks are sampled from before the warm-up until after the per-stage timings: the GPU is busy
+    # throughout, and the timed region lies inside that window
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for i in range(args.warmup):
         device_step(i, i + 1)
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    time.sleep(0.3)
     launches0 = A.launch_count()
     torch.cuda.synchronize()
     e_start.record(stream)
@@ -409,7 +413,6 @@ def run_b200(args, w):
     torch.cuda.synchronize()
     launches = A.launch_count() - launches0
     dev_ms = e_start.elapsed_time(e_stop)
-    clk = clocks.stop()
     timed = batches[args.warmup:]
     edges_timed = int(sum(len(b[1]) for b in timed))
     phi_ms = float(sum(a.elapsed_time(b) for a, b in evs))
@@ -454,6 +457,7 @@ def run_b200(args, w):
     t_stage("update_beta", lambda: ctx.update_beta(p, d_theta, d_beta, store, dts, de, Eb, 2.0 * E / m, 7, bpool,
                                                    d_ts, d_g, ws), bytes_beta(Eb, K))
     t_stage("perplexity", f_ppx, bytes_ppx(H, K))
+    clk = clocks.stop()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

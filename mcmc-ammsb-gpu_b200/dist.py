@@ -463,13 +463,13 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
         lrn.device_step(nodes_of(i), _Buf(d_edges_all.ptr.value + 8 * int(e_off[i])), len(nodes), len(edges), wgt,
                         i % lrn.STREAMS, ev, seq=i + 1)
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # sampled from before the warm-up to the end of the timed region
     for i in range(args.warmup):
         step(i)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     dist.barrier()
     torch.cuda.synchronize()
     launches0 = A.launch_count()
