@@ -148,6 +148,16 @@ class ClockSampler:
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
                        samples=len(sm), power_w_max=float(max(power)))
+        else:  # the sampler delivered nothing inside the window: one synchronous query, flagged as such
+            try:
+                txt = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                f = [x.strip() for x in txt.strip().split(",")]
+                out.update(sm_mhz=float(f[1]), sm_max_mhz=float(f[2]), samples=1, power_w_max=float(f[3]),
+                           reasons=[n for n, v in zip(names, f[5:9]) if v == "Active"],
+                           note="sampled right after the timed region")
+            except Exception:
+                pass
         return out
 
 
