@@ -516,7 +516,7 @@ def run_b200(args, w):
         e2e = {"value": e_edges / dt, "unit": UNIT, "h2d_bytes_per_step": (lrn.h2d_bytes() - b0) / args.steps,
                "d2h_bytes_per_step": 8 * K, "iterations_per_s": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
                "api": "mcmc::Learner::Run(steps): per iteration the host mini-batch sampler (sample.cc strategies; "
-                      "two sampler streams, each a 2-stage thread pipeline over a ring of 4 mini-batches), H2D of "
+                      "two sampler streams, each a 3-stage thread pipeline over a ring of 6 mini-batches), H2D of "
                       "edges/nodes, 7 kernels, D2H of beta[2K] into pinned host memory; 2 iterations in flight",
                "heldout_perplexity": ppx, "perplexity_eval_s": ppx_s}
         lrn.close()

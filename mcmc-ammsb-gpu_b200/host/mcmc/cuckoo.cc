@@ -1,5 +1,6 @@
 #include "mcmc/cuckoo.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -20,15 +21,22 @@ const uint64_t kPrimePairs[4][2] = {{15485807ull, 920429591ull},
 Set::Set(size_t n)
     : inserted_(0),
       bins_(static_cast<size_t>(1 + std::ceil((1.15 * n) / (NUM_BUCKETS * NUM_SLOTS)))),
+      mod_bins_(bins_),
       rand_state_(42),
       max_displacements_(n / 2 + 1),
       prime_idx_(0) {}
 
 size_t Set::Bin(Edge k, size_t bucket) const {
-  return bucket == 0 ? (kPrimePairs[prime_idx_][0] * k) % bins_ : (k ^ kPrimePairs[prime_idx_][1]) % bins_;
+  // (P1 * k) % bins (64-bit wrap of the product) and (k ^ P2) % bins, reference cuckoo.cc:199-209
+  return bucket == 0 ? mod_bins_.Mod(kPrimePairs[prime_idx_][0] * k) : mod_bins_.Mod(k ^ kPrimePairs[prime_idx_][1]);
 }
 
 bool Set::SetContents(std::vector<Edge>::const_iterator start, std::vector<Edge>::const_iterator end) {
+  {
+    std::lock_guard<std::mutex> lock(index_mu_);
+    index_built_ = false;
+    index_.reset();
+  }
   for (prime_idx_ = 0; prime_idx_ < 4; ++prime_idx_) {
     cells_.assign(Capacity(), KEY_INVALID);
     bool ok = true;
@@ -93,6 +101,44 @@ bool Set::Has(Edge k) const {
       if (cell[s] == k) return true;
   }
   return false;
+}
+
+const Set::Partners* Set::PartnerIndex() const {
+  std::lock_guard<std::mutex> lock(index_mu_);
+  if (index_built_) return index_.get();
+  index_built_ = true;
+  [this] {
+    size_t keys = 0;
+    Vertex top = 0;
+    for (Edge e : cells_) {
+      if (e == KEY_INVALID) continue;
+      ++keys;
+      top = std::max(top, std::max(static_cast<Vertex>(e >> 32), static_cast<Vertex>(e)));
+    }
+    if (keys == 0 || keys > kMaxIndexedKeys) return;
+    std::unique_ptr<Partners> idx(new Partners);
+    idx->offsets.assign(static_cast<size_t>(top) + 2, 0);
+    // a key stored with its endpoints out of order can never equal a canonical query: skipped
+    for (Edge e : cells_) {
+      if (e == KEY_INVALID) continue;
+      const Vertex a = static_cast<Vertex>(e >> 32), b = static_cast<Vertex>(e);
+      if (a > b) continue;
+      ++idx->offsets[a + 1];
+      if (a != b) ++idx->offsets[b + 1];
+    }
+    for (size_t i = 1; i < idx->offsets.size(); ++i) idx->offsets[i] += idx->offsets[i - 1];
+    idx->partners.resize(idx->offsets.back());
+    std::vector<uint64_t> fill(idx->offsets.begin(), idx->offsets.end() - 1);
+    for (Edge e : cells_) {
+      if (e == KEY_INVALID) continue;
+      const Vertex a = static_cast<Vertex>(e >> 32), b = static_cast<Vertex>(e);
+      if (a > b) continue;
+      idx->partners[fill[a]++] = b;
+      if (a != b) idx->partners[fill[b]++] = a;
+    }
+    index_ = std::move(idx);
+  }();
+  return index_.get();
 }
 
 OpenClSet::OpenClSet(std::shared_ptr<OpenClSetFactory> factory, clcuda::Queue queue, const Set& set)

@@ -8,8 +8,10 @@
 #include <array>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <vector>
 
+#include "mcmc/fastmod.h"
 #include "mcmc/types.h"
 
 namespace mcmc {
@@ -51,6 +53,21 @@ class Set {
   // flat [bucket][bin][slot] image, the layout the device lookup indexes
   std::vector<Edge> Serialize() const { return cells_; }
 
+  // The stored keys seen from one endpoint: Partners(u) lists every v for which the canonical
+  // key (min(u,v) << 32 | max(u,v)) is stored, so Has(canonical(u, v)) == "v is in Partners(u)".
+  // Built from the cells on first use (hence consistent with Has() by construction) and only
+  // for sets of at most kMaxIndexedKeys keys; PartnerIndex() returns nullptr otherwise.  The
+  // non-link mini-batch strategy tests thousands of pairs that share one endpoint: with the
+  // partner list of that endpoint it needs no table lookups (each of which is two cache misses).
+  struct Partners {
+    std::vector<uint64_t> offsets;  // [max vertex + 2]
+    std::vector<Vertex> partners;
+    const Vertex* begin(Vertex u) const { return u + 1 < offsets.size() ? partners.data() + offsets[u] : nullptr; }
+    const Vertex* end(Vertex u) const { return u + 1 < offsets.size() ? partners.data() + offsets[u + 1] : nullptr; }
+  };
+  static const size_t kMaxIndexedKeys = size_t(1) << 27;
+  const Partners* PartnerIndex() const;
+
  private:
   size_t Bin(Edge k, size_t bucket) const;
   Edge* Cell(size_t bucket, size_t bin) { return &cells_[(bucket * bins_ + bin) * NUM_SLOTS]; }
@@ -59,10 +76,14 @@ class Set {
 
   size_t inserted_;
   const size_t bins_;
+  const FastMod64 mod_bins_;  // k % bins_ without a divide (same value)
   std::vector<Edge> cells_;
   unsigned int rand_state_;
   const size_t max_displacements_;
   uint32_t prime_idx_;
+  mutable std::mutex index_mu_;
+  mutable bool index_built_ = false;
+  mutable std::unique_ptr<Partners> index_;
 };
 
 class OpenClSetFactory;

@@ -116,11 +116,13 @@ Float sampleNodeLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* 
 // distinct pairs.  (u == v is not excluded and no v is ever blacklisted -- kept as is.)
 // Scale 2E/m.
 //
-// The reference consumes one rand_r draw per candidate whatever its fate, so the candidate
-// stream does not depend on the membership answers: candidates are drawn a block at a time,
-// their cuckoo bins hashed and prefetched together, and then examined in draw order.  The
-// seed is rewound to the draw that completed the mini-batch, so the stream position -- and
-// with it every later mini-batch -- is the reference's.
+// The reference consumes one rand_r draw per candidate whatever its fate and asks both cuckoo
+// sets about every candidate (two random 32-byte bins each: four cache misses per draw).  All
+// candidates of a mini-batch share the endpoint u, so here the sets are asked once, up front:
+// the stored keys that involve u (Set::PartnerIndex(), a handful) are marked as refused in the
+// very table that de-duplicates the picks, and a candidate then costs its rand_r draw plus the
+// one probe it needed anyway.  Same answers, same draw count, same stream position.  Sets too
+// large to index fall back to block-wise hashing with prefetch.
 Float sampleNodeNonLink(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed) {
   // std::unordered_set<Edge> order, flat storage; bound to a reference once: in a shared
   // library every direct use of a thread_local goes through the TLS wrapper
@@ -129,25 +131,37 @@ Float sampleNodeNonLink(const Config& cfg, std::vector<Edge>* edges, unsigned in
   picked.Clear();
   const Vertex u = DrawVertex(cfg, seed);
   const size_t m = cfg.mini_batch_size;
-  const int kBlock = 32;
-  Edge cand[kBlock];
-  unsigned int after[kBlock];
-  size_t hb[kBlock][2], tb[kBlock][2];
+  const uint32_t n_vertices = static_cast<uint32_t>(cfg.N);
+  const bool narrow = cfg.N <= 0xffffffffull;  // rand_r() % N in 32 bits is the same number
+  const Set::Partners* in_heldout = cfg.heldout ? cfg.heldout->PartnerIndex() : nullptr;
+  const Set::Partners* in_training = cfg.training->PartnerIndex();
   unsigned int s = *seed;
-  while (picked.size() < m) {
-    const int take = static_cast<int>(std::min<size_t>(kBlock, m - picked.size()));
-    for (int i = 0; i < take; ++i) {
-      cand[i] = Canonical(u, rand_r(&s) % cfg.N);
-      after[i] = s;
-      cfg.heldout->Locate(cand[i], hb[i]);
-      cfg.training->Locate(cand[i], tb[i]);
+  if (narrow && in_training != nullptr && (in_heldout != nullptr || !cfg.heldout)) {
+    for (const Set::Partners* idx : {in_heldout, in_training}) {
+      if (idx == nullptr) continue;
+      for (const Vertex* v = idx->begin(u); v != idx->end(u); ++v) picked.Block(Canonical(u, *v));
     }
-    // at most `take` insertions can happen, so the block never overshoots m mid-way
-    for (int i = 0; i < take; ++i) {
-      if (cfg.heldout->HasAt(cand[i], hb[i]) || cfg.training->HasAt(cand[i], tb[i])) continue;
-      picked.Insert(cand[i]);
+    while (picked.size() < m) picked.Insert(Canonical(u, static_cast<uint32_t>(rand_r(&s)) % n_vertices));
+  } else {
+    const int kBlock = 32;
+    Edge cand[kBlock];
+    unsigned int after[kBlock];
+    size_t hb[kBlock][2], tb[kBlock][2];
+    while (picked.size() < m) {
+      const int take = static_cast<int>(std::min<size_t>(kBlock, m - picked.size()));
+      for (int i = 0; i < take; ++i) {
+        cand[i] = Canonical(u, rand_r(&s) % cfg.N);
+        after[i] = s;
+        cfg.heldout->Locate(cand[i], hb[i]);
+        cfg.training->Locate(cand[i], tb[i]);
+      }
+      // at most `take` insertions can happen, so the block never overshoots m mid-way
+      for (int i = 0; i < take; ++i) {
+        if (cfg.heldout->HasAt(cand[i], hb[i]) || cfg.training->HasAt(cand[i], tb[i])) continue;
+        picked.Insert(cand[i]);
+      }
+      s = after[take - 1];
     }
-    s = after[take - 1];
   }
   *seed = s;
   picked.EmitTo(edges);
@@ -325,6 +339,7 @@ Sample::~Sample() {
   cv_.notify_all();
   if (a_.joinable()) a_.join();
   if (b_.joinable()) b_.join();
+  if (c_.joinable()) c_.join();
 }
 
 void Sample::Start(Strategy strategy, SamplerStats* stats) {
@@ -332,6 +347,7 @@ void Sample::Start(Strategy strategy, SamplerStats* stats) {
   stats_ = stats;
   a_ = std::thread(&Sample::StageA, this);
   b_ = std::thread(&Sample::StageB, this);
+  c_ = std::thread(&Sample::StageC, this);
 }
 
 namespace {
@@ -366,20 +382,40 @@ void Sample::StageA() {
   }
 }
 
-// stage B: ExtractNodesFromMiniBatch + Buffer::Write x2 + NeighborSampler (learner.cc:175-194)
+// stage B: ExtractNodesFromMiniBatch (learner.cc:162-173, 177-178)
 void Sample::StageB() {
   std::unique_lock<std::mutex> lock(mu_);
   for (;;) {
-    cv_.wait(lock, [this] { return stop_ || (ready_ < drawn_ && !error_); });
+    cv_.wait(lock, [this] { return stop_ || (extracted_ < drawn_ && !error_); });
     if (stop_) return;
-    SampleSlot& slot = *ring[ready_ % kRing];
+    SampleSlot& slot = *ring[extracted_ % kRing];
     lock.unlock();
     std::exception_ptr err;
     try {
       const uint64_t t0 = NowNs();
       ExtractNodesFromMiniBatch(slot.edges, &slot.nodes_vec);
-      const uint64_t t1 = NowNs();
+      stats_->extract += NowNs() - t0;
       if (slot.nodes_vec.empty()) throw BackendError("mini-batch size = 0!");
+    } catch (...) {
+      err = std::current_exception();
+    }
+    lock.lock();
+    if (err) error_ = err; else ++extracted_;
+    cv_.notify_all();
+  }
+}
+
+// stage C: Buffer::Write x2 + NeighborSampler (learner.cc:179-193)
+void Sample::StageC() {
+  std::unique_lock<std::mutex> lock(mu_);
+  for (;;) {
+    cv_.wait(lock, [this] { return stop_ || (ready_ < extracted_ && !error_); });
+    if (stop_) return;
+    SampleSlot& slot = *ring[ready_ % kRing];
+    lock.unlock();
+    std::exception_ptr err;
+    try {
+      const uint64_t t1 = NowNs();
       if (slot.edges.size() > slot.dev_edges.GetSize() / sizeof(Edge) ||
           slot.nodes_vec.size() > slot.dev_nodes.GetSize() / sizeof(Vertex))
         throw BackendError("mini-batch exceeds the device buffers");
@@ -388,7 +424,6 @@ void Sample::StageB() {
       const uint64_t t2 = NowNs();
       neighbor_sampler(static_cast<uint32_t>(slot.nodes_vec.size()), &slot.dev_nodes, &slot.neighbors);
       const uint64_t t3 = NowNs();
-      stats_->extract += t1 - t0;
       stats_->copy += t2 - t1;
       stats_->neighbors += t3 - t2;
       stats_->h2d_bytes += slot.edges.size() * sizeof(Edge) + slot.nodes_vec.size() * sizeof(Vertex);
@@ -460,7 +495,7 @@ bool Sample::Parse(std::istream* in, bool pending) {
   Quiesce();
   std::unique_lock<std::mutex> lock(mu_);
   // restart the counters: the parsed mini-batch lands in slot 0
-  drawn_ = ready_ = 1;
+  drawn_ = extracted_ = ready_ = 1;
   consumed_ = pending ? 0 : 1;
   allowed_ = drawn_;
   SampleSlot& slot = *ring[0];

@@ -94,10 +94,12 @@ struct SampleSlot {
 // NeighborSampler with its own RNG pool).  The Learner alternates between two of them.
 //
 // The reference draws mini-batch t+1 on one std::async thread while t is processed
-// (learner.cc:216-232).  Here each stream is a two-stage pipeline over a small ring of slots,
-//   stage A (thread): host strategy with the stream's seed           -> slot.edges, weight
-//   stage B (thread): node extraction, H2D copies, neighbor sampling -> device buffers
-// so several mini-batches of a stream are in flight.  Nothing in either stage reads the model,
+// (learner.cc:216-232).  Here each stream is a three-stage pipeline over a small ring of slots,
+//   stage A (thread): host strategy with the stream's seed -> slot.edges, weight
+//   stage B (thread): node extraction                      -> slot.nodes_vec
+//   stage C (thread): H2D copies, neighbor sampling        -> device buffers
+// so several mini-batches of a stream are in flight.  (Stage C mostly waits: the neighbor
+// kernel shares the GPU with an update_phi launch that holds every SM.)  Nothing in either stage reads the model,
 // and each stage handles the stream's mini-batches strictly in order (seed and RNG pool advance
 // exactly as in the reference), so the mini-batches are the same; only how far ahead they are
 // drawn differs.  `Allow()` bounds that: a Run(n) call lets the streams draw only the n
@@ -105,7 +107,7 @@ struct SampleSlot {
 // Serialize() on return is the reference's.
 struct Sample {
   typedef Float (*Strategy)(const Config& cfg, std::vector<Edge>* edges, unsigned int* seed);
-  static const uint64_t kRing = 4;
+  static const uint64_t kRing = 6;
 
   clcuda::Queue queue;
   std::vector<std::unique_ptr<SampleSlot>> ring;
@@ -131,15 +133,16 @@ struct Sample {
  private:
   void StageA();
   void StageB();
+  void StageC();
   const Config& cfg_;
   Strategy strategy_ = nullptr;
   SamplerStats* stats_ = nullptr;
   std::mutex mu_;
   std::condition_variable cv_;
-  uint64_t drawn_ = 0, ready_ = 0, consumed_ = 0, allowed_ = 0;  // mini-batches of this stream
+  uint64_t drawn_ = 0, extracted_ = 0, ready_ = 0, consumed_ = 0, allowed_ = 0;  // mini-batches of this stream
   bool stop_ = false, a_busy_ = false;
   std::exception_ptr error_;
-  std::thread a_, b_;
+  std::thread a_, b_, c_;
 };
 
 }  // namespace mcmc
