@@ -517,7 +517,7 @@ def run_b200(args, w):
                "d2h_bytes_per_step": 8 * K, "iterations_per_s": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
                "api": "mcmc::Learner::Run(steps): per iteration the host mini-batch sampler (sample.cc strategies; "
                       "two sampler streams, each a 3-stage thread pipeline over a ring of 6 mini-batches), H2D of "
-                      "edges/nodes, 7 kernels, D2H of beta[2K] into pinned host memory; 2 iterations in flight",
+                      "edges/nodes, 5 kernels (neighbor sampling, update_phi, update_pi, beta partials, beta reduction + theta step), D2H of beta[2K] into pinned host memory; 2 iterations in flight",
                "heldout_perplexity": ppx, "perplexity_eval_s": ppx_s}
         lrn.close()
 

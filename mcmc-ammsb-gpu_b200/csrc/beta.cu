@@ -283,14 +283,48 @@ __global__ void __launch_bounds__(BETA_WARPS * 32)
   }
 }
 
+// one Langevin step of theta_k and beta_k = theta_k / (theta_k0 + theta_k1): update_theta
+// (beta.cc:51-82) + CopyTo(beta) + WG_NORMALIZE_KERNEL rows of 2 (beta.cc:378-379,
+// normalize.cc:13-32).  State index k, two normals per k.
+__device__ __forceinline__ void theta_step(float* __restrict__ theta, float* __restrict__ beta, float g0, float g1,
+                                           uint32_t k, float eps_t, float eta0, float eta1, float scale,
+                                           ulonglong2* pool) {
+  Rng s = rng_load(pool, k);
+  const float half = __fdiv_rn(eps_t, 2.0f);
+  const float r0 = rng_randn(s);
+  float t0 = theta[2 * k];
+  const float f0 = __fsqrt_rn(__fmul_rn(eps_t, t0));
+  t0 = fabsf(__fadd_rn(__fadd_rn(t0, __fmul_rn(half, __fadd_rn(__fsub_rn(eta0, t0), __fmul_rn(scale, g0)))),
+                       __fmul_rn(f0, r0)));
+  t0 = fmaxf(t0, 1e-24f);
+  const float r1 = rng_randn(s);
+  float t1 = theta[2 * k + 1];
+  const float f1 = __fsqrt_rn(__fmul_rn(eps_t, t1));
+  t1 = fabsf(__fadd_rn(__fadd_rn(t1, __fmul_rn(half, __fadd_rn(__fsub_rn(eta1, t1), __fmul_rn(scale, g1)))),
+                       __fmul_rn(f1, r1)));
+  t1 = fmaxf(t1, 1e-24f);
+  rng_store(pool, k, s);
+  theta[2 * k] = t0;
+  theta[2 * k + 1] = t1;
+  const float sum = __fadd_rn(__fadd_rn(0.f, t0), t1);
+  beta[2 * k] = __fdiv_rn(t0, sum);
+  beta[2 * k + 1] = __fdiv_rn(t1, sum);
+}
+
 // sum_theta (beta.cc:30-37) + the tail of calculate_grads_partial/sum_grads:
 //   g_k0 = A_k (1/theta_k0 - 1/thetaSum_k) - B_k / thetaSum_k
 //   g_k1 = B_k (1/theta_k1 - 1/thetaSum_k) - A_k / thetaSum_k        (beta.cc:130-135)
 #define BETA_RED_PY 16
+struct ThetaStep {  // the update_theta launch that follows, folded into the reduction's last stage
+  float* theta;     // nullptr: reduce only (multi-GPU: the gradient is all-reduced first)
+  float* beta;
+  float eps_t, eta0, eta1, scale;
+  ulonglong2* pool;
+};
 __global__ void __launch_bounds__(32 * BETA_RED_PY)
     k_beta_reduce(const float* __restrict__ partial, uint32_t P, uint32_t K,
                   const float* __restrict__ theta, float* __restrict__ theta_sum,
-                  float* __restrict__ grads) {
+                  float* __restrict__ grads, const ThetaStep ts_) {
   // 32 consecutive k per CTA; the P partials are split over BETA_RED_PY rows of threads
   // (p = py, py + PY, ...), combined in row order: a fixed association for a given P
   __shared__ float sA[BETA_RED_PY][32], sB[BETA_RED_PY][32];
@@ -315,8 +349,12 @@ __global__ void __launch_bounds__(32 * BETA_RED_PY)
   const float ts = __fadd_rn(t0, t1);
   const float rts = __fdiv_rn(1.0f, ts);
   theta_sum[k] = ts;
-  grads[2 * k] = A * (__fdiv_rn(1.0f, t0) - rts) + B * (0.0f - rts);
-  grads[2 * k + 1] = A * (0.0f - rts) + B * (__fdiv_rn(1.0f, t1) - rts);
+  const float g0 = A * (__fdiv_rn(1.0f, t0) - rts) + B * (0.0f - rts);
+  const float g1 = A * (0.0f - rts) + B * (__fdiv_rn(1.0f, t1) - rts);
+  grads[2 * k] = g0;
+  grads[2 * k + 1] = g1;
+  // theta_k is read and written by this thread only, and beta is no longer read by anyone
+  if (ts_.theta != nullptr) theta_step(ts_.theta, ts_.beta, g0, g1, k, ts_.eps_t, ts_.eta0, ts_.eta1, ts_.scale, ts_.pool);
 }
 
 // update_theta (beta.cc:51-82) + CopyTo(beta) + WG_NORMALIZE_KERNEL rows of 2
@@ -326,28 +364,7 @@ __global__ void k_update_theta(float* __restrict__ theta, float* __restrict__ be
                                float eta1, float scale, ulonglong2* pool) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  Rng s = rng_load(pool, k);
-  const float half = __fdiv_rn(eps_t, 2.0f);
-  const float r0 = rng_randn(s);
-  float t0 = theta[2 * k];
-  const float f0 = __fsqrt_rn(__fmul_rn(eps_t, t0));
-  t0 = fabsf(__fadd_rn(
-      __fadd_rn(t0, __fmul_rn(half, __fadd_rn(__fsub_rn(eta0, t0), __fmul_rn(scale, grads[2 * k])))),
-      __fmul_rn(f0, r0)));
-  t0 = fmaxf(t0, 1e-24f);
-  const float r1 = rng_randn(s);
-  float t1 = theta[2 * k + 1];
-  const float f1 = __fsqrt_rn(__fmul_rn(eps_t, t1));
-  t1 = fabsf(__fadd_rn(
-      __fadd_rn(t1, __fmul_rn(half, __fadd_rn(__fsub_rn(eta1, t1), __fmul_rn(scale, grads[2 * k + 1])))),
-      __fmul_rn(f1, r1)));
-  t1 = fmaxf(t1, 1e-24f);
-  rng_store(pool, k, s);
-  theta[2 * k] = t0;
-  theta[2 * k + 1] = t1;
-  const float sum = __fadd_rn(__fadd_rn(0.f, t0), t1);
-  beta[2 * k] = __fdiv_rn(t0, sum);
-  beta[2 * k + 1] = __fdiv_rn(t1, sum);
+  theta_step(theta, beta, grads[2 * k], grads[2 * k + 1], k, eps_t, eta0, eta1, scale, pool);
 }
 
 static uint32_t beta_max_ctas(const ammsb_ctx* c) { return (uint32_t)c->sm_count * 3; }
@@ -357,10 +374,10 @@ extern "C" int ammsb_beta_workspace_bytes(ammsb_ctx* c, uint32_t K, size_t* byte
   return 0;
 }
 
-extern "C" int ammsb_beta_grads(ammsb_ctx* c, const ammsb_params* p, const float* d_theta,
-                                const float* d_beta, ammsb_store* store, ammsb_set* train,
-                                const uint64_t* d_edges, uint32_t E_mb, float* d_theta_sum,
-                                float* d_grads, void* d_ws, size_t ws_bytes) {
+static int beta_grads_impl(ammsb_ctx* c, const ammsb_params* p, const float* d_theta,
+                           const float* d_beta, ammsb_store* store, ammsb_set* train,
+                           const uint64_t* d_edges, uint32_t E_mb, float* d_theta_sum,
+                           float* d_grads, void* d_ws, size_t ws_bytes, const ThetaStep& step) {
   AMMSB_REQUIRE(p->K == store->K, "params do not match the store");
   AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
   const uint32_t K = p->K;
@@ -402,9 +419,18 @@ extern "C" int ammsb_beta_grads(ammsb_ctx* c, const ammsb_params* p, const float
     AMMSB_LAUNCH_CHECK();
   }
   k_beta_reduce<<<(K + 31) / 32, 32 * BETA_RED_PY, 0, c->stream>>>((const float*)d_ws, ctas, K, d_theta,
-                                                        d_theta_sum, d_grads);
+                                                        d_theta_sum, d_grads, step);
   AMMSB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ammsb_beta_grads(ammsb_ctx* c, const ammsb_params* p, const float* d_theta,
+                                const float* d_beta, ammsb_store* store, ammsb_set* train,
+                                const uint64_t* d_edges, uint32_t E_mb, float* d_theta_sum,
+                                float* d_grads, void* d_ws, size_t ws_bytes) {
+  ThetaStep none = {};
+  return beta_grads_impl(c, p, d_theta, d_beta, store, train, d_edges, E_mb, d_theta_sum, d_grads, d_ws, ws_bytes,
+                         none);
 }
 
 extern "C" int ammsb_update_theta(ammsb_ctx* c, const ammsb_params* p, float* d_theta, float* d_beta,
@@ -419,12 +445,22 @@ extern "C" int ammsb_update_theta(ammsb_ctx* c, const ammsb_params* p, float* d_
   return 0;
 }
 
+// single-GPU path: the Langevin step of theta_k runs in the thread that finished the reduction
+// of column k (one launch less per iteration; same arithmetic as ammsb_beta_grads followed by
+// ammsb_update_theta)
 extern "C" int ammsb_update_beta(ammsb_ctx* c, const ammsb_params* p, float* d_theta, float* d_beta,
                                  ammsb_store* store, ammsb_set* train, const uint64_t* d_edges,
                                  uint32_t E_mb, float scale, uint32_t step_count, ammsb_rng* pool,
                                  float* d_theta_sum, float* d_grads, void* d_ws, size_t ws_bytes) {
-  int rc = ammsb_beta_grads(c, p, d_theta, d_beta, store, train, d_edges, E_mb, d_theta_sum,
-                            d_grads, d_ws, ws_bytes);
-  if (rc) return rc;
-  return ammsb_update_theta(c, p, d_theta, d_beta, d_grads, scale, step_count, pool);
+  AMMSB_REQUIRE(pool && pool->n >= p->K, "beta RNG pool smaller than K");
+  ThetaStep step;
+  step.theta = d_theta;
+  step.beta = d_beta;
+  step.eps_t = ammsb_eps_t(p, step_count);
+  step.eta0 = p->eta0;
+  step.eta1 = p->eta1;
+  step.scale = scale;
+  step.pool = pool->d_state;
+  return beta_grads_impl(c, p, d_theta, d_beta, store, train, d_edges, E_mb, d_theta_sum, d_grads, d_ws, ws_bytes,
+                         step);
 }

@@ -684,6 +684,151 @@ __global__ void __launch_bounds__(192) k_update_phi_team(const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------ split ---
+//
+// Few slots (link mini-batches: V = 1 + deg(u), a handful): the launch is a latency chain, not
+// bandwidth -- with one warp per slot the n neighbors are handled one after the other by a
+// single warp while 140 SMs idle.  Here a slot gets a whole CTA: its n neighbors are dealt
+// round-robin to WPS gather warps (warp w takes neighbors w, w + WPS, ...; a ring of R rows in
+// flight per warp, so all n rows of a 32-neighbor slot are requested at once), one more warp
+// draws the slot's Langevin noise meanwhile, and the per-warp gradient partials are added in
+// warp order (a fixed association, but not the neighbor-by-neighbor one of the kernels above:
+// results agree with them to fp32 rounding, not bit for bit -- which is why this kernel is chosen
+// by the mini-batch's slot count alone, never by the share a rank owns).  One slot per unit.
+template <int KPL, int WPS, int R, bool EXACT>
+__global__ void __launch_bounds__((WPS + 1) * 32) k_update_phi_split(const __grid_constant__ PhiArgs a) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const uint32_t K = a.K;
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t row_bytes = K * 4;
+  // layout: own row | noise row (later: the new phi row) | [WPS][R] stage rows | bar_own,
+  // [WPS][R] stage barriers
+  float* s_own = reinterpret_cast<float*>(s_raw);
+  float* s_noise = s_own + K;
+  float* s_stage_all = s_noise + K;
+  uint64_t* bar_own = reinterpret_cast<uint64_t*>(s_stage_all + (size_t)WPS * R * K);
+  uint64_t* bars_all = bar_own + 1;
+  const uint32_t slot = a.part_index + a.part_count * blockIdx.x;  // slot == unit
+  if (slot >= a.V || slot >= a.units) return;                      // CTA-uniform
+  const uint32_t node = __ldg(&a.nodes[slot]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_own, 1);
+    for (int i = 0; i < WPS * R; ++i) mbar_init(&bars_all[i], 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar_own, row_bytes);
+    bulk_g2s(s_own, store_row(a.sv, node), row_bytes, bar_own);
+  }
+  __syncthreads();
+  const float phi_sum = *store_phi(a.sv, node);
+
+  if (wib == WPS) {
+    // ---- noise warp: the unit's stream in the reference's per-state draw order ----
+    if (!a.disable_noise) {
+      if (a.mode == AMMSB_MODE_WG && a.wg == 32) {
+        Rng st = rng_load(a.pool, (uint64_t)slot * 32 + lane);
+        for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn(st);
+        rng_store(a.pool, (uint64_t)slot * 32 + lane, st);
+      } else {
+        const uint32_t vw = a.mode == AMMSB_MODE_THREAD ? 1u : a.wg;
+        for (uint32_t vl = lane; vl < vw; vl += 32) {
+          Rng vs = rng_load(a.pool, (uint64_t)slot * vw + vl);
+          for (uint32_t k = vl; k < K; k += vw) s_noise[k] = rng_randn(vs);
+          rng_store(a.pool, (uint64_t)slot * vw + vl, vs);
+        }
+      }
+    }
+  } else {
+    // ---- gather warp w: neighbors w, w + WPS, ... (lane i holds the i-th of them) ----
+    const uint32_t w = wib;
+    float* s_stage = s_stage_all + (size_t)w * R * K;
+    uint64_t* bars = bars_all + w * R;
+    const uint32_t cnt = a.n > w ? (a.n - w + WPS - 1) / WPS : 0;  // <= 32 (checked by the host)
+    const float* my_ptr = nullptr;
+    bool y = false;
+    if (lane < cnt) {
+      const uint32_t nb = __ldg(&a.neighbors[(size_t)slot * a.n + w + lane * WPS]);
+      my_ptr = store_row(a.sv, nb);
+      if (lane < R) {
+        mbar_expect_tx(&bars[lane], row_bytes);
+        bulk_g2s(s_stage + (size_t)lane * K, my_ptr, row_bytes, &bars[lane]);
+      }
+      y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+    }
+    const uint32_t mask = __ballot_sync(FULL_MASK, y);
+    float fb[KPL], g[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const uint32_t k = lane + 32 * i;
+      fb[i] = (EXACT || k < K) ? __ldg(&a.beta[2 * k + 1]) - a.epsilon : 0.f;
+      g[i] = 0.f;
+    }
+    const float e_link = a.epsilon, e_non = 1.0f - a.epsilon;
+    const float rphi = 1.0f / phi_sum;
+    uint32_t phase = 0;
+    mbar_wait(bar_own, 0);
+    for (uint32_t j = 0; j < cnt; ++j) {
+      const uint32_t s = j % R;
+      const bool link = (mask >> j) & 1;
+      const float e = link ? e_link : e_non;
+      const float sgn = link ? 1.0f : -1.0f;
+      mbar_wait(&bars[s], (phase >> s) & 1);
+      phase ^= 1u << s;
+      const float* row = s_stage + (size_t)s * K;
+      float t[KPL];
+      float S = 0.f;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const uint32_t k = lane + 32 * i;
+        if (EXACT || k < K) {
+          t[i] = fmaf(row[k], sgn * fb[i], e);
+          S = fmaf(s_own[k], t[i], S);
+        } else {
+          t[i] = 0.f;
+        }
+      }
+      __syncwarp();  // every lane has consumed the stage -> refill
+      if (j + R < cnt && lane == j + R) {
+        mbar_expect_tx(&bars[s], row_bytes);
+        bulk_g2s(s_stage + (size_t)s * K, my_ptr, row_bytes, &bars[s]);
+      }
+      S = warp_sum(S);
+      const float inv = 1.0f / (S * phi_sum);
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) g[i] += fmaf(t[i], inv, -rphi);
+    }
+    // partial gradient of this warp into its (drained) first stage row
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const uint32_t k = lane + 32 * i;
+      if (EXACT || k < K) s_stage[k] = g[i];
+    }
+  }
+  __syncthreads();  // partials and the noise row are complete
+  if (wib == WPS) mbar_wait(bar_own, 0);  // the noise warp has not yet observed the own-row copy
+
+  // Langevin step (phi.cc:266-274): every thread of the CTA takes columns t, t + threads, ...
+  const float half_eps = a.eps_t / 2;
+  float* out = a.phi_vec + (size_t)slot * K;
+  for (uint32_t k = threadIdx.x; k < K; k += (WPS + 1) * 32) {
+    float gk = 0.f;
+#pragma unroll
+    for (int w = 0; w < WPS; ++w) gk += s_stage_all[(size_t)w * R * K + k];
+    const float noise = a.disable_noise ? 1.0f : s_noise[k];
+    const float phi_k = s_own[k] * phi_sum;
+    float v = fabsf(phi_k + half_eps * (a.alpha - phi_k + a.Nn * gk) + sqrtf(a.eps_t * phi_k) * noise);
+    v = fmaxf(v, 1e-24f);
+    out[k] = v;
+    s_noise[k] = v;  // this thread's own column: no other reader of the noise value
+  }
+  __syncthreads();
+  if (wib == 0) {  // row sum in the association of the one-warp-per-slot kernels (= WG_SUM, wg 32)
+    float lsum = 0.f;
+    for (uint32_t k = lane; k < K; k += 32) lsum += s_noise[k];
+    lsum = warp_sum(lsum);
+    if (lane == 0) a.phi_sum[slot] = lsum;
+  }
+}
+
 // cudaFuncSetAttribute + the occupancy query cost microseconds of host time per launch; their
 // result depends only on (kernel, device, block, smem), so it is computed once per combination.
 template <class Kern>
@@ -700,7 +845,13 @@ static int resident_ctas_per_sm(Kern kern, int device, int block, size_t smem, i
         return 0;
       }
   }
-  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the limit is a property of the function, not of one launch: it is raised to the device
+  // maximum once and never lowered (a kernel is launched with different row sizes, and a cached
+  // entry must stay launchable after a smaller one was added)
+  int optin = 0;
+  AMMSB_CHECK_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  AMMSB_REQUIRE(smem <= (size_t)optin, "update_phi: shared memory request exceeds the device limit");
+  AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   int occ = 0;
   AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
   std::lock_guard<std::mutex> lock(mu);
@@ -731,6 +882,22 @@ static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   const uint32_t resident = (uint32_t)occ * c->sm_count;
   if (blocks > resident) blocks = resident;  // persistent: one wave, warps stride over units
   kern<<<blocks, (WARPS + NW) * 32, smem, c->stream>>>(a);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int KPL>
+static int launch_split(ammsb_ctx* c, const PhiArgs& a) {
+  constexpr int WPS = 8, R = 4;
+  const size_t smem = (size_t)(2 + WPS * R) * a.K * 4 + (size_t)(1 + WPS * R) * 8;
+  const bool exact = (a.K == 32u * KPL);
+  auto kern = exact ? k_update_phi_split<KPL, WPS, R, true> : k_update_phi_split<KPL, WPS, R, false>;
+  int occ = 0;
+  if (resident_ctas_per_sm(kern, c->device, (WPS + 1) * 32, smem, &occ)) return 1;
+  AMMSB_REQUIRE(occ > 0, "update_phi: split kernel does not fit on an SM");
+  const uint32_t blocks = my_units(a);
+  if (blocks == 0) return 0;
+  kern<<<blocks, (WPS + 1) * 32, smem, c->stream>>>(a);
   AMMSB_LAUNCH_CHECK();
   return 0;
 }
@@ -812,6 +979,16 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
   const bool fast_ok = !o->strict && (p->K % 4 == 0) && p->K <= 1024;
   if (fast_ok) {
     const uint32_t kpl = (p->K + 31) / 32;
+    // few slots (link mini-batches: V = 1 + deg(u)): a CTA per slot, neighbors split over its
+    // warps.  Chosen by the slot count of the whole mini-batch, so that every rank of a
+    // multi-GPU run takes the same path (the two paths differ in fp32 rounding).
+    if (V <= a.units && V <= (uint32_t)c->sm_count && a.n <= 256 && !getenv("AMMSB_PHI_NOSPLIT")) {
+      if (kpl <= 2) return launch_split<2>(c, a);
+      if (kpl <= 4) return launch_split<4>(c, a);
+      if (kpl <= 8) return launch_split<8>(c, a);
+      if (kpl <= 16) return launch_split<16>(c, a);
+      return launch_split<32>(c, a);
+    }
     if (kpl <= 2) return launch_fast<2, 8, 4, 2>(c, a);
     if (kpl <= 4) return launch_fast<4, 8, 4, 2>(c, a);
     if (kpl <= 8) return launch_fast<8, 6, 4, 2>(c, a);

@@ -2,6 +2,7 @@
 same seeded inputs.  Integer / index / membership results must be bit-exact; fp32
 results are held to the tolerance stated in each test."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -255,6 +256,33 @@ def test_update_phi_fast_nonstandard_wg_stream(ctx, orc):
         assert r["state_ok"]
         err = rel_err(r["got"], r["want"])
         assert float((err > RTOL).mean()) < 1e-3 and err.max() < 1e-3
+
+
+@pytest.mark.parametrize("K,n,V", [(1024, 32, 8), (1024, 32, 21), (64, 32, 7), (256, 5, 148), (1000, 250, 3),
+                                   (512, 64, 30)])
+@pytest.mark.parametrize("noise", [False, True])
+def test_update_phi_few_slots_kernel_vs_oracle(ctx, orc, K, n, V, noise):
+    """link mini-batches (V = 1 + deg(u) <= #SMs) take the CTA-per-slot kernel, whose gradient is a
+    sum of per-warp partials: same bars against the oracle as the one-warp-per-slot kernel, RNG
+    pool state bit-identical, and agreement with that kernel (AMMSB_PHI_NOSPLIT) to fp32 rounding"""
+    prob = link_heavy_problem(orc, 500, K, n, seed=K + V)
+    r = run_phi(ctx, orc, prob, V, A.MODE_WG, 32, noise, strict=False)
+    assert r["state_ok"], "phi RNG pool state diverged from the reference stream"
+    err = rel_err(r["got"], r["want"])
+    cond = np.abs(r["got"].astype(np.float64) - r["want"]) / phi_scale(prob, r)
+    assert cond.max() < 5e-7
+    assert float((err > RTOL).mean()) < 3e-3 and np.median(err) < 1e-6
+    epi = rel_err(r["pi_d"], r["pi_o"])
+    assert float((epi > RTOL).mean()) < 3e-3 and np.median(epi) < 1e-6
+    assert rel_err(r["phi_d"], r["phi_o"]).max() < RTOL
+    os.environ["AMMSB_PHI_NOSPLIT"] = "1"
+    try:
+        r1 = run_phi(ctx, orc, prob, V, A.MODE_WG, 32, noise, strict=False)
+    finally:
+        del os.environ["AMMSB_PHI_NOSPLIT"]
+    e2 = rel_err(r["got"], r1["got"])
+    assert np.median(e2) < 1e-6 and float((e2 > RTOL).mean()) < 3e-3
+    assert not np.array_equal(r["got"], r1["got"]) or n <= 8  # it really is another kernel
 
 
 # ---------------------------------------------------------- update_beta ----
