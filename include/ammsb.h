@@ -134,6 +134,48 @@ int ammsb_set_destroy(ammsb_set* set);
 int ammsb_set_has(ammsb_set* set, const uint64_t* h_keys, uint64_t n, uint8_t* h_out);
 int ammsb_set_has_device(ammsb_set* set, const uint64_t* d_keys, uint64_t n, uint8_t* d_out);
 
+/* On-device build of the same set (cuckoo::Set::SetContents, cuckoo.cc:117-161): table geometry
+ * (bins = 1 + ceil(1.15 n / 8), cuckoo.cc:98-104) and hash functions are the host's, so the
+ * lookup is unchanged; keys are placed in parallel, so the slot a key ends up in differs from the
+ * host's random walk while membership is the same.  Falls back through the four hash-constant
+ * pairs like the host build and fails with "Failed to insert into the cuckoo set" after that. */
+int ammsb_set_build(ammsb_ctx* ctx, const uint64_t* h_keys, uint64_t n, ammsb_set** out);
+int ammsb_set_build_device(ammsb_ctx* ctx, const uint64_t* d_keys, uint64_t n, ammsb_set** out);
+int ammsb_set_info(const ammsb_set* set, uint64_t* num_bins, uint32_t* prime_idx);
+int ammsb_set_read_table(ammsb_set* set, uint64_t* h_table /* [8 * num_bins] */); /* Set::Serialize() */
+
+/* ---- graph inputs built in HBM (the reference builds them on the host: data.cc:12-128).
+ *      ammsb_graph_generate: the synthetic graphs of the named shapes -- E distinct undirected
+ *      pairs u < v with uniform endpoints, in a pseudo-random order, a function of (N, E, seed).
+ *      ammsb_graph_nonlinks: `count` distinct pairs that are in neither set (the held-out
+ *      non-links of GenerateSetsFromEdges, data.cc:110-126; b may be NULL).
+ *      ammsb_graph_csr: mcmc::Graph (data.cc:12-25) -- d_offsets [N+1], d_adj [2E] (neighbors of v
+ *      ascending), d_degree [N] (may be NULL). ---- */
+int ammsb_graph_generate(ammsb_ctx* ctx, uint64_t N, uint64_t E, uint64_t seed, uint64_t* d_edges);
+int ammsb_graph_nonlinks(ammsb_ctx* ctx, uint64_t N, uint64_t count, uint64_t seed, ammsb_set* a,
+                         ammsb_set* b, uint64_t* d_out);
+int ammsb_graph_csr(ammsb_ctx* ctx, uint64_t N, const uint64_t* d_edges, uint64_t E, uint64_t* d_offsets,
+                    uint32_t* d_adj, uint32_t* d_degree);
+
+/* ---- the Node mini-batch strategy on the device (sampleNodeLink / sampleNodeNonLink,
+ *      sample.cc:253-293, + ExtractNodesFromMiniBatch, learner.cc:162-173) for graphs whose host
+ *      copy is impractical.  The caller draws the coin and the vertex u with rand_r as sampleNode
+ *      does.  ammsb_minibatch_nonlink examines the same rand_r candidate stream as the host
+ *      strategy (*seed = state after u was drawn), refuses, drops and stops like it, and leaves
+ *      *seed where the host leaves it: the mini-batch has the same edges and nodes; they are
+ *      emitted in draw order (nodes: u first), not in std::unordered_set order.  It waits for the
+ *      stream (the draw count decides the next seed).  d_edges [m], d_nodes [m + 1].
+ *      ammsb_minibatch_link emits every training edge of u (degree > 0): d_edges [degree],
+ *      d_nodes [degree + 1]; asynchronous. ---- */
+typedef struct ammsb_sampler ammsb_sampler;
+int ammsb_sampler_create(ammsb_ctx* ctx, uint64_t N, uint32_t mini_batch_size, ammsb_sampler** out);
+int ammsb_sampler_destroy(ammsb_sampler* sampler);
+int ammsb_minibatch_nonlink(ammsb_sampler* sampler, ammsb_ctx* ctx, uint32_t u, unsigned int* seed,
+                            ammsb_set* train, ammsb_set* heldout, uint64_t* d_edges, uint32_t* d_nodes,
+                            uint32_t* num_edges, uint32_t* num_nodes);
+int ammsb_minibatch_link(ammsb_ctx* ctx, uint32_t u, uint32_t degree, const uint64_t* d_offsets,
+                         const uint32_t* d_adj, uint64_t* d_edges, uint32_t* d_nodes);
+
 /* ---- pi/phi store: RowPartitionedMatrixFactory<Float>::CreateMatrix(rows, cols)
  *      (partitioned-alloc.h:152-157) + the phi[N] buffer (learner.cc:83).
  *      Node-partitioned over `num_shards` GPUs: shard s owns rows

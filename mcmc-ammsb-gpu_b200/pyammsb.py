@@ -290,6 +290,90 @@ class DevSet:
             self.h = None
 
 
+class BuiltSet(DevSet):
+    """cuckoo set built on the device from a key list (host array or device buffer)"""
+
+    def __init__(self, ctx, keys, n=None):
+        h = C.c_void_p()
+        if isinstance(keys, np.ndarray):
+            keys = np.ascontiguousarray(keys, dtype=np.uint64)
+            _ck(lib().ammsb_set_build(ctx.h, _p(keys), C.c_uint64(len(keys)), C.byref(h)))
+        else:
+            _ck(lib().ammsb_set_build_device(ctx.h, keys.ptr, C.c_uint64(n), C.byref(h)))
+        self.h, self.ctx = h, ctx
+        bins, prime = C.c_uint64(0), C.c_uint32(0)
+        _ck(lib().ammsb_set_info(h, C.byref(bins), C.byref(prime)))
+        self.num_bins, self.prime_idx = bins.value, prime.value
+
+    def table(self):
+        out = np.empty(8 * self.num_bins, dtype=np.uint64)
+        _ck(lib().ammsb_set_read_table(self.h, _p(out)))
+        return out
+
+
+def graph_generate(ctx, N, E, seed, d_edges):
+    _ck(lib().ammsb_graph_generate(ctx.h, C.c_uint64(N), C.c_uint64(E), C.c_uint64(seed), d_edges.ptr))
+
+
+def graph_nonlinks(ctx, N, count, seed, set_a, set_b, d_out):
+    _ck(lib().ammsb_graph_nonlinks(ctx.h, C.c_uint64(N), C.c_uint64(count), C.c_uint64(seed), set_a.h,
+                                   set_b.h if set_b is not None else None, d_out.ptr))
+
+
+def graph_csr(ctx, N, d_edges, E, d_offsets, d_adj, d_degree=None):
+    _ck(lib().ammsb_graph_csr(ctx.h, C.c_uint64(N), d_edges.ptr, C.c_uint64(E), d_offsets.ptr, d_adj.ptr,
+                              d_degree.ptr if d_degree is not None else None))
+
+
+_libc = None
+
+
+def rand_r(seed):
+    """glibc rand_r on a ctypes c_uint (advanced in place)"""
+    global _libc
+    if _libc is None:
+        _libc = C.CDLL(None)
+        _libc.rand_r.argtypes = [C.POINTER(C.c_uint)]
+        _libc.rand_r.restype = C.c_int
+    return _libc.rand_r(C.byref(seed))
+
+
+class DeviceSampler:
+    """sampleNode (sample.cc:295-302) with the mini-batch produced on the device: the host draws
+    the coin and the vertex with rand_r exactly as the strategy does, the device examines the
+    candidate stream.  Same edges and nodes as the host strategy for the same seed (in draw
+    order), same seed afterwards."""
+
+    def __init__(self, ctx, N, E, m, train, heldout, d_offsets, d_adj, degree):
+        h = C.c_void_p()
+        _ck(lib().ammsb_sampler_create(ctx.h, C.c_uint64(N), m, C.byref(h)))
+        self.h, self.ctx, self.N, self.E, self.m = h, ctx, N, E, m
+        self.train, self.heldout, self.d_offsets, self.d_adj, self.degree = train, heldout, d_offsets, d_adj, degree
+
+    def sample(self, seed, d_edges, d_nodes, ctx=None):
+        """one mini-batch into d_edges / d_nodes; returns (weight, E_mb, V)"""
+        ctx = ctx or self.ctx
+        if rand_r(seed) % 2:  # sampleNodeLink: unseen vertices until one has training neighbors
+            while True:
+                u = rand_r(seed) % self.N
+                d = int(self.degree[u])
+                if d > 0:
+                    break
+            _ck(lib().ammsb_minibatch_link(ctx.h, u, d, self.d_offsets.ptr, self.d_adj.ptr, d_edges.ptr, d_nodes.ptr))
+            return float(np.float32(self.N)), d, d + 1
+        u = rand_r(seed) % self.N
+        ne, nn = C.c_uint32(0), C.c_uint32(0)
+        _ck(lib().ammsb_minibatch_nonlink(self.h, ctx.h, u, C.byref(seed), self.train.h,
+                                          self.heldout.h if self.heldout is not None else None, d_edges.ptr,
+                                          d_nodes.ptr, C.byref(ne), C.byref(nn)))
+        return float(np.float32(2 * self.E) / np.float32(self.m)), ne.value, nn.value
+
+    def free(self):
+        if self.h is not None:
+            lib().ammsb_sampler_destroy(self.h)
+            self.h = None
+
+
 class Peer:
     """cross-GPU barrier / rank-ordered all-reduce over NVLink peer memory (csrc/peer.cu)"""
 
