@@ -54,6 +54,9 @@ def parse_args():
                     help="multi-GPU pi layout: node-partitioned (NVLink peer loads) or one copy per GPU")
     ap.add_argument("--collectives", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU exchange steps: own kernels over NVLink peer memory, or NCCL")
+    ap.add_argument("--graph", default="auto", choices=["auto", "host", "device"],
+                    help="multi-GPU runs: build the synthetic graph, the cuckoo sets and the mini-batches on the host "
+                         "(the reference's path) or in HBM (csrc/graph.cu; auto: device above 100 M edges)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -322,7 +325,7 @@ def run_b200(args, w):
         raise SystemExit("bench.py: no CUDA device and no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
-    if world > 1:
+    if world > 1 or args.graph == "device":  # the sharded driver (also on one GPU for device-built graphs)
         import dist as D
         return D.bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_name,
                                ClockSampler, cpu_reference)

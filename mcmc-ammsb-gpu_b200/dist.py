@@ -133,14 +133,21 @@ class ShardedLearner:
     STREAMS = 4  # independent host sampler streams (the reference has 2: its two Samples)
 
     def __init__(self, cfg, rank, world, local_rank, seed=12345, prefetch=True, store_mode="partitioned",
-                 collectives="peer"):
+                 collectives="peer", graph=None, shape=None):
+        """cfg: a pymcmc.Config (host graph, host sets, host mini-batch strategy), or None with
+        graph = a devgraph.DeviceGraph built on this rank's GPU and shape = (K, n, m): sets,
+        held-out pairs, adjacency and the mini-batch strategy then live on the device"""
         import torch
         import torch.distributed as dist
         import pyammsb as A
         import pymcmc
         self.torch, self.dist, self.A = torch, dist, A
-        self.cfg, self.rank, self.world = cfg, rank, world
-        self.p = cfg.params()
+        self.cfg, self.rank, self.world, self.graph = cfg, rank, world, graph
+        if graph is not None:
+            K_, n_, self.m = shape
+            self.p = A.make_params(graph.N, graph.E, K_, n_)
+        else:
+            self.p = cfg.params()
         self.N, self.K, self.n = int(self.p.N), int(self.p.K), int(self.p.num_neighbors)
         self.stream = torch.cuda.current_stream()
         self.ctx = A.Ctx(local_rank)
@@ -187,16 +194,22 @@ class ShardedLearner:
             os.close(fd)
         self.store.init_pi(float(self.p.eta0), float(self.p.eta1))
         # ---- replicated: edge sets, theta/beta, RNG pools ----
-        t_tab, t_bins, t_prime = cfg.set_table(0)
-        h_tab, h_bins, h_prime = cfg.set_table(1)
-        self.train = A.DevSet(self.ctx, t_tab, t_bins, t_prime)
-        self.heldout = A.DevSet(self.ctx, h_tab, h_bins, h_prime)
+        if graph is not None:
+            self.train, self.heldout = graph.train, graph.heldout
+        else:
+            t_tab, t_bins, t_prime = cfg.set_table(0)
+            h_tab, h_bins, h_prime = cfg.set_table(1)
+            self.train = A.DevSet(self.ctx, t_tab, t_bins, t_prime)
+            self.heldout = A.DevSet(self.ctx, h_tab, h_bins, h_prime)
         theta = pymcmc.init_theta_host(self.K, float(self.p.eta0), float(self.p.eta1))
         th2 = theta.reshape(self.K, 2)
         beta = (th2 / (th2[:, :1] + th2[:, 1:])).astype(np.float32).ravel()
         self.theta = torch.from_numpy(theta).to(dev)
         self.beta = torch.from_numpy(beta).to(dev)
-        self.Vmax, self.Emax = cfg.max_nodes(), cfg.max_edges()
+        if graph is not None:
+            self.Vmax, self.Emax = graph.max_nodes(self.m), graph.max_edges(self.m)
+        else:
+            self.Vmax, self.Emax = cfg.max_nodes(), cfg.max_edges()
         n = self.n
         self.npools = [A.Rng(self.ctx, self.Vmax * 2 * n, 56, 57) for _ in range(self.STREAMS)]
         self.ppool = A.Rng(self.ctx, self.Vmax * 32, 42, 43)
@@ -222,12 +235,18 @@ class ShardedLearner:
         self.h_beta = torch.empty(2 * self.K, dtype=torch.float32).pin_memory()
         self.opts = A.PhiOpts(A.MODE_WG, 32, 0, 0, rank, world)
         # ---- held-out pairs: this rank's chunk ----
-        he = cfg.edges()[1]
-        self.H = len(he)
-        lo, hi = chunk(self.H, rank, world)
+        if graph is not None:
+            self.H = graph.H
+            lo, hi = chunk(self.H, rank, world)
+            self.hedges = _Buf(graph.d_heldout_pairs.ptr.value + 8 * lo)
+        else:
+            he = cfg.edges()[1]
+            self.H = len(he)
+            lo, hi = chunk(self.H, rank, world)
+            self.d_hedges = torch.from_numpy(he[lo:hi].astype(np.int64)).to(dev) if hi > lo else \
+                torch.zeros(1, dtype=torch.int64, device=dev)
+            self.hedges = tbuf(self.d_hedges)
         self.H_local = hi - lo
-        self.d_hedges = torch.from_numpy(he[lo:hi].astype(np.int64)).to(dev) if hi > lo else \
-            torch.zeros(1, dtype=torch.int64, device=dev)
         self.d_ppx = torch.zeros(max(self.H_local, 1), dtype=torch.float32, device=dev)
         self.pws = torch.empty(self.ctx.perplexity_workspace_bytes(), dtype=torch.uint8, device=dev)
         self.sums = torch.zeros(4, dtype=torch.float64, device=dev)
@@ -245,6 +264,21 @@ class ShardedLearner:
         self.drawn = 0
         self.q = None
         self.t = 0
+        if graph is not None:
+            # device mini-batches: every rank draws the same mini-batch (same seed, same stream) on
+            # its own GPU, on a sampler stream of its own, one step ahead of its use
+            prefetch = False
+            self.smp_stream = torch.cuda.Stream()
+            self.ctx_smp = A.Ctx(local_rank)
+            self.ctx_smp.set_stream(self.smp_stream.cuda_stream)
+            self.dsampler = graph.sampler(self.m, ctx=self.ctx_smp)
+            self.dseed = C.c_uint(seed)
+            self.mb_edges = [torch.empty(self.Emax, dtype=torch.int64, device=dev) for _ in range(2)]
+            self.mb_nodes = [torch.empty(self.Vmax, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.mb_meta = [None, None]
+            self.ev_mb_free = [torch.cuda.Event() for _ in range(2)]
+            self.ev_mb_ready = [torch.cuda.Event() for _ in range(2)]
+            self.mb_drawn = 0
         if prefetch:
             self.local_seeds = [C.c_uint(seed + 7919 * (rank * self.LOCAL + i) + 104729) for i in range(self.LOCAL)]
             self.q = [queue.Queue(maxsize=2) for _ in range(self.LOCAL)]
@@ -377,14 +411,50 @@ class ShardedLearner:
         self.t = t + 1
         return E_mb
 
+    def draw_device_minibatch(self, d_edges=None, d_nodes=None):
+        """the next mini-batch of the device sampler stream into the given buffers (default: the
+        double-buffered slots of device_graph_step); returns (weight, E_mb, V)"""
+        t = self.mb_drawn
+        b = t & 1
+        if d_edges is None:
+            self.smp_stream.wait_event(self.ev_mb_free[b])  # the kernels of mini-batch t-2 are done with the slot
+            d_edges, d_nodes = tbuf(self.mb_edges[b]), tbuf(self.mb_nodes[b])
+        meta = self.dsampler.sample(self.dseed, d_edges, d_nodes, ctx=self.ctx_smp)
+        self.ev_mb_ready[b].record(self.smp_stream)
+        self.mb_drawn = t + 1
+        return meta
+
+    def device_graph_step(self):
+        """one iteration with the mini-batch drawn on the device: mini-batch t+1 is drawn (sampler
+        stream) while the kernels of t run"""
+        t = self.t
+        b = t & 1
+        if self.mb_drawn <= t:
+            self.mb_meta[b] = self.draw_device_minibatch()
+        weight, E_mb, V = self.mb_meta[b]
+        self.stream.wait_event(self.ev_mb_ready[b])
+        d_nodes, d_edges = tbuf(self.mb_nodes[b]), tbuf(self.mb_edges[b])
+        self.enqueue_neighbors(d_nodes, V, t % self.STREAMS, t + 1, after=self.ev_mb_ready[b])
+        self.device_step(d_nodes, d_edges, V, E_mb, weight, t % self.STREAMS, seq=t + 1)
+        self.ev_mb_free[b].record(self.stream)
+        self.mb_meta[1 - b] = self.draw_device_minibatch()  # blocks the host, not the compute stream
+        self.enqueue_neighbors(tbuf(self.mb_nodes[1 - b]), self.mb_meta[1 - b][2], (t + 1) % self.STREAMS, t + 2,
+                               after=self.ev_mb_ready[1 - b])
+        self.h_beta.copy_(self.beta, non_blocking=True)
+        self.t = t + 1
+        return E_mb
+
     def run(self, iters):
         for _ in range(iters):
-            self.host_step()
+            if self.graph is not None:
+                self.device_graph_step()
+            else:
+                self.host_step()
 
     def heldout_perplexity(self):
         self.ppx_calls += 1
         if self.H_local > 0:
-            self.ctx.perplexity_partial(self.p, self.store, tbuf(self.beta), self.heldout, tbuf(self.d_hedges),
+            self.ctx.perplexity_partial(self.p, self.store, tbuf(self.beta), self.heldout, self.hedges,
                                         self.H_local, tbuf(self.d_ppx), self.ppx_calls, tbuf(self.sums), tbuf(self.pws))
         else:
             self.sums.zero_()
@@ -418,49 +488,86 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     import pymcmc
     import synth
 
+    for k, v in (("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29541"), ("RANK", "0"), ("WORLD_SIZE", "1")):
+        os.environ.setdefault(k, v)  # a plain `python bench.py --graph device` run on one GPU
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N, E, K, n = w["N"], w["E"], w["K"], w["n"]
     m = w["m"] * world
     t0 = time.time()
-    # rank 0 generates the synthetic edge list once; the other ranks load it
-    path = os.path.join("/tmp", "ammsb_edges_%d_%d_%d.npy" % (N, E, int(os.environ.get("MASTER_PORT", "0"))))
-    if rank == 0:
-        np.save(path, synth.make_edges(N, E, 1))
-    dist.barrier()
-    keys = np.load(path)
-    dist.barrier()
-    if rank == 0:
-        os.unlink(path)
-    cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=w["heldout_ratio"], strategy="Node")
-    cfg.set_graph(N, keys)
-    log("graph + split + sets: %.1fs" % (time.time() - t0))
     mode = getattr(args, "store", "auto")
     if mode == "auto":  # replicate while a full copy (plus mini-batch buffers) is a small part of 180 GB
         mode = "replicated" if 4.0 * N * K <= 48e9 else "partitioned"
     coll = getattr(args, "collectives", "peer")
-    lrn = ShardedLearner(cfg, rank, world, local_rank, prefetch=False, store_mode=mode, collectives=coll)
+    gmode = getattr(args, "graph", "auto")
+    if gmode == "auto":
+        gmode = "device" if E > 100e6 else "host"
+    graph = cfg = None
+    if gmode == "device":
+        # every rank builds the same graph, sets, held-out pairs and adjacency in its own HBM
+        import devgraph
+        torch.cuda.set_device(local_rank)
+        gctx = A.Ctx(local_rank)
+        graph = devgraph.DeviceGraph(gctx, N, E, w["heldout_ratio"], seed=1, log=log)
+
+        def make_learner(prefetch):
+            return ShardedLearner(None, rank, world, local_rank, store_mode=mode, collectives=coll, graph=graph,
+                                  shape=(K, n, m))
+    else:
+        # rank 0 generates the synthetic edge list once; the other ranks load it
+        path = os.path.join("/tmp", "ammsb_edges_%d_%d_%d.npy" % (N, E, int(os.environ.get("MASTER_PORT", "0"))))
+        if rank == 0:
+            np.save(path, synth.make_edges(N, E, 1))
+        dist.barrier()
+        keys = np.load(path)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(path)
+        cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=w["heldout_ratio"],
+                            strategy="Node")
+        cfg.set_graph(N, keys)
+
+        def make_learner(prefetch):
+            return ShardedLearner(cfg, rank, world, local_rank, prefetch=prefetch, store_mode=mode, collectives=coll)
+    log("graph + split + sets (%s): %.1fs" % (gmode, time.time() - t0))
+    lrn = make_learner(False)
     stream = lrn.stream
     ctx = lrn.ctx
 
     # ---- value leg: pre-sampled mini-batches resident in HBM ----
     total = args.warmup + args.steps
     t0 = time.time()
-    batches = [lrn.next_minibatch() for _ in range(total)]
-    log("host sampler: %d mini-batches of up to %d edges in %.1fs" % (total, m, time.time() - t0))
-    e_off = np.cumsum([0] + [len(b[1]) for b in batches])
-    v_off = np.cumsum([0] + [len(b[2]) for b in batches])
-    d_edges_all = ctx.from_host(np.concatenate([b[1] for b in batches]))
-    d_nodes_all = ctx.from_host(np.concatenate([b[2] for b in batches]))
+    if graph is not None:
+        # (weight, E_mb, V) per mini-batch, drawn by the device sampler into one resident buffer
+        d_edges_all = ctx.buf(np.uint64, total * lrn.Emax)
+        d_nodes_all = ctx.buf(np.uint32, total * lrn.Vmax)
+        e_off = np.arange(total + 1, dtype=np.int64) * lrn.Emax
+        v_off = np.arange(total + 1, dtype=np.int64) * lrn.Vmax
+        batches = []
+        for i in range(total):
+            wgt, E_mb, V = lrn.draw_device_minibatch(_Buf(d_edges_all.ptr.value + 8 * int(e_off[i])),
+                                                     _Buf(d_nodes_all.ptr.value + 4 * int(v_off[i])))
+            batches.append((wgt, E_mb, V))
+        torch.cuda.synchronize()
+        log("device sampler: %d mini-batches of up to %d edges in %.2fs" % (total, m, time.time() - t0))
+    else:
+        drawn = [lrn.next_minibatch() for _ in range(total)]
+        log("host sampler: %d mini-batches of up to %d edges in %.1fs" % (total, m, time.time() - t0))
+        e_off = np.cumsum([0] + [len(b[1]) for b in drawn])
+        v_off = np.cumsum([0] + [len(b[2]) for b in drawn])
+        d_edges_all = ctx.from_host(np.concatenate([b[1] for b in drawn]))
+        d_nodes_all = ctx.from_host(np.concatenate([b[2] for b in drawn]))
+        batches = [(b[0], len(b[1]), len(b[2])) for b in drawn]
+        del drawn
 
     def nodes_of(i):
         return _Buf(d_nodes_all.ptr.value + 4 * int(v_off[i]))
 
     def step(i, ev=None):
-        wgt, edges, nodes = batches[i]
-        lrn.enqueue_neighbors(nodes_of(i), len(nodes), i % lrn.STREAMS, i + 1)
+        wgt, E_mb, V = batches[i]
+        lrn.enqueue_neighbors(nodes_of(i), V, i % lrn.STREAMS, i + 1)
         if i + 1 < total:  # the next mini-batch's neighbors are drawn while this one is processed
-            lrn.enqueue_neighbors(nodes_of(i + 1), len(batches[i + 1][2]), (i + 1) % lrn.STREAMS, i + 2)
-        lrn.device_step(nodes_of(i), _Buf(d_edges_all.ptr.value + 8 * int(e_off[i])), len(nodes), len(edges), wgt,
+            lrn.enqueue_neighbors(nodes_of(i + 1), batches[i + 1][2], (i + 1) % lrn.STREAMS, i + 2)
+        lrn.device_step(nodes_of(i), _Buf(d_edges_all.ptr.value + 8 * int(e_off[i])), V, E_mb, wgt,
                         i % lrn.STREAMS, ev, seq=i + 1)
 
     clocks = ClockSampler(local_rank)
@@ -487,9 +594,9 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     dev_ms, phi_ms = float(t[0]), float(t[1])
     clk = clocks.stop() if rank == 0 else None
     timed = batches[args.warmup:]
-    edges_timed = int(sum(len(b[1]) for b in timed))
+    edges_timed = int(sum(b[1] for b in timed))
     value = edges_timed / (dev_ms * 1e-3)
-    Vs = [len(b[2]) for b in timed]
+    Vs = [b[2] for b in timed]
     nvlink_peak = 770.0  # GB/s per direction per GPU, measured peer copy (B200_PROFILING.md)
     peaks = {}
     try:
@@ -530,15 +637,13 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     # ---- e2e leg: host mini-batches through the sharded driver ----
     e2e = None
     if not args.no_e2e:
-        l2 = ShardedLearner(cfg, rank, world, local_rank, prefetch=True, store_mode=mode, collectives=coll)
-        for _ in range(args.warmup):
-            l2.host_step()
+        l2 = make_learner(True)
+        l2.run(args.warmup)
         dist.barrier()
         torch.cuda.synchronize()
         b0, e0 = l2.h2d_bytes, l2.edges_processed
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            l2.host_step()
+        l2.run(args.steps)
         torch.cuda.synchronize()
         dist.barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
@@ -549,15 +654,20 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
         e2e = {"value": (l2.edges_processed - e0) / dt, "unit": UNIT,
                "h2d_bytes_per_step": float(hb[0]) / args.steps, "d2h_bytes_per_step": (8 * K + 32) * world,
                "iterations_per_s": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
-               "api": "dist.ShardedLearner.host_step(): mini-batch t drawn on rank t % N (2 sampler threads per "
-                      "rank), H2D from pinned memory there, NCCL broadcast one step ahead, sharded kernels + "
-                      "all-reduces, D2H of beta"}
+               "api": ("dist.ShardedLearner.host_step(): mini-batch t drawn on rank t % N (2 sampler threads per "
+                       "rank), H2D from pinned memory there, NCCL broadcast one step ahead, sharded kernels + "
+                       "all-reduces, D2H of beta") if graph is None else
+                      ("dist.ShardedLearner.device_graph_step(): coin and vertex drawn on the host (rand_r), the "
+                       "mini-batch on every GPU by the device sampler one step ahead (D2H of its 16-byte header), "
+                       "sharded kernels + all-reduces, D2H of beta; the graph, the cuckoo sets and the adjacency "
+                       "were built in HBM, nothing but kernel arguments goes host to device")}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w, world),
+                       "graph": "built in HBM (csrc/graph.cu)" if graph is not None else "built on the host",
                        "parallelism": ("pi/phi node-partitioned over %d GPUs (NVLink peer loads), " % world
                                        if mode == "partitioned" else
                                        "pi/phi replicated on %d GPUs (fits: %.1f GB), mini-batch slots split over "

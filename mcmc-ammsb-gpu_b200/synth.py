@@ -15,6 +15,9 @@ SHAPES = {
     # host can build in a minute: exercises the partitioned store and its NVLink gathers at the
     # Friendster scale without the 1.8 G-edge host-side graph build
     "com-Friendster-store": (65608366, 20000000, 512, 0.01),
+    # one GPU's eighth of the Friendster shape (the per-GPU footprint of the 8-GPU run: 16.8 GB of
+    # pi, a 2 GB cuckoo table) -- with the graph built in HBM (bench.py --graph device)
+    "com-Friendster-eighth": (8201046, 225758392, 512, 0.01),
 }
 
 
