@@ -22,6 +22,7 @@
 #include <cub/cub.cuh>
 
 #include <cmath>
+#include <string>
 
 #include "common.cuh"
 
@@ -223,8 +224,8 @@ static int generate_unique(ammsb_ctx* c, uint64_t N, uint64_t want, uint64_t see
     void* d_tmp = nullptr;
     size_t tmp_sort = 0, tmp_uniq = 0;
     cub::DoubleBuffer<uint64_t> buf(nullptr, nullptr);
-    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, buf, (int64_t)count, 0, 64, c->stream);
-    cub::DeviceSelect::Unique(nullptr, tmp_uniq, d_a, d_b, d_num, (int64_t)count, c->stream);
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, buf, (int)count, 0, 64, c->stream);
+    cub::DeviceSelect::Unique(nullptr, tmp_uniq, d_a, d_b, d_num, (int)count, c->stream);
     const size_t tmp_bytes = tmp_sort > tmp_uniq ? tmp_sort : tmp_uniq;
     cudaError_t e1 = cudaMalloc((void**)&d_a, 8 * count), e2 = cudaMalloc((void**)&d_b, 8 * count),
                 e3 = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 8), e4 = cudaMalloc((void**)&d_num, 8);
@@ -239,43 +240,53 @@ static int generate_unique(ammsb_ctx* c, uint64_t N, uint64_t want, uint64_t see
       cudaGetLastError();
       AMMSB_REQUIRE(false, "out of device memory while generating edges");
     }
+    // every step is checked on its own: at the Friendster size a failure must say where
+#define GEN_STEP(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      release();                                                                              \
+      ammsb_set_error(std::string("generate_unique: ") + #expr + ": " + cudaGetErrorString(_e) + \
+                      " (count " + std::to_string(count) + ")");                              \
+      cudaGetLastError();                                                                     \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
     if (a != nullptr)
       k_gen_nonlink_candidates<<<grid_for(c, count), 256, 0, c->stream>>>(N, seed, salt, count, a->view(),
                                                                           b ? b->view() : a->view(), b != nullptr, d_a);
     else
       k_gen_candidates<<<grid_for(c, count), 256, 0, c->stream>>>(N, seed, salt, count, d_a);
     g_launch_count.fetch_add(1);
+    GEN_STEP(cudaGetLastError());
     buf = cub::DoubleBuffer<uint64_t>(d_a, d_b);
     size_t tb = tmp_bytes;
-    cub::DeviceRadixSort::SortKeys(d_tmp, tb, buf, (int64_t)count, 0, 64, c->stream);
+    // count < 2^31 (checked above): the 32-bit item count is the well-trodden path of both primitives
+    GEN_STEP(cub::DeviceRadixSort::SortKeys(d_tmp, tb, buf, (int)count, 0, 64, c->stream));
     uint64_t* sorted = buf.Current();
     uint64_t* other = buf.Alternate();
     tb = tmp_bytes;
-    cub::DeviceSelect::Unique(d_tmp, tb, sorted, other, d_num, (int64_t)count, c->stream);
+    GEN_STEP(cub::DeviceSelect::Unique(d_tmp, tb, sorted, other, d_num, (int)count, c->stream));
     uint64_t num = 0;
-    cudaError_t e = cudaMemcpyAsync(&num, d_num, 8, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) {
-      release();
-      AMMSB_CHECK_CUDA(e);
-    }
+    GEN_STEP(cudaMemcpyAsync(&num, d_num, 8, cudaMemcpyDeviceToHost, c->stream));
+    GEN_STEP(cudaStreamSynchronize(c->stream));
     // refused candidates were all mapped to ~0: at most one survivor, and it is the last
-    uint64_t last = 0;
     if (a != nullptr && num > 0) {
-      e = cudaMemcpy(&last, other + num - 1, 8, cudaMemcpyDeviceToHost);
-      if (e == cudaSuccess && last == ~0ull) --num;
+      uint64_t last = 0;
+      GEN_STEP(cudaMemcpy(&last, other + num - 1, 8, cudaMemcpyDeviceToHost));
+      if (last == ~0ull) --num;
     }
-    if (e == cudaSuccess && num >= want) {
+    if (num >= want) {
       k_unscramble<<<grid_for(c, want), 256, 0, c->stream>>>(other, want, salt);
       g_launch_count.fetch_add(1);
-      e = cudaMemcpyAsync(d_out, other, 8 * want, cudaMemcpyDeviceToDevice, c->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      GEN_STEP(cudaGetLastError());
+      GEN_STEP(cudaMemcpyAsync(d_out, other, 8 * want, cudaMemcpyDeviceToDevice, c->stream));
+      GEN_STEP(cudaStreamSynchronize(c->stream));
       release();
-      AMMSB_CHECK_CUDA(e);
       return 0;
     }
     release();
-    AMMSB_CHECK_CUDA(e);
+#undef GEN_STEP
   }
   AMMSB_REQUIRE(false, "could not draw enough distinct pairs (graph too dense?)");
 }
@@ -346,8 +357,8 @@ extern "C" int ammsb_graph_csr(ammsb_ctx* c, uint64_t N, const uint64_t* d_edges
   unsigned long long* d_deg = nullptr;
   void* d_tmp = nullptr;
   size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)(N + 1),
-                                c->stream);
+  AMMSB_REQUIRE(N < 0x7fffffffull, "N out of range");
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)(N + 1), c->stream);
   AMMSB_CHECK_CUDA(cudaMalloc((void**)&d_deg, 8 * (N + 1)));
   if (cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 8) != cudaSuccess) {
     cudaFree(d_deg);
@@ -355,7 +366,7 @@ extern "C" int ammsb_graph_csr(ammsb_ctx* c, uint64_t N, const uint64_t* d_edges
   }
   cudaMemsetAsync(d_deg, 0, 8 * (N + 1), c->stream);
   if (E > 0) k_degree<<<grid_for(c, E), 256, 0, c->stream>>>(d_edges, E, d_deg);
-  cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, (uint64_t*)d_deg, d_offsets, (int64_t)(N + 1), c->stream);
+  cudaError_t es = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, (uint64_t*)d_deg, d_offsets, (int)(N + 1), c->stream);
   cudaMemsetAsync(d_deg, 0, 8 * (N + 1), c->stream);
   if (E > 0) k_fill_adj<<<grid_for(c, E), 256, 0, c->stream>>>(d_edges, E, d_offsets, d_deg, d_adj);
   k_sort_adj<<<grid_for(c, N), 256, 0, c->stream>>>(d_offsets, N, d_adj, d_degree);
@@ -363,6 +374,7 @@ extern "C" int ammsb_graph_csr(ammsb_ctx* c, uint64_t N, const uint64_t* d_edges
   cudaError_t e = cudaStreamSynchronize(c->stream);
   cudaFree(d_deg);
   cudaFree(d_tmp);
+  AMMSB_CHECK_CUDA(es);
   AMMSB_CHECK_CUDA(e);
   AMMSB_CHECK_CUDA(cudaGetLastError());
   return 0;

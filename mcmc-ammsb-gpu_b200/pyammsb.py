@@ -47,6 +47,12 @@ def lib():
         L.ammsb_round_param.argtypes = [C.c_float]
         L.ammsb_eps_t.restype = C.c_float
         L.ammsb_eps_t.argtypes = [C.c_void_p, C.c_uint32]
+        # byte counts are size_t: without a prototype ctypes passes a Python int as a 32-bit int
+        L.ammsb_malloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.ammsb_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.ammsb_memset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
+        for f in (L.ammsb_h2d, L.ammsb_d2h, L.ammsb_d2d, L.ammsb_h2d_async, L.ammsb_d2h_async):
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
 
