@@ -189,6 +189,28 @@ uint64_t mcmc_test_set_order(const uint64_t* keys, uint64_t n, int width, uint64
   return a.size() == b.size() ? a.size() : ~0ull;
 }
 
+// test hooks: exact remainder without a divide, and the per-endpoint view of a cuckoo set that
+// the non-link strategy filters with (which: 0 training, 1 held-out)
+void mcmc_test_fastmod(const uint64_t* a, const uint64_t* d, uint64_t n, uint64_t* out) {
+  for (uint64_t i = 0; i < n; ++i) out[i] = FastMod64(d[i]).Mod(a[i]);
+}
+uint64_t mcmc_config_set_has(void* vc, int which, const uint64_t* keys, uint64_t n, uint8_t* out) {
+  Config* c = static_cast<Config*>(vc);
+  const Set* s = which == 0 ? c->training.get() : c->heldout.get();
+  for (uint64_t i = 0; i < n; ++i) out[i] = s->Has(keys[i]) ? 1 : 0;
+  return n;
+}
+int64_t mcmc_config_partners(void* vc, int which, uint32_t u, uint32_t* out, uint64_t cap) {
+  Config* c = static_cast<Config*>(vc);
+  const Set* s = which == 0 ? c->training.get() : c->heldout.get();
+  const Set::Partners* idx = s->PartnerIndex();
+  if (idx == nullptr) return -1;
+  uint64_t n = 0;
+  for (const Vertex* v = idx->begin(u); v != idx->end(u); ++v, ++n)
+    if (n < cap) out[n] = *v;
+  return static_cast<int64_t>(n);
+}
+
 // theta init stream of Learner::Learner (host mt19937 + gamma_distribution)
 void mcmc_init_theta_host(uint32_t K, float eta0, float eta1, float* theta_out) {
   std::mt19937 engine(6342455113);

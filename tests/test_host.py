@@ -165,3 +165,49 @@ def test_minibatch_strategies_match_reference_code_at_size(N, E, m):
     finally:
         L.ref_sampler_destroy(h)
         cfg.close()
+
+
+def test_fastmod_is_the_exact_remainder():
+    """cuckoo bins and std::unordered_set buckets are remainders by a slowly-changing divisor; the
+    host hot loops compute them without a divide (fastmod.h) -- the value must be a % d for every
+    64-bit a and d"""
+    rng = np.random.default_rng(5)
+    d = np.concatenate([np.array([1, 2, 3, 13, 29, 143374, 20753, 258324041, 2**32 - 1, 2**32, 2**32 + 1, 2**63,
+                                  2**63 + 1, 2**64 - 2, 2**64 - 1], dtype=np.uint64),
+                        rng.integers(1, 2**63, size=2000, dtype=np.uint64) >> rng.integers(0, 62, size=2000).astype(np.uint64)])
+    d = np.maximum(d, np.uint64(1))
+    a = rng.integers(0, 2**64, size=len(d) * 64, dtype=np.uint64, endpoint=False)
+    a[::7] >>= np.uint64(33)
+    dd = np.repeat(d, 64)
+    a[1::64] = dd[1::64] - np.uint64(1)
+    a[2::64] = dd[2::64]
+    a[3::64] = np.uint64(2**64 - 1)
+    a[4::64] = np.uint64(0)
+    out = np.zeros(len(a), dtype=np.uint64)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    pymcmc.lib().mcmc_test_fastmod(vp(a), vp(dd), C.c_uint64(len(a)), vp(out))
+    assert np.array_equal(out, a % dd)
+
+
+def test_partner_index_is_the_cuckoo_set_seen_from_one_endpoint(cfg):
+    """the non-link strategy refuses candidates by the partner list of the shared endpoint instead of
+    asking the cuckoo sets: the list must be exactly {v : Has(canonical(u, v))}, for both sets"""
+    L = pymcmc.lib()
+    L.mcmc_config_partners.restype = C.c_int64
+    N = int(cfg.params().N)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    for which in (0, 1):
+        for u in list(range(0, N, max(1, N // 25))) + [N - 1]:
+            buf = np.zeros(4096, dtype=np.uint32)
+            n = L.mcmc_config_partners(cfg.h, which, C.c_uint32(u), vp(buf), C.c_uint64(len(buf)))
+            assert 0 <= n <= len(buf)
+            v = np.arange(N, dtype=np.uint64)
+            keys = (np.minimum(v, np.uint64(u)) << np.uint64(32)) | np.maximum(v, np.uint64(u))
+            has = np.zeros(N, dtype=np.uint8)
+            L.mcmc_config_set_has(cfg.h, which, vp(keys), C.c_uint64(N), vp(has))
+            assert np.array_equal(np.sort(buf[:n]), np.nonzero(has)[0].astype(np.uint32))
+    tr, he = cfg.edges()
+    # and the sets hold what data.cc puts in them: all training edges; the held-out LINKS only
+    has = np.zeros(len(he), dtype=np.uint8)
+    L.mcmc_config_set_has(cfg.h, 1, vp(he), C.c_uint64(len(he)), vp(has))
+    assert has[:len(he) // 2].all() and not has[len(he) // 2:].any()
