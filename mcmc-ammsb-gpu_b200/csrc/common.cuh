@@ -186,11 +186,34 @@ __device__ const uint32_t d_zig_ytab[128] = AMMSB_ZIG_YTAB_BITS_INIT;
 __device__ const uint32_t d_zig_ktab[128] = AMMSB_ZIG_KTAB_INIT;
 __device__ const uint32_t d_zig_wtab[128] = AMMSB_ZIG_WTAB_BITS_INIT;
 
+// Where the three 128-entry ziggurat tables are read from.  ZigGlobal: the __device__ arrays through
+// the read-only path.  ZigShared: a per-CTA copy (ytab | ktab | wtab) -- update_phi keeps shared
+// memory so full that almost no L1 is left, the tables then live in L2 and every draw pays two
+// L2 round trips; kernels that draw noise in their inner loop stage the tables once per CTA.
+#define ZIG_WORDS 384
+struct ZigGlobal {
+  __device__ __forceinline__ uint32_t y(uint32_t i) const { return __ldg(&d_zig_ytab[i]); }
+  __device__ __forceinline__ uint32_t k(uint32_t i) const { return __ldg(&d_zig_ktab[i]); }
+  __device__ __forceinline__ uint32_t w(uint32_t i) const { return __ldg(&d_zig_wtab[i]); }
+};
+struct ZigShared {
+  const uint32_t* t;
+  __device__ __forceinline__ uint32_t y(uint32_t i) const { return t[i]; }
+  __device__ __forceinline__ uint32_t k(uint32_t i) const { return t[128 + i]; }
+  __device__ __forceinline__ uint32_t w(uint32_t i) const { return t[256 + i]; }
+};
+// every thread of the CTA takes part; the caller synchronises the CTA before the first draw
+__device__ __forceinline__ void zig_stage(uint32_t* s_zig) {
+  for (uint32_t i = threadIdx.x; i < ZIG_WORDS; i += blockDim.x)
+    s_zig[i] = i < 128 ? d_zig_ytab[i] : (i < 256 ? d_zig_ktab[i - 128] : d_zig_wtab[i - 256]);
+}
+
 // gsl_ran_gaussian_ziggurat, random.cl.inc:221-274 (sigma = 1).  The wedge/tail
 // tests use the precise expf/logf (never the fast-math intrinsics) so that the
 // accept/reject decisions -- and with them the stream position -- agree with the
 // reference evaluated on an IEEE host.
-__device__ __forceinline__ float rng_randn(Rng& s) {
+template <class Tab>
+__device__ __forceinline__ float rng_randn_t(Rng& s, const Tab& tab) {
   const float R = 3.44428647676f;
   float x;
   uint32_t sign;
@@ -200,12 +223,12 @@ __device__ __forceinline__ float rng_randn(Rng& s) {
     const uint32_t j = (uint32_t)(k >> 8) & 0xFFFFFFu;
     sign = i & 0x80u;
     i &= 0x7fu;
-    x = __fmul_rn((float)j, __uint_as_float(__ldg(&d_zig_wtab[i])));
-    if (j < __ldg(&d_zig_ktab[i])) break;
+    x = __fmul_rn((float)j, __uint_as_float(tab.w(i)));
+    if (j < tab.k(i)) break;
     float y;
     if (i < 127) {
-      const float y0 = __uint_as_float(__ldg(&d_zig_ytab[i]));
-      const float y1 = __uint_as_float(__ldg(&d_zig_ytab[i + 1]));
+      const float y0 = __uint_as_float(tab.y(i));
+      const float y1 = __uint_as_float(tab.y(i + 1));
       const float U1 = rng_uniform(s);
       y = __fadd_rn(y1, __fmul_rn(__fsub_rn(y0, y1), U1));
     } else {
@@ -218,6 +241,7 @@ __device__ __forceinline__ float rng_randn(Rng& s) {
   }
   return sign ? x : -x;
 }
+__device__ __forceinline__ float rng_randn(Rng& s) { return rng_randn_t(s, ZigGlobal()); }
 
 __device__ __forceinline__ float rng_uniform_pos(Rng& s) {  // random.cl.inc:311-318
   float x;

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) k_update_phi_strict(const __grid_constant
 // The compute warps then never stall on the RNG and keep their TMA ring busy.
 template <int WARPS, int NW>
 __device__ __forceinline__ void noise_producer(const PhiArgs& a, uint32_t p, float* s_nz, uint64_t* full,
-                                               uint64_t* empty, uint32_t lane) {
+                                               uint64_t* empty, uint32_t lane, const ZigShared zig) {
   constexpr int PER = WARPS / NW;  // compute warps served by this producer
   const uint32_t K = a.K;
   const bool fast_noise = (a.mode == AMMSB_MODE_WG && a.wg == 32);
@@ -184,11 +184,11 @@ __device__ __forceinline__ void noise_producer(const PhiArgs& a, uint32_t p, flo
           st[c] = rng_load(a.pool, (uint64_t)unit[c] * 32 + lane);
           open[c] = true;
         }
-        for (uint32_t k = lane; k < K; k += 32) out[k] = rng_randn(st[c]);
+        for (uint32_t k = lane; k < K; k += 32) out[k] = rng_randn_t(st[c], zig);
       } else {
         for (uint32_t vl = lane; vl < vw; vl += 32) {
           Rng vs = rng_load(a.pool, (uint64_t)unit[c] * vw + vl);
-          for (uint32_t k = vl; k < K; k += vw) out[k] = rng_randn(vs);
+          for (uint32_t k = vl; k < K; k += vw) out[k] = rng_randn_t(vs, zig);
           rng_store(a.pool, (uint64_t)unit[c] * vw + vl, vs);
         }
       }
@@ -224,20 +224,22 @@ __global__ void __launch_bounds__((WARPS + NW) * 32)
   uint64_t* bar_base = reinterpret_cast<uint64_t*>(s_raw + ((size_t)WARPS * (STAGES + 1) + (NW ? WARPS : 0)) * row_bytes);
   uint64_t* nz_full = bar_base + WARPS * (STAGES + 1);
   uint64_t* nz_empty = nz_full + WARPS;
+  // ziggurat tables, after the last barrier word
+  uint32_t* s_zig = reinterpret_cast<uint32_t*>(bar_base + WARPS * (STAGES + 1) + (NW ? 2 * WARPS : 0));
+  const ZigShared zig{s_zig};
   const bool ws_noise = NW > 0 && !a.disable_noise;
-  if (NW > 0) {
-    if (threadIdx.x == 0) {
-      for (int w = 0; w < WARPS; ++w) {
-        mbar_init(&nz_full[w], 1);
-        mbar_init(&nz_empty[w], 1);
-      }
-      mbar_fence_init();
+  zig_stage(s_zig);
+  if (NW > 0 && threadIdx.x == 0) {
+    for (int w = 0; w < WARPS; ++w) {
+      mbar_init(&nz_full[w], 1);
+      mbar_init(&nz_empty[w], 1);
     }
-    __syncthreads();
-    if (wib >= WARPS) {  // producer warps: noise only, no row traffic
-      if (ws_noise) noise_producer<WARPS, (NW > 0 ? NW : 1)>(a, wib - WARPS, s_nz, nz_full, nz_empty, lane);
-      return;
-    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (NW > 0 && wib >= WARPS) {  // producer warps: noise only, no row traffic
+    if (ws_noise) noise_producer<WARPS, (NW > 0 ? NW : 1)>(a, wib - WARPS, s_nz, nz_full, nz_empty, lane, zig);
+    return;
   }
   float* s_own = reinterpret_cast<float*>(s_raw) + (size_t)wib * (STAGES + 1) * K;
   float* s_stage = s_own + K;
@@ -406,11 +408,11 @@ __global__ void __launch_bounds__((WARPS + NW) * 32)
         if (ws_noise) mbar_wait(&nz_full[wib], nz_item & 1);  // the producer's row for this slot
       } else if (!a.disable_noise) {
         if (fast_noise) {
-          for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn(st);
+          for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn_t(st, zig);
         } else {
           for (uint32_t vl = lane; vl < vw; vl += 32) {
             Rng vs = rng_load(a.pool, (uint64_t)unit * vw + vl);
-            for (uint32_t k = vl; k < K; k += vw) s_noise[k] = rng_randn(vs);
+            for (uint32_t k = vl; k < K; k += vw) s_noise[k] = rng_randn_t(vs, zig);
             rng_store(a.pool, (uint64_t)unit * vw + vl, vs);
           }
           __syncwarp();
@@ -476,7 +478,10 @@ __global__ void __launch_bounds__(192) k_update_phi_team(const __grid_constant__
   uint64_t* nz_full_all = bar_base + WARPS * (STAGES + 1);
   uint64_t* nz_empty_all = nz_full_all + TEAMS * 2;
   float* s_part_all = reinterpret_cast<float*>(nz_empty_all + TEAMS * 2);
+  uint32_t* s_zig = reinterpret_cast<uint32_t*>(s_part_all + TEAMS * 3 * T);  // ziggurat tables
+  const ZigShared zig{s_zig};
   const bool ws_noise = !a.disable_noise;
+  zig_stage(s_zig);
   if (threadIdx.x == 0) {
     for (int i = 0; i < TEAMS * 2; ++i) {
       mbar_init(&nz_full_all[i], 1);
@@ -504,12 +509,12 @@ __global__ void __launch_bounds__(192) k_update_phi_team(const __grid_constant__
       mbar_wait(&nz_empty_all[team * 2 + b], ((i >> 1) & 1) ^ 1);
       if (fast_noise) {
         Rng st = rng_load(a.pool, (uint64_t)unit * 32 + lane);
-        for (uint32_t k = lane; k < K; k += 32) out[k] = rng_randn(st);
+        for (uint32_t k = lane; k < K; k += 32) out[k] = rng_randn_t(st, zig);
         rng_store(a.pool, (uint64_t)unit * 32 + lane, st);
       } else {
         for (uint32_t vl = lane; vl < vw; vl += 32) {
           Rng vs = rng_load(a.pool, (uint64_t)unit * vw + vl);
-          for (uint32_t k = vl; k < K; k += vw) out[k] = rng_randn(vs);
+          for (uint32_t k = vl; k < K; k += vw) out[k] = rng_randn_t(vs, zig);
           rng_store(a.pool, (uint64_t)unit * vw + vl, vs);
         }
       }
@@ -708,9 +713,12 @@ __global__ void __launch_bounds__((WPS + 1) * 32) k_update_phi_split(const __gri
   float* s_stage_all = s_noise + K;
   uint64_t* bar_own = reinterpret_cast<uint64_t*>(s_stage_all + (size_t)WPS * R * K);
   uint64_t* bars_all = bar_own + 1;
+  uint32_t* s_zig = reinterpret_cast<uint32_t*>(bars_all + WPS * R);  // ziggurat tables
+  const ZigShared zig{s_zig};
   const uint32_t slot = a.part_index + a.part_count * blockIdx.x;  // slot == unit
   if (slot >= a.V || slot >= a.units) return;                      // CTA-uniform
   const uint32_t node = __ldg(&a.nodes[slot]);
+  zig_stage(s_zig);
   if (threadIdx.x == 0) {
     mbar_init(bar_own, 1);
     for (int i = 0; i < WPS * R; ++i) mbar_init(&bars_all[i], 1);
@@ -726,13 +734,13 @@ __global__ void __launch_bounds__((WPS + 1) * 32) k_update_phi_split(const __gri
     if (!a.disable_noise) {
       if (a.mode == AMMSB_MODE_WG && a.wg == 32) {
         Rng st = rng_load(a.pool, (uint64_t)slot * 32 + lane);
-        for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn(st);
+        for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn_t(st, zig);
         rng_store(a.pool, (uint64_t)slot * 32 + lane, st);
       } else {
         const uint32_t vw = a.mode == AMMSB_MODE_THREAD ? 1u : a.wg;
         for (uint32_t vl = lane; vl < vw; vl += 32) {
           Rng vs = rng_load(a.pool, (uint64_t)slot * vw + vl);
-          for (uint32_t k = vl; k < K; k += vw) s_noise[k] = rng_randn(vs);
+          for (uint32_t k = vl; k < K; k += vw) s_noise[k] = rng_randn_t(vs, zig);
           rng_store(a.pool, (uint64_t)slot * vw + vl, vs);
         }
       }
@@ -869,7 +877,7 @@ static uint32_t my_units(const PhiArgs& a) {
 template <int KPL, int STAGES, int WARPS, int NB = 1, int NW = 0>
 static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   const size_t smem = ((size_t)WARPS * (STAGES + 1) + (NW ? WARPS : 0)) * a.K * 4 +
-                      (size_t)WARPS * (STAGES + 1) * 8 + (NW ? 2 * WARPS * 8 : 0);
+                      (size_t)WARPS * (STAGES + 1) * 8 + (NW ? 2 * WARPS * 8 : 0) + ZIG_WORDS * 4;
   const bool exact = (a.K == 32u * KPL);
   auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB, NW>
                     : k_update_phi_fast<KPL, STAGES, WARPS, false, NB, NW>;
@@ -889,7 +897,7 @@ static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
 template <int KPL>
 static int launch_split(ammsb_ctx* c, const PhiArgs& a) {
   constexpr int WPS = 8, R = 4;
-  const size_t smem = (size_t)(2 + WPS * R) * a.K * 4 + (size_t)(1 + WPS * R) * 8;
+  const size_t smem = (size_t)(2 + WPS * R) * a.K * 4 + (size_t)(1 + WPS * R) * 8 + ZIG_WORDS * 4;
   const bool exact = (a.K == 32u * KPL);
   auto kern = exact ? k_update_phi_split<KPL, WPS, R, true> : k_update_phi_split<KPL, WPS, R, false>;
   int occ = 0;
@@ -907,7 +915,8 @@ static int launch_team(ammsb_ctx* c, const PhiArgs& a) {
   const uint32_t KS = a.K / T;
   const uint32_t teams_per_cta = 4 / T;
   const size_t smem = (size_t)4 * (STAGES + 1) * KS * 4 + (size_t)teams_per_cta * 2 * a.K * 4 +
-                      (size_t)4 * (STAGES + 1) * 8 + (size_t)teams_per_cta * 4 * 8 + (size_t)teams_per_cta * 3 * T * 4;
+                      (size_t)4 * (STAGES + 1) * 8 + (size_t)teams_per_cta * 4 * 8 + (size_t)teams_per_cta * 3 * T * 4 +
+                      ZIG_WORDS * 4;
   const bool exact = (KS == 32u * KPL);
   auto kern = exact ? k_update_phi_team<KPL, STAGES, T, true> : k_update_phi_team<KPL, STAGES, T, false>;
   int occ = 0;

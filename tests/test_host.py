@@ -211,3 +211,27 @@ def test_partner_index_is_the_cuckoo_set_seen_from_one_endpoint(cfg):
     has = np.zeros(len(he), dtype=np.uint8)
     L.mcmc_config_set_has(cfg.h, 1, vp(he), C.c_uint64(len(he)), vp(has))
     assert has[:len(he) // 2].all() and not has[len(he) // 2:].any()
+
+
+def test_flat_set_order_property():
+    """property test (hypothesis): any insert sequence -- repeats, clustered keys, the all-ones key,
+    lengths on both sides of every std::unordered_set growth step -- iterates like
+    std::unordered_set"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(0, 2**32 - 1), st.integers(0, 700), st.sampled_from([8, 4]),
+           st.sampled_from([1, 13, 97, 1 << 12, 1 << 31, 1 << 40]), st.booleans())
+    def check(seed, n, width, span, with_sentinel):
+        rng = np.random.default_rng(seed)
+        hi = span if width == 8 else min(span, 1 << 32)
+        keys = rng.integers(0, hi, size=n, dtype=np.uint64)
+        if n > 4 and rng.integers(0, 2):
+            keys[rng.integers(0, n, size=n // 3)] = keys[0]
+        if with_sentinel and n > 2:
+            keys[rng.integers(0, n)] = np.uint64(2**64 - 1 if width == 8 else 2**32 - 1)
+        a, b = pymcmc.set_order(keys, width)
+        assert len(a) == len(np.unique(keys))
+        assert np.array_equal(a, b)
+
+    check()
