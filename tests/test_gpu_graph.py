@@ -151,6 +151,14 @@ def test_device_sampler_draws_the_host_strategys_minibatches(ctx, N, E, m, built
         assert len(np.unique(n_d)) == nn
         assert np.float32(w_d) == np.float32(w_h)
         assert seed_d.value == seed_h.value
+        if ne == m:
+            # a non-link mini-batch is emitted in draw order, which is the order in which the host
+            # strategy inserts into its std::unordered_set: putting the device's edges through that
+            # container's ordering gives the host's mini-batch exactly, order included
+            assert np.array_equal(pymcmc.set_order(e_d, 8)[1], e_h)
+            ends, cnt = np.unique(np.concatenate([e_d >> np.uint64(32), e_d & np.uint64(0xFFFFFFFF)]),
+                                  return_counts=True)
+            assert n_d[0] == ends[cnt.argmax()]  # the shared endpoint u comes first
         kinds.add(ne == m)
     assert kinds == {True, False}  # both link and non-link mini-batches were drawn
     for x in (d_tr, d_off, d_adj, d_deg, d_edges, d_nodes):
