@@ -485,6 +485,9 @@ def run_b200(args, w):
     except Exception:
         pass
     achieved = phi_bytes / (phi_ms * 1e-3) / 1e9
+    # `achieved` averages every update_phi launch of the timed region: the non-link mini-batches
+    # (k_update_phi_fast, V = m + 1 slots, bandwidth-bound) and the link ones (k_update_phi_split,
+    # V = 1 + deg(u) slots, a latency chain); canonical_launch is the non-link launch alone
     roofline = {"bound": "hbm", "kernel": "k_update_phi_fast", "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "launches": args.steps, "algorithmic_bytes_per_launch": round(phi_bytes / args.steps), "share_of_step": round(phi_ms / dev_ms, 4),
