@@ -211,17 +211,24 @@ __device__ __forceinline__ void noise_producer(const PhiArgs& a, uint32_t p, flo
 // wait, shuffle tree, reciprocal, refill) dominates the issue slots; NB = 2 interleaves two
 // neighbors (two shuffle trees in flight, own row kept in registers) without changing any
 // result: every sum is formed in the same order as with NB = 1.
-template <int KPL, int STAGES, int WARPS, bool EXACT, int NB, int NW>
+// EARLY (NW == 0 only): the gather warp draws a slot's noise itself, but at the START of the
+// slot -- right after it has requested the own row and the first STAGES neighbor rows, while it
+// would otherwise just wait for them -- into a shared-memory row of its own, instead of after the
+// neighbor loop with nothing in flight.  Same draws in the same order (a unit's slots are visited
+// in order either way).
+template <int KPL, int STAGES, int WARPS, bool EXACT, int NB, int NW, bool EARLY>
 __global__ void __launch_bounds__((WARPS + NW) * 32)
     k_update_phi_fast(const __grid_constant__ PhiArgs a) {
+  static_assert(!(EARLY && NW > 0), "EARLY is the producer-less way to take the noise off the critical path");
+  constexpr bool NZ_ROWS = NW > 0 || EARLY;  // a noise row per gather warp
   extern __shared__ __align__(128) unsigned char s_raw[];
   const uint32_t K = a.K;
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t row_bytes = K * 4;
-  // layout: [WARPS][(own + STAGES rows)] | NW ? [WARPS][noise row] | [WARPS][STAGES+1] stage
-  // barriers | NW ? full[WARPS], empty[WARPS]
+  // layout: [WARPS][(own + STAGES rows)] | NZ_ROWS ? [WARPS][noise row] | [WARPS][STAGES+1] stage
+  // barriers | NW ? full[WARPS], empty[WARPS] | ziggurat tables
   float* s_nz = reinterpret_cast<float*>(s_raw) + (size_t)WARPS * (STAGES + 1) * K;
-  uint64_t* bar_base = reinterpret_cast<uint64_t*>(s_raw + ((size_t)WARPS * (STAGES + 1) + (NW ? WARPS : 0)) * row_bytes);
+  uint64_t* bar_base = reinterpret_cast<uint64_t*>(s_raw + ((size_t)WARPS * (STAGES + 1) + (NZ_ROWS ? WARPS : 0)) * row_bytes);
   uint64_t* nz_full = bar_base + WARPS * (STAGES + 1);
   uint64_t* nz_empty = nz_full + WARPS;
   // ziggurat tables, after the last barrier word
@@ -303,6 +310,19 @@ __global__ void __launch_bounds__((WARPS + NW) * 32)
           y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
         }
         nxt_mask = __ballot_sync(FULL_MASK, y);
+      }
+      if (EARLY && !a.disable_noise) {  // the rows requested above are in flight meanwhile
+        float* nz = s_nz + (size_t)wib * K;
+        if (fast_noise) {
+          for (uint32_t k = lane; k < K; k += 32) nz[k] = rng_randn_t(st, zig);  // read back by this lane only
+        } else {
+          for (uint32_t vl = lane; vl < vw; vl += 32) {
+            Rng vs = rng_load(a.pool, (uint64_t)unit * vw + vl);
+            for (uint32_t k = vl; k < K; k += vw) nz[k] = rng_randn_t(vs, zig);
+            rng_store(a.pool, (uint64_t)unit * vw + vl, vs);
+          }
+          __syncwarp();
+        }
       }
       float g[KPL];
 #pragma unroll
@@ -403,10 +423,10 @@ __global__ void __launch_bounds__((WARPS + NW) * 32)
       }
 
       // Langevin noise (phi.cc:266-274) in the reference's per-state draw order
-      float* s_noise = NW > 0 ? s_nz + (size_t)wib * K : s_stage;  // NW == 0: all stages are drained here
+      float* s_noise = NZ_ROWS ? s_nz + (size_t)wib * K : s_stage;  // else: all stages are drained here
       if (NW > 0) {
         if (ws_noise) mbar_wait(&nz_full[wib], nz_item & 1);  // the producer's row for this slot
-      } else if (!a.disable_noise) {
+      } else if (!EARLY && !a.disable_noise) {
         if (fast_noise) {
           for (uint32_t k = lane; k < K; k += 32) s_noise[k] = rng_randn_t(st, zig);
         } else {
@@ -874,13 +894,13 @@ static uint32_t my_units(const PhiArgs& a) {
   return active > a.part_index ? (active - a.part_index + a.part_count - 1) / a.part_count : 0;
 }
 
-template <int KPL, int STAGES, int WARPS, int NB = 1, int NW = 0>
+template <int KPL, int STAGES, int WARPS, int NB = 1, int NW = 0, bool EARLY = false>
 static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
-  const size_t smem = ((size_t)WARPS * (STAGES + 1) + (NW ? WARPS : 0)) * a.K * 4 +
+  const size_t smem = ((size_t)WARPS * (STAGES + 1) + ((NW || EARLY) ? WARPS : 0)) * a.K * 4 +
                       (size_t)WARPS * (STAGES + 1) * 8 + (NW ? 2 * WARPS * 8 : 0) + ZIG_WORDS * 4;
   const bool exact = (a.K == 32u * KPL);
-  auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB, NW>
-                    : k_update_phi_fast<KPL, STAGES, WARPS, false, NB, NW>;
+  auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB, NW, EARLY>
+                    : k_update_phi_fast<KPL, STAGES, WARPS, false, NB, NW, EARLY>;
   int occ = 0;
   if (resident_ctas_per_sm(kern, c->device, (WARPS + NW) * 32, smem, &occ)) return 1;
   AMMSB_REQUIRE(occ > 0, "update_phi: kernel does not fit on an SM");
@@ -998,13 +1018,17 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
       if (kpl <= 16) return launch_split<16>(c, a);
       return launch_split<32>(c, a);
     }
-    if (kpl <= 2) return launch_fast<2, 8, 4, 2>(c, a);
-    if (kpl <= 4) return launch_fast<4, 8, 4, 2>(c, a);
-    if (kpl <= 8) return launch_fast<8, 6, 4, 2>(c, a);
+    // K <= 512: no producer warps (they cost the occupancy short rows need); the gather warp
+    // draws the slot's noise while its first rows are in flight (AMMSB_PHI_LATE_NOISE: after the
+    // neighbor loop, the earlier behaviour -- kept for A/B measurements)
+    const bool late = getenv("AMMSB_PHI_LATE_NOISE") != nullptr;
+    if (kpl <= 2) return late ? launch_fast<2, 8, 4, 2>(c, a) : launch_fast<2, 8, 4, 2, 0, true>(c, a);
+    if (kpl <= 4) return late ? launch_fast<4, 8, 4, 2>(c, a) : launch_fast<4, 8, 4, 2, 0, true>(c, a);
+    if (kpl <= 8) return late ? launch_fast<8, 6, 4, 2>(c, a) : launch_fast<8, 6, 4, 2, 0, true>(c, a);
     if (kpl <= 16) {
       // NB = 2 costs occupancy here (measured -6%); producer warps do not pay either at K = 512
       // (8 gather warps/SM cannot cover 2 KB rows: 5.28 vs 5.32 TB/s)
-      return launch_fast<16, 4, 4>(c, a);
+      return late ? launch_fast<16, 4, 4>(c, a) : launch_fast<16, 4, 4, 1, 0, true>(c, a);
     }
     // 4 gather warps x 4 stages + 2 noise-producer warps, 2 CTAs/SM: 6.10 TB/s at K = 1024
     // (the all-in-one <32,3,4> kernel: 5.66 TB/s; without noise both reach 6.3 TB/s)

@@ -251,11 +251,12 @@ def test_update_phi_fast_nonstandard_wg_stream(ctx, orc):
     """production kernel with the reference launched at phi_wg_size 64 and in THREAD mode:
     same noise stream mapping (state = slot*wg + k%wg)."""
     prob = link_heavy_problem(orc, 400, 128, 8)
-    for mode, wg in ((A.MODE_WG, 64), (A.MODE_THREAD, 32)):
-        r = run_phi(ctx, orc, prob, 100, mode, wg, True, strict=False)
-        assert r["state_ok"]
-        err = rel_err(r["got"], r["want"])
-        assert float((err > RTOL).mean()) < 1e-3 and err.max() < 1e-3
+    for V in (100, 300):  # the CTA-per-slot kernel (V <= #SMs) and the warp-per-slot kernel
+        for mode, wg in ((A.MODE_WG, 64), (A.MODE_THREAD, 32)):
+            r = run_phi(ctx, orc, prob, V, mode, wg, True, strict=False)
+            assert r["state_ok"]
+            err = rel_err(r["got"], r["want"])
+            assert float((err > RTOL).mean()) < 1e-3 and err.max() < 1e-3
 
 
 @pytest.mark.parametrize("K,n,V", [(1024, 32, 8), (1024, 32, 21), (64, 32, 7), (256, 5, 148), (1000, 250, 3),
