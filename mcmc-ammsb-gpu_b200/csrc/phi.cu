@@ -1033,6 +1033,8 @@ extern "C" int ammsb_update_phi(ammsb_ctx* c, const ammsb_params* p, const ammsb
     // 4 gather warps x 4 stages + 2 noise-producer warps, 2 CTAs/SM: 6.10 TB/s at K = 1024
     // (the all-in-one <32,3,4> kernel: 5.66 TB/s; without noise both reach 6.3 TB/s)
     if (getenv("AMMSB_PHI_NOWS")) return launch_fast<32, 3, 4>(c, a);
+    // experiment: no producers, early noise as for K <= 512 (8 gather warps/SM, 4 stages each)
+    if (getenv("AMMSB_PHI_EARLY_1024")) return launch_fast<32, 4, 4, 1, 0, true>(c, a);
     // few slots (link mini-batches: V = 1 + deg(u)): the launch is a latency chain of row
     // round trips, not bandwidth -- one gather warp per CTA with 16 rows in flight
     if (my_units(a) <= (uint32_t)c->sm_count && !getenv("AMMSB_PHI_NOSMALL")) return launch_fast<32, 16, 1, 1, 1>(c, a);
