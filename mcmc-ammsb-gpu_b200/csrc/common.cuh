@@ -187,9 +187,10 @@ __device__ const uint32_t d_zig_ktab[128] = AMMSB_ZIG_KTAB_INIT;
 __device__ const uint32_t d_zig_wtab[128] = AMMSB_ZIG_WTAB_BITS_INIT;
 
 // Where the three 128-entry ziggurat tables are read from.  ZigGlobal: the __device__ arrays through
-// the read-only path.  ZigShared: a per-CTA copy (ytab | ktab | wtab) -- update_phi keeps shared
-// memory so full that almost no L1 is left, the tables then live in L2 and every draw pays two
-// L2 round trips; kernels that draw noise in their inner loop stage the tables once per CTA.
+// the read-only path.  ZigShared: a per-CTA copy (ytab | ktab | wtab) for the gather warps that draw
+// their own noise (K <= 512: measured +1..3 % together with drawing at the start of a slot); the
+// noise-producer warps of the K >= 1024 kernels keep ZigGlobal, shared memory being the busy
+// resource there (K = 1024: 0.3838 ms with the shared copy, 0.3798 ms without).
 #define ZIG_WORDS 384
 struct ZigGlobal {
   __device__ __forceinline__ uint32_t y(uint32_t i) const { return __ldg(&d_zig_ytab[i]); }
