@@ -235,7 +235,7 @@ __global__ void __launch_bounds__((WARPS + NW) * 32)
   uint32_t* s_zig = reinterpret_cast<uint32_t*>(bar_base + WARPS * (STAGES + 1) + (NW ? 2 * WARPS : 0));
   const ZigShared zig{s_zig};
   const bool ws_noise = NW > 0 && !a.disable_noise;
-  zig_stage(s_zig);
+  if (NW == 0) zig_stage(s_zig);  // gather warps that draw their own noise; producers read the global tables
   if (NW > 0 && threadIdx.x == 0) {
     for (int w = 0; w < WARPS; ++w) {
       mbar_init(&nz_full[w], 1);
@@ -897,7 +897,7 @@ static uint32_t my_units(const PhiArgs& a) {
 template <int KPL, int STAGES, int WARPS, int NB = 1, int NW = 0, bool EARLY = false>
 static int launch_fast(ammsb_ctx* c, const PhiArgs& a) {
   const size_t smem = ((size_t)WARPS * (STAGES + 1) + ((NW || EARLY) ? WARPS : 0)) * a.K * 4 +
-                      (size_t)WARPS * (STAGES + 1) * 8 + (NW ? 2 * WARPS * 8 : 0) + ZIG_WORDS * 4;
+                      (size_t)WARPS * (STAGES + 1) * 8 + (NW ? 2 * WARPS * 8 : ZIG_WORDS * 4);
   const bool exact = (a.K == 32u * KPL);
   auto kern = exact ? k_update_phi_fast<KPL, STAGES, WARPS, true, NB, NW, EARLY>
                     : k_update_phi_fast<KPL, STAGES, WARPS, false, NB, NW, EARLY>;
