@@ -11,7 +11,7 @@ import pytest
 import pyammsb as A
 import pymcmc
 import pyoracle
-from util import make_edges
+from util import RefSampler, make_edges
 
 pytestmark = pytest.mark.gpu
 
@@ -121,9 +121,13 @@ def test_device_sampler_draws_the_host_strategys_minibatches(ctx, N, E, m, built
     (compared as sets: the device emits in draw order, the host in std::unordered_set order), the
     same weight, and the same rand_r state afterwards -- so the streams never drift apart.  The
     dense 3000-vertex graph makes the first candidate pass fall short (refusals + repeats)."""
+    keys = make_edges(N, E, 9)
     cfg = pymcmc.Config(K=8, mini_batch_size=m, heldout_ratio=0.1, strategy="Node")
-    cfg.set_graph(N, make_edges(N, E, 9), srand_seed=5)
+    cfg.set_graph(N, keys, srand_seed=5)
     tr, he = cfg.edges()
+    # when the reference-derived library travelled with the repo: the reference's own sample.cc too
+    ref = RefSampler(N, keys, 0.1, 5, m) if RefSampler.available() else None
+    seed_r = C.c_uint(77)
     if built:
         n_links = len(he) // 2  # held-out links come first (data.cc:86-100); the set holds only those
         train, heldout = A.BuiltSet(ctx, tr), A.BuiltSet(ctx, he[:n_links])
@@ -142,6 +146,9 @@ def test_device_sampler_draws_the_host_strategys_minibatches(ctx, N, E, m, built
     kinds = set()
     for _ in range(16):
         w_h, e_h, n_h = cfg.sample("Node", seed_h)
+        if ref is not None:
+            w_r, e_r, n_r = ref.sample("Node", seed_r)
+            assert np.array_equal(e_r, e_h) and np.array_equal(n_r, n_h) and seed_r.value == seed_h.value
         w_d, ne, nn = smp.sample(seed_d, d_edges, d_nodes)
         ctx.sync()
         e_d, n_d = d_edges.read(ne), d_nodes.read(nn)
@@ -164,3 +171,5 @@ def test_device_sampler_draws_the_host_strategys_minibatches(ctx, N, E, m, built
     for x in (d_tr, d_off, d_adj, d_deg, d_edges, d_nodes):
         x.free()
     smp.free(); train.free(); heldout.free(); cfg.close()
+    if ref is not None:
+        ref.close()

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import pymcmc
-from util import make_edges
+from util import RefSampler, make_edges
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -119,51 +119,33 @@ def test_flat_set_iterates_like_std_unordered_set(width):
     assert np.array_equal(a, b)
 
 
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
-
-
-@pytest.mark.parametrize("N,E,m", [(20000, 120000, 4096), (3000, 40000, 2500)])
+@pytest.mark.parametrize("N,E,m", [(20000, 120000, 4096), (3000, 40000, 2500), (317080, 1049866, 16384)])
 def test_minibatch_strategies_match_reference_code_at_size(N, E, m):
     """the production strategies against the reference's own sample.cc / data.cc (compiled in place
     into oracle/_ref) at mini-batch sizes that go through every std::unordered_set growth step and,
-    for the small dense graph, many refused and repeated candidates: edges and nodes in order, weight
-    and rand_r stream position, 8 mini-batches in a row per strategy"""
-    if not os.path.exists(REF_SO):
+    for the small dense graph, many refused and repeated candidates (the last shape is bench.py's:
+    com-DBLP-shaped, 16384 edges): edges and nodes in order, weight and rand_r stream position,
+    8 mini-batches in a row per strategy"""
+    if not RefSampler.available():
         pytest.skip("oracle/_ref not built (needs /root/reference); golden vectors still apply")
-    L = C.CDLL(REF_SO)
-    L.ref_generate_sets.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64, C.c_double, C.c_uint, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p]
-    L.ref_sampler_create.restype = C.c_void_p
-    L.ref_sampler_create.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
-                                     C.c_uint64]
-    L.ref_sampler_destroy.argtypes = [C.c_void_p]
-    L.ref_sample.restype = C.c_float
-    L.ref_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     keys = make_edges(N, E, 9)
-    vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    tr, he = np.zeros(E, dtype=np.uint64), np.zeros(E, dtype=np.uint64)
-    ntr, nhe = C.c_uint64(0), C.c_uint64(0)
-    assert L.ref_generate_sets(N, vp(keys), E, 0.1, 777, vp(tr), C.byref(ntr), vp(he), C.byref(nhe))
-    tr, he = tr[:ntr.value], he[:nhe.value]
-    h = L.ref_sampler_create(N, E, vp(tr), len(tr), vp(he), E - len(tr), m)
+    ref = RefSampler(N, keys, 0.1, 777, m)
     cfg = pymcmc.Config(K=8, mini_batch_size=m, heldout_ratio=0.1)
     cfg.set_graph(N, keys, srand_seed=777)
     try:
         a, b = cfg.edges()
-        assert np.array_equal(a, tr) and np.array_equal(b, he)
+        assert np.array_equal(a, ref.training) and np.array_equal(b, ref.heldout)
         for strategy in ("Node", "NodeNonLink", "NodeLink", "BF"):
             s = pymcmc.STRATEGIES.index(strategy)
             seed_ref, seed = C.c_uint(31 + s), C.c_uint(31 + s)
             for _ in range(8):
-                eb, nb = np.zeros(8 * m + 4096, dtype=np.uint64), np.zeros(16 * m + 8192, dtype=np.uint32)
-                ne, nn = C.c_uint64(0), C.c_uint64(0)
-                w_ref = L.ref_sample(h, s, C.byref(seed_ref), vp(eb), C.byref(ne), vp(nb), C.byref(nn))
+                w_ref, e_ref, n_ref = ref.sample(strategy, seed_ref)
                 w, edges, nodes = cfg.sample(strategy, seed)
-                assert np.array_equal(edges, eb[:ne.value]), strategy
-                assert np.array_equal(nodes, nb[:nn.value]), strategy
+                assert np.array_equal(edges, e_ref), strategy
+                assert np.array_equal(nodes, n_ref), strategy
                 assert np.float32(w) == np.float32(w_ref) and seed.value == seed_ref.value
     finally:
-        L.ref_sampler_destroy(h)
+        ref.close()
         cfg.close()
 
 

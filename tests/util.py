@@ -1,5 +1,60 @@
 """Shared synthetic-problem helpers for the parity tests."""
+import ctypes as C
+import os
+
 import numpy as np
+
+REF_SO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref",
+                      "libref_oracle.so")
+
+
+class RefSampler:
+    """The reference's own data.cc split and sample.cc strategies (compiled in place into
+    oracle/_ref; test infrastructure): GenerateSetsFromEdges on `keys`, then mini-batches."""
+
+    STRATEGIES = ["Node", "NodeLink", "NodeNonLink", "BFLink", "BFNonLink", "BF"]
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self, N, keys, heldout_ratio, srand_seed, m):
+        L = self.L = C.CDLL(REF_SO)
+        L.ref_generate_sets.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64, C.c_double, C.c_uint, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_sampler_create.restype = C.c_void_p
+        L.ref_sampler_create.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                         C.c_uint64]
+        L.ref_sampler_destroy.argtypes = [C.c_void_p]
+        L.ref_sample.restype = C.c_float
+        L.ref_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        E = len(keys)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        tr, he = np.zeros(E, dtype=np.uint64), np.zeros(E, dtype=np.uint64)
+        ntr, nhe = C.c_uint64(0), C.c_uint64(0)
+        if not L.ref_generate_sets(N, vp(keys), E, heldout_ratio, srand_seed, vp(tr), C.byref(ntr), vp(he),
+                                   C.byref(nhe)):
+            raise RuntimeError("reference GenerateSetsFromEdges failed")
+        self.training, self.heldout = tr[:ntr.value].copy(), he[:nhe.value].copy()
+        self.m = m
+        self.h = L.ref_sampler_create(N, E, vp(self.training), len(self.training), vp(self.heldout),
+                                      E - len(self.training), m)
+
+    def sample(self, strategy, seed):
+        """(weight, edges, nodes) of the reference strategy; `seed` (c_uint) advances in place"""
+        s = self.STRATEGIES.index(strategy)
+        eb = np.zeros(8 * self.m + 65536, dtype=np.uint64)
+        nb = np.zeros(16 * self.m + 131072, dtype=np.uint32)
+        ne, nn = C.c_uint64(0), C.c_uint64(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        w = self.L.ref_sample(self.h, s, C.byref(seed), vp(eb), C.byref(ne), vp(nb), C.byref(nn))
+        return float(w), eb[:ne.value].copy(), nb[:nn.value].copy()
+
+    def close(self):
+        if self.h:
+            self.L.ref_sampler_destroy(self.h)
+            self.h = None
 
 
 def make_edges(N, E, seed):
