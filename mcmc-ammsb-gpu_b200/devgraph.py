@@ -24,14 +24,20 @@ class _View:
         self.ptr = C.c_void_p(ptr)
 
 
+def split_sizes(E, heldout_ratio):
+    """(training edges, held-out links) of GenerateSetsFromEdges (data.cc:86-88):
+    training = ceil((1 - r/2) E) in double, r being Config::heldout_ratio, a float"""
+    r = float(np.float32(heldout_ratio))
+    training_len = int(math.ceil((1 - r / 2) * E))
+    return training_len, int(E) - training_len
+
+
 class DeviceGraph:
     def __init__(self, ctx, N, E, heldout_ratio, seed=1, log=lambda *a: None):
         import time
         t0 = time.time()
         self.ctx, self.N, self.E = ctx, int(N), int(E)
-        training_len = int(math.ceil((1 - heldout_ratio / 2) * E))  # data.cc:86-88
-        self.num_heldout_links = self.E - training_len
-        self.num_training = training_len
+        self.num_training, self.num_heldout_links = split_sizes(E, heldout_ratio)
         edges = ctx.buf(np.uint64, self.E)
         A.graph_generate(ctx, self.N, self.E, seed, edges)
         links = _View(edges.ptr.value)

@@ -217,3 +217,24 @@ def test_flat_set_order_property():
         assert np.array_equal(a, b)
 
     check()
+
+
+@pytest.mark.parametrize("E,r", [(14496, 0.01), (1049866, 0.10), (34681189, 0.01), (1806067135, 0.01), (3000, 0.1),
+                                 (120001, 0.3), (7, 0.5)])
+def test_device_graph_split_sizes_are_data_cc(E, r):
+    """devgraph.DeviceGraph splits the edge list like GenerateSetsFromEdges (data.cc:86-88):
+    checked against the SURVEY table for the named shapes and against the host split where a host
+    can build the graph"""
+    import devgraph
+    tr, he = devgraph.split_sizes(E, r)
+    assert tr + he == E
+    table = {14496: 14424, 1049866: 997373, 34681189: 34507784, 1806067135: 1797036800}  # SURVEY.md section 8
+    if E in table:
+        assert tr == table[E]
+    if E <= 200000:
+        N = 2000
+        c = pymcmc.Config(K=8, mini_batch_size=8, heldout_ratio=r)
+        c.set_graph(N, make_edges(N, E, 3))
+        a, b = c.edges()
+        assert (len(a), len(b)) == (tr, 2 * he)
+        c.close()
