@@ -8,6 +8,7 @@
 #include <sstream>
 
 #include "mcmc/learner.h"
+#include "mcmc/serialize.h"
 #include "mcmc/std_order_set.h"
 #include <unordered_set>
 
@@ -189,6 +190,28 @@ uint64_t mcmc_test_set_order(const uint64_t* keys, uint64_t n, int width, uint64
   return a.size() == b.size() ? a.size() : ~0ull;
 }
 
+// data.h entry points for the harness: the SNAP text loader (after srand(seed), as main.cc leaves
+// libc's generator) and the gzip dataset dump of main.cc:109-143
+int64_t mcmc_unique_edges_from_file(const char* path, unsigned srand_seed, uint64_t* count_vertices,
+                                    uint64_t* edges_out, uint64_t cap) {
+  std::vector<Edge> vals;
+  srand(srand_seed);
+  if (!GetUniqueEdgesFromFile(path, count_vertices, &vals)) return -1;
+  if (vals.size() > cap) return -2;
+  std::memcpy(edges_out, vals.data(), 8 * vals.size());
+  return static_cast<int64_t>(vals.size());
+}
+int mcmc_dump_dataset(const char* path, uint64_t N, float heldout_ratio, const uint64_t* edges, uint64_t n) {
+  return DumpDataset(path, N, heldout_ratio, std::vector<Edge>(edges, edges + n)) ? 0 : 1;
+}
+int64_t mcmc_load_dataset(const char* path, uint64_t* N, float* heldout_ratio, uint64_t* edges_out, uint64_t cap) {
+  std::vector<Edge> vals;
+  if (!LoadDataset(path, N, heldout_ratio, &vals)) return -1;
+  if (vals.size() > cap) return -2;
+  std::memcpy(edges_out, vals.data(), 8 * vals.size());
+  return static_cast<int64_t>(vals.size());
+}
+
 // test hooks: exact remainder without a divide, and the per-endpoint view of a cuckoo set that
 // the non-link strategy filters with (which: 0 training, 1 held-out)
 void mcmc_test_fastmod(const uint64_t* a, const uint64_t* d, uint64_t n, uint64_t* out) {
@@ -209,6 +232,116 @@ int64_t mcmc_config_partners(void* vc, int which, uint32_t u, uint32_t* out, uin
   for (const Vertex* v = idx->begin(u); v != idx->end(u); ++v, ++n)
     if (n < cap) out[n] = *v;
   return static_cast<int64_t>(n);
+}
+
+// test hooks: one checkpoint record (uint64 length + proto2 message, serialize.h) of each kind,
+// written from / parsed into plain arrays.  kind: 0 BetaProperties, 1 PhiProperties,
+// 2 PerplexityProperties, 3 SampleStorage, 4 LearnerProperties, 5 VectorStorage, 6 RpmProperties.
+// ints/dbls hold the integer / double fields in field order; b1/b2 the bytes fields.
+uint64_t mcmc_test_serialize(int kind, const uint64_t* ints, const double* dbls, const char* b1, uint64_t n1,
+                             const char* b2, uint64_t n2, char* out, uint64_t cap) {
+  std::ostringstream o;
+  bool ok = false;
+  switch (kind) {
+    case 0: {
+      BetaProperties m;
+      m.count_calls = static_cast<uint32_t>(ints[0]);
+      m.theta_sum_time = dbls[0]; m.grads_partial_time = dbls[1]; m.grads_sum_time = dbls[2];
+      m.update_theta_time = dbls[3]; m.normalize_time = dbls[4];
+      ok = SerializeMessage(&o, m);
+      break;
+    }
+    case 1: {
+      PhiProperties m;
+      m.count_calls = static_cast<uint32_t>(ints[0]);
+      m.update_phi_time = dbls[0]; m.update_pi_time = dbls[1];
+      ok = SerializeMessage(&o, m);
+      break;
+    }
+    case 2: {
+      PerplexityProperties m;
+      m.count_calls = static_cast<uint32_t>(ints[0]);
+      m.ppx_time = dbls[0]; m.accumulate_time = dbls[1];
+      ok = SerializeMessage(&o, m);
+      break;
+    }
+    case 3: {
+      SampleStorage m;
+      m.edges.assign(b1, n1);
+      m.nodes_vec.assign(b2, n2);
+      m.seed = static_cast<uint32_t>(ints[0]);
+      ok = SerializeMessage(&o, m);
+      break;
+    }
+    case 4: {
+      LearnerProperties m;
+      m.stepCount = static_cast<uint32_t>(ints[0]);
+      m.time = ints[1]; m.samplingTime = ints[2];
+      m.phase = static_cast<int32_t>(static_cast<int64_t>(ints[3]));
+      m.weight = dbls[0];
+      ok = SerializeMessage(&o, m);
+      break;
+    }
+    case 5: ok = SerializeBytes(&o, b1, n1); break;
+    case 6:
+      ok = WriteRpmProperties(&o, static_cast<uint32_t>(ints[0]), static_cast<uint32_t>(ints[1]),
+                              static_cast<uint32_t>(ints[2]));
+      break;
+  }
+  const std::string s = o.str();
+  if (!ok || s.size() > cap) return ~0ull;
+  std::memcpy(out, s.data(), s.size());
+  return s.size();
+}
+int mcmc_test_parse(int kind, const char* bytes, uint64_t n, uint64_t* ints, double* dbls, char* b1, uint64_t* n1,
+                    char* b2, uint64_t* n2) {
+  std::istringstream in(std::string(bytes, n));
+  switch (kind) {
+    case 0: {
+      BetaProperties m;
+      if (!ParseMessage(&in, &m)) return 1;
+      ints[0] = m.count_calls;
+      dbls[0] = m.theta_sum_time; dbls[1] = m.grads_partial_time; dbls[2] = m.grads_sum_time;
+      dbls[3] = m.update_theta_time; dbls[4] = m.normalize_time;
+      return 0;
+    }
+    case 1: {
+      PhiProperties m;
+      if (!ParseMessage(&in, &m)) return 1;
+      ints[0] = m.count_calls; dbls[0] = m.update_phi_time; dbls[1] = m.update_pi_time;
+      return 0;
+    }
+    case 2: {
+      PerplexityProperties m;
+      if (!ParseMessage(&in, &m)) return 1;
+      ints[0] = m.count_calls; dbls[0] = m.ppx_time; dbls[1] = m.accumulate_time;
+      return 0;
+    }
+    case 3: {
+      SampleStorage m;
+      if (!ParseMessage(&in, &m) || m.edges.size() > *n1 || m.nodes_vec.size() > *n2) return 1;
+      std::memcpy(b1, m.edges.data(), m.edges.size());
+      std::memcpy(b2, m.nodes_vec.data(), m.nodes_vec.size());
+      *n1 = m.edges.size(); *n2 = m.nodes_vec.size(); ints[0] = m.seed;
+      return 0;
+    }
+    case 4: {
+      LearnerProperties m;
+      if (!ParseMessage(&in, &m)) return 1;
+      ints[0] = m.stepCount; ints[1] = m.time; ints[2] = m.samplingTime;
+      ints[3] = static_cast<uint64_t>(static_cast<int64_t>(m.phase));
+      dbls[0] = m.weight;
+      return 0;
+    }
+    case 5: return ParseBytes(&in, b1, *n1) ? 0 : 1;  // *n1 = expected size (mismatch fails)
+    case 6: {
+      uint32_t r = 0, c = 0, b = 0;
+      if (!ReadRpmProperties(&in, &r, &c, &b)) return 1;
+      ints[0] = r; ints[1] = c; ints[2] = b;
+      return 0;
+    }
+  }
+  return 1;
 }
 
 // theta init stream of Learner::Learner (host mt19937 + gamma_distribution)

@@ -125,12 +125,33 @@ bool ParseBytes(std::istream* in, void* data, size_t n) {
   return r.ok && found;
 }
 
-bool SerializeRpm(std::ostream* out, RowPartitionedMatrix<Float>* rpm) {
+bool WriteRpmProperties(std::ostream* out, uint32_t rows, uint32_t cols, uint32_t rows_in_block) {
   std::string props;
-  wire::PutUInt(&props, 1, rpm->Rows());
-  wire::PutUInt(&props, 2, rpm->Cols());
-  wire::PutUInt(&props, 3, rpm->RowsPerBlock());
-  if (!WriteRecord(out, props)) return false;
+  wire::PutUInt(&props, 1, rows);
+  wire::PutUInt(&props, 2, cols);
+  wire::PutUInt(&props, 3, rows_in_block);
+  return WriteRecord(out, props);
+}
+
+bool ReadRpmProperties(std::istream* in, uint32_t* rows, uint32_t* cols, uint32_t* rows_in_block) {
+  std::string props;
+  if (!ReadRecord(in, &props)) return false;
+  wire::Reader r{props.data(), props.data() + props.size()};
+  uint32_t f, t;
+  while (r.Next(&f, &t)) {
+    if (t != 0) { r.Skip(t); continue; }
+    const uint64_t v = r.Varint();
+    if (f == 1) *rows = static_cast<uint32_t>(v);
+    if (f == 2) *cols = static_cast<uint32_t>(v);
+    if (f == 3) *rows_in_block = static_cast<uint32_t>(v);
+  }
+  return r.ok;
+}
+
+bool SerializeRpm(std::ostream* out, RowPartitionedMatrix<Float>* rpm) {
+  if (!WriteRpmProperties(out, static_cast<uint32_t>(rpm->Rows()), static_cast<uint32_t>(rpm->Cols()),
+                          static_cast<uint32_t>(rpm->RowsPerBlock())))
+    return false;
   std::vector<Float> host;
   for (uint64_t row = 0; row < rpm->Rows(); row += rpm->RowsPerBlock()) {
     const uint64_t n = std::min<uint64_t>(rpm->RowsPerBlock(), rpm->Rows() - row);
@@ -142,18 +163,9 @@ bool SerializeRpm(std::ostream* out, RowPartitionedMatrix<Float>* rpm) {
 }
 
 bool ParseRpm(std::istream* in, RowPartitionedMatrix<Float>* rpm) {
-  std::string props;
-  if (!ReadRecord(in, &props)) return false;
-  wire::Reader r{props.data(), props.data() + props.size()};
-  uint32_t f, t, rows = 0, cols = 0, rib = 0;
-  while (r.Next(&f, &t)) {
-    if (t != 0) { r.Skip(t); continue; }
-    const uint64_t v = r.Varint();
-    if (f == 1) rows = static_cast<uint32_t>(v);
-    if (f == 2) cols = static_cast<uint32_t>(v);
-    if (f == 3) rib = static_cast<uint32_t>(v);
-  }
-  if (!r.ok || rows != rpm->Rows() || cols != rpm->Cols() || rib != rpm->RowsPerBlock()) return false;
+  uint32_t rows = 0, cols = 0, rib = 0;
+  if (!ReadRpmProperties(in, &rows, &cols, &rib)) return false;
+  if (rows != rpm->Rows() || cols != rpm->Cols() || rib != rpm->RowsPerBlock()) return false;
   std::vector<Float> host;
   for (uint64_t row = 0; row < rows; row += rib) {
     const uint64_t n = std::min<uint64_t>(rib, rows - row);

@@ -59,6 +59,8 @@ bool Parse(std::istream* in, clcuda::Buffer<T>* buf, clcuda::Queue* queue) {
 // followed by one VectorStorage per block of rows_in_block rows (serialize.h:72-113)
 template <class T>
 class RowPartitionedMatrix;
+bool WriteRpmProperties(std::ostream* out, uint32_t rows, uint32_t cols, uint32_t rows_in_block);
+bool ReadRpmProperties(std::istream* in, uint32_t* rows, uint32_t* cols, uint32_t* rows_in_block);
 bool SerializeRpm(std::ostream* out, RowPartitionedMatrix<Float>* rpm);
 bool ParseRpm(std::istream* in, RowPartitionedMatrix<Float>* rpm);
 

@@ -494,6 +494,18 @@ int ref_generate_sets(uint64_t N_, const uint64_t* edges, uint64_t n, double hel
   return 1;
 }
 
+// GetUniqueEdgesFromFile (data.cc:36-78) after srand(seed): SNAP text -> renumbered, sorted,
+// de-duplicated, shuffled edge list.  Returns the edge count (-1: failure, -2: edges_out too small).
+int64_t ref_unique_edges_from_file(const char* path, unsigned srand_seed, uint64_t* count_vertices,
+                                   uint64_t* edges_out, uint64_t cap) {
+  std::vector<mcmc::Edge> vals;
+  srand(srand_seed);
+  if (!mcmc::GetUniqueEdgesFromFile(path, count_vertices, &vals)) return -1;
+  if (vals.size() > cap) return -2;
+  memcpy(edges_out, vals.data(), 8 * vals.size());
+  return (int64_t)vals.size();
+}
+
 // one mini-batch of the given strategy + ExtractNodesFromMiniBatch (learner.cc:162-173)
 struct RefSamplerCtx {
   mcmc::Config cfg;

@@ -125,3 +125,21 @@ for strat, name in enumerate(["Node", "NodeLink", "NodeNonLink", "BFLink", "BFNo
     host["mb_%s_meta" % name] = np.array(meta, dtype=np.float64)
 L.ref_sampler_destroy(h)
 save("host.npz", **host)
+
+# ---- SNAP text loader (data.cc:36-78): a small file with a 4-line header, repeated and reversed
+# pairs, sparse vertex ids ----
+L.ref_unique_edges_from_file.restype = C.c_int64
+L.ref_unique_edges_from_file.argtypes = [C.c_char_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint64]
+rng = np.random.default_rng(11)
+ids = rng.choice(100000, size=300, replace=False)
+pairs = [(int(ids[a]), int(ids[b])) for a, b in rng.integers(0, 300, size=(2500, 2)) if a != b]
+pairs += [(b, a) for a, b in pairs[:200]] + pairs[200:300]
+snap_text = "# Undirected graph: synthetic\n# test fixture\n# Nodes: 300 Edges: %d\n# FromNodeId\tToNodeId\n" % len(pairs)
+snap_text += "".join("%d\t%d\n" % p for p in pairs)
+snap_path = "/tmp/ammsb_golden_snap.txt"
+open(snap_path, "w").write(snap_text)
+out_e = np.zeros(len(pairs), dtype=np.uint64)
+nv = C.c_uint64(0)
+n = L.ref_unique_edges_from_file(snap_path.encode(), 4321, C.byref(nv), out_e.ctypes.data_as(C.c_void_p), len(out_e))
+assert n > 0
+save("snap.npz", text=np.frombuffer(snap_text.encode(), dtype=np.uint8), srand_seed=4321, N=nv.value, edges=out_e[:n])
