@@ -60,6 +60,14 @@ int mcmc_config_set(void* vc, const char* key, double v) {
   else if (k == "calc_train_ppx") c->calc_train_ppx = v != 0;
   else if (k == "training_ppx_ratio") c->training_ppx_ratio = v;
   else if (k == "stage_timers") c->stage_timers = v != 0;
+  else if (k == "N") c->N = static_cast<uint64_t>(v);
+  else if (k == "E") c->E = static_cast<uint64_t>(v);
+  else if (k == "ppx_wg_size") c->ppx_wg_size = static_cast<uint32_t>(v);
+  else if (k == "beta_wg_size") c->beta_wg_size = static_cast<uint32_t>(v);
+  else if (k == "phi_vector_width") c->phi_vector_width = static_cast<uint32_t>(v);
+  else if (k == "phi_probs_shared") c->phi_probs_shared = v != 0;
+  else if (k == "phi_grads_shared") c->phi_grads_shared = v != 0;
+  else if (k == "phi_pi_shared") c->phi_pi_shared = v != 0;
   else { g_err = "unknown config key " + k; return 1; }
   return 0;
 }
@@ -106,6 +114,16 @@ int mcmc_config_print(void* vc, char* buf, size_t len) {
   o << *static_cast<Config*>(vc);
   std::strncpy(buf, o.str().c_str(), len - 1);
   buf[len - 1] = 0;
+  return 0;
+}
+// operator<<(Config), then "flags:" and the MakeCompileFlags list one per line
+int mcmc_config_print_with_flags(void* vc, char* buf, size_t len) {
+  std::ostringstream o;
+  o << *static_cast<Config*>(vc) << "flags:\n";
+  for (const std::string& f : MakeCompileFlags(*static_cast<Config*>(vc))) o << f << "\n";
+  const std::string s = o.str();
+  if (s.size() + 1 > len) return 1;
+  std::memcpy(buf, s.c_str(), s.size() + 1);
   return 0;
 }
 void mcmc_config_params(void* vc, ammsb_params* p) { *p = MakeParams(*static_cast<Config*>(vc)); }

@@ -15,6 +15,7 @@
 #include <omp.h>
 
 #include <memory>
+#include <sstream>
 #include <string>
 #include <tuple>
 #include <unordered_set>
@@ -527,6 +528,34 @@ void* ref_sampler_create(uint64_t N_, uint64_t E_, const uint64_t* training, uin
   return c;
 }
 void ref_sampler_destroy(void* h) { delete (RefSamplerCtx*)h; }
+
+// operator<<(Config) (config.cc:85-117) followed by the MakeCompileFlags list (config.cc:66-83), one
+// flag per line after a "flags:" line.  v[] = heldout_ratio, alpha, a, b, c, epsilon, eta0, eta1, K, m, n,
+// N, E, ppx_wg, phi_wg, beta_wg, strategy, phi_mode, phi_vector_width, probs/grads/pi shared;
+// seeds = phi, beta, neighbor (x, y each).  h (may be NULL): a sampler context whose sets are printed.
+int ref_config_print(void* h, const double* v, const uint64_t* seeds, char* buf, uint64_t len) {
+  mcmc::Config local;
+  mcmc::Config& c = h ? ((RefSamplerCtx*)h)->cfg : local;
+  c.heldout_ratio = v[0]; c.alpha = v[1]; c.a = v[2]; c.b = v[3]; c.c = v[4]; c.epsilon = v[5];
+  c.eta0 = v[6]; c.eta1 = v[7];
+  c.K = (uint64_t)v[8]; c.mini_batch_size = (uint64_t)v[9]; c.num_node_sample = (uint64_t)v[10];
+  c.N = (uint64_t)v[11]; c.E = (uint64_t)v[12];
+  c.ppx_wg_size = (uint32_t)v[13]; c.phi_wg_size = (uint32_t)v[14]; c.beta_wg_size = (uint32_t)v[15];
+  c.strategy = (mcmc::SampleStrategy)(int)v[16];
+  c.phi_mode = (mcmc::PhiUpdaterMode)(int)v[17];
+  c.phi_vector_width = (uint32_t)v[18];
+  c.phi_probs_shared = v[19] != 0; c.phi_grads_shared = v[20] != 0; c.phi_pi_shared = v[21] != 0;
+  c.phi_seed = {seeds[0], seeds[1]};
+  c.beta_seed = {seeds[2], seeds[3]};
+  c.neighbor_seed = {seeds[4], seeds[5]};
+  std::ostringstream o;
+  o << c << "flags:\n";
+  for (const std::string& f : mcmc::MakeCompileFlags(c)) o << f << "\n";
+  const std::string s = o.str();
+  if (s.size() + 1 > len) return 1;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
 uint64_t ref_sampler_max_fan_out(void* h) { return ((RefSamplerCtx*)h)->cfg.trainingGraph->MaxFanOut(); }
 
 // strategy numbering = enum SampleStrategy (sample.h:94-101)

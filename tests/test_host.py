@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import pymcmc
-from util import RefSampler, make_edges
+from util import REF_SO, RefSampler, make_edges
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -238,3 +238,64 @@ def test_device_graph_split_sizes_are_data_cc(E, r):
         a, b = c.edges()
         assert (len(a), len(b)) == (tr, 2 * he)
         c.close()
+
+
+CFG_KEYS = ["heldout_ratio", "alpha", "a", "b", "c", "epsilon", "eta0", "eta1", "K", "mini_batch_size",
+            "num_node_sample", "N", "E", "ppx_wg_size", "phi_wg_size", "beta_wg_size", "strategy", "phi_mode",
+            "phi_vector_width", "phi_probs_shared", "phi_grads_shared", "phi_pi_shared"]
+
+
+def _config_texts(values, seeds, ref_handle=None, cfg=None):
+    L = C.CDLL(REF_SO)
+    buf = C.create_string_buffer(1 << 14)
+    v = np.array(values, dtype=np.float64)
+    s = np.array(seeds, dtype=np.uint64)
+    L.ref_config_print.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint64]
+    assert L.ref_config_print(ref_handle, v.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), buf, len(buf)) == 0
+    want = buf.value.decode()
+    own = cfg or pymcmc.Config(cli_defaults=False)
+    own.set(**dict(zip(CFG_KEYS, values)))
+    for name, (x, y) in zip(("phi_seed", "beta_seed", "neighbor_seed"), zip(seeds[::2], seeds[1::2])):
+        own.set_seed(name, x, y)
+    assert pymcmc.lib().mcmc_config_print_with_flags(own.h, buf, C.c_size_t(len(buf))) == 0
+    got = buf.value.decode()
+    if cfg is None:
+        own.close()
+    return got, want
+
+
+@pytest.mark.parametrize("values,seeds", [
+    ([0.01, 0.001, 0.0315, 1024, 0.5, 1e-7, 1, 1, 32, 32, 32, 0, 0, 32, 32, 32, 0, 1, 1, 1, 1, 1], [42, 43, 113, 117, 3337, 54351]),
+    ([0.1, 1.0 / 1024, 0.01, 4096, 0.55, 1e-30, 0.5, 2.25, 1024, 16384, 32, 317080, 1049866, 64, 128, 256, 4, 0, 4, 1, 1, 1],
+     [1, 2, 3, 4, 5, 6]),
+    ([0.333333, 1.0 / 3, 123456.789, 3e9, 1e-3, 0.1, 1e10, 7e-5, 7, 5, 3, 65608366, 1806067135, 1, 1, 1, 5, 3, 16, 0, 1, 0],
+     [2 ** 64 - 1, 0, 2 ** 63, 9, 8, 7]),
+    ([0.05, 0.2, 0.0315, 1024, 0.5, 1e-7, 1, 1, 5, 100, 10, 1000, 8000, 32, 32, 32, 2, 2, 2, 1, 0, 1], [42, 43, 44, 45, 56, 57]),
+])
+def test_config_print_and_compile_flags_match_reference_code(values, seeds):
+    """operator<<(Config) (config.cc:85-117) and the -D flag list of MakeCompileFlags
+    (config.cc:57-83: every Float as "%e" text + "f") character for character against the
+    reference's own config.cc, over all strategies / phi modes / the CODE_GEN-only lines"""
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    got, want = _config_texts(values, seeds)
+    assert got == want
+    assert "flags:\n-DK=" in got or "-DK=" in got
+
+
+def test_config_print_with_sets_matches_reference_code():
+    """the same with the edge sets in place: the "|Training edges|" / "|Heldout edges|" lines print
+    cuckoo::Set::Size(), the count of successful inserts"""
+    if not RefSampler.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    N, E, m = 3000, 40000, 64
+    keys = make_edges(N, E, 9)
+    ref = RefSampler(N, keys, 0.1, 777, m)
+    cfg = pymcmc.Config(cli_defaults=False, heldout_ratio=0.1)
+    cfg.set_graph(N, keys, srand_seed=777)
+    values = [0.1, 0.001, 0.0315, 1024, 0.5, 1e-7, 1, 1, 32, m, 32, N, E, 32, 32, 32, 0, 1, 1, 1, 1, 1]
+    got, want = _config_texts(values, [42, 43, 113, 117, 3337, 54351], ref_handle=ref.h, cfg=cfg)
+    assert "|Training edges|: " in want and "|Heldout edges|: " in want
+    assert got == want
+    ref.close()
+    cfg.close()
