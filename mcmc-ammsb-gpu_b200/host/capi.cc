@@ -116,6 +116,22 @@ int mcmc_config_print(void* vc, char* buf, size_t len) {
   buf[len - 1] = 0;
   return 0;
 }
+// operator>>(SampleStrategy) / operator>>(PhiUpdaterMode): the enum value, -1 when the parser throws
+int mcmc_parse_token(int kind, const char* token) {
+  std::istringstream in(token);
+  try {
+    if (kind == 0) {
+      SampleStrategy s;
+      in >> s;
+      return static_cast<int>(s);
+    }
+    PhiUpdaterMode m;
+    in >> m;
+    return static_cast<int>(m);
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
 // operator<<(Config), then "flags:" and the MakeCompileFlags list one per line
 int mcmc_config_print_with_flags(void* vc, char* buf, size_t len) {
   std::ostringstream o;

@@ -529,6 +529,24 @@ void* ref_sampler_create(uint64_t N_, uint64_t E_, const uint64_t* training, uin
 }
 void ref_sampler_destroy(void* h) { delete (RefSamplerCtx*)h; }
 
+// operator>>(SampleStrategy) (sample.cc:135-156) / operator>>(PhiUpdaterMode) (config.cc:119-137):
+// the enum value for a token, -1 when the reference throws
+int ref_parse_token(int kind, const char* token) {
+  std::istringstream in(token);
+  try {
+    if (kind == 0) {
+      mcmc::SampleStrategy s;
+      in >> s;
+      return (int)s;
+    }
+    mcmc::PhiUpdaterMode m;
+    in >> m;
+    return (int)m;
+  } catch (...) {
+    return -1;
+  }
+}
+
 // operator<<(Config) (config.cc:85-117) followed by the MakeCompileFlags list (config.cc:66-83), one
 // flag per line after a "flags:" line.  v[] = heldout_ratio, alpha, a, b, c, epsilon, eta0, eta1, K, m, n,
 // N, E, ppx_wg, phi_wg, beta_wg, strategy, phi_mode, phi_vector_width, probs/grads/pi shared;

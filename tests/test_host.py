@@ -299,3 +299,19 @@ def test_config_print_with_sets_matches_reference_code():
     assert got == want
     ref.close()
     cfg.close()
+
+
+def test_strategy_and_phi_mode_tokens_parse_like_the_reference():
+    """--strategy / --phi-mode tokens (case-insensitive; anything else is refused) and their printed
+    names, against the reference's operator>> / to_string"""
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    R, L = C.CDLL(REF_SO), pymcmc.lib()
+    tokens = ["Node", "node", "NODE", "NodeLink", "nodelink", "NodeNonLink", "BFLink", "bflink", "BFNonLink", "BF", "bf",
+              "Nod", "NodeX", "", "Random", "THREAD", "thread", "WG-NAIVE", "wg-naive", "WG-SHARED", "WG-GEN", "wg-gen",
+              "WG", "WG_NAIVE", "naive"]
+    for kind in (0, 1):
+        for t in tokens:
+            assert L.mcmc_parse_token(kind, t.encode()) == R.ref_parse_token(kind, t.encode()), (kind, t)
+    assert [L.mcmc_parse_token(0, s.encode()) for s in pymcmc.STRATEGIES] == list(range(6))
+    assert [L.mcmc_parse_token(1, s.encode()) for s in pymcmc.PHI_MODES] == list(range(4))
