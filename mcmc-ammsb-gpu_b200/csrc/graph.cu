@@ -220,6 +220,7 @@ static int generate_unique(ammsb_ctx* c, uint64_t N, uint64_t want, uint64_t see
   const uint64_t salt = mix64(seed ^ 0x5851f42d4c957f2dull);
   uint64_t count = want + want / 32 + 4096;
   for (int attempt = 0; attempt < 6; ++attempt, count += count / 2) {
+    AMMSB_REQUIRE(count < (1ull << 31), "too many candidates for one generation pass (graph too dense?)");
     uint64_t *d_a = nullptr, *d_b = nullptr, *d_num = nullptr;
     void* d_tmp = nullptr;
     size_t tmp_sort = 0, tmp_uniq = 0;
