@@ -16,6 +16,12 @@ host sampling, H2D of edges/nodes and a D2H read of beta inside the timed region
 `--impl reference` times the reference's own CPU implementation (oracle/_ref: the reference's
 kernel text + host sampler compiled from /root/reference; falls back to the oracle port) on the
 box's host cores for the same metric on a bounded sample of the same workload.
+
+Other shapes (development; the contract run uses the defaults): --shape com-LiveJournal |
+com-Friendster | com-Friendster-eighth ..., --K/--m/--n.  --graph device (default above 100 M
+edges) builds the synthetic graph, the cuckoo sets, the held-out pairs and the adjacency in HBM
+and draws the mini-batches on the device (csrc/graph.cu) through the sharded driver -- the only
+way to run the full com-Friendster shape (1.8 G edges).
 """
 import argparse
 import ctypes as C
