@@ -246,6 +246,16 @@ int64_t mcmc_load_dataset(const char* path, uint64_t* N, float* heldout_ratio, u
   return static_cast<int64_t>(vals.size());
 }
 
+// Graph::NeighborsOf (data.h) of the training (which = 0) or held-out graph; returns the degree
+int64_t mcmc_config_neighbors(void* vc, int which, uint32_t u, uint32_t* out, uint64_t cap) {
+  Config* c = static_cast<Config*>(vc);
+  const Graph* g = which == 0 ? c->trainingGraph.get() : c->heldoutGraph.get();
+  if (g == nullptr) return -1;
+  const std::vector<Vertex>& adj = g->NeighborsOf(u);
+  for (size_t i = 0; i < adj.size() && i < cap; ++i) out[i] = adj[i];
+  return static_cast<int64_t>(adj.size());
+}
+
 // test hooks: exact remainder without a divide, and the per-endpoint view of a cuckoo set that
 // the non-link strategy filters with (which: 0 training, 1 held-out)
 void mcmc_test_fastmod(const uint64_t* a, const uint64_t* d, uint64_t n, uint64_t* out) {

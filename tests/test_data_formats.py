@@ -79,3 +79,31 @@ def test_dataset_dump_is_the_references_gzip_layout(tmp_path):
     assert np.array_equal(out[:n], edges[:-7])
     assert L.mcmc_load_dataset(str(tmp_path / "missing.gz").encode(), C.byref(n_), C.byref(r_),
                                out.ctypes.data_as(C.c_void_p), C.c_uint64(len(out))) == -1
+
+
+def test_graph_adjacency_is_symmetric_and_complete():
+    """data-test.cc:27-53 of the reference: every edge appears in both endpoints' neighbor lists,
+    nothing else does; lists are in edge-list order (the order sampleNodeLink emits in) and
+    MaxFanOut is the largest list"""
+    N, E = 800, 6000
+    keys = make_edges(N, E, 4)
+    cfg = pymcmc.Config(K=8, mini_batch_size=8, heldout_ratio=0.1)
+    cfg.set_graph(N, keys)
+    tr, he = cfg.edges()
+    L = pymcmc.lib()
+    L.mcmc_config_neighbors.restype = C.c_int64
+    for which, edges in ((0, tr), (1, he)):
+        want = [[] for _ in range(N)]
+        for e in edges:
+            u, v = int(e) >> 32, int(e) & 0xFFFFFFFF
+            want[u].append(v)
+            want[v].append(u)
+        fan = 0
+        for u in range(N):
+            buf = np.zeros(256, dtype=np.uint32)
+            d = L.mcmc_config_neighbors(cfg.h, which, C.c_uint32(u), buf.ctypes.data_as(C.c_void_p), C.c_uint64(256))
+            assert d == len(want[u]) and buf[:d].tolist() == want[u]
+            fan = max(fan, d)
+        if which == 0:
+            assert cfg.max_fan_out() == fan
+    cfg.close()
