@@ -291,6 +291,10 @@ int ammsb_peer_attach_fd(ammsb_peer* peer, uint32_t peer_rank, int fd);
 int ammsb_peer_barrier(ammsb_ctx* ctx, ammsb_peer* peer);
 int ammsb_peer_allreduce_f32(ammsb_ctx* ctx, ammsb_peer* peer, float* d_inout, uint32_t count);
 int ammsb_peer_allreduce_f64(ammsb_ctx* ctx, ammsb_peer* peer, double* d_inout, uint32_t count);
+/* a wait inside one of the kernels above gives up after a few seconds (a peer died or never
+ * launched) instead of hanging the GPU; *timed_out_epoch is the call number of the first such
+ * wait, 0 if there was none.  Synchronous. */
+int ammsb_peer_check(ammsb_peer* peer, uint32_t* timed_out_epoch);
 
 /* ---- work-group helpers the reference tests directly (wg-sum-test.cc,
  *      wg-normalize-test.cc): rows of `len` floats, one warp per row, reference

@@ -276,14 +276,20 @@ static int store_create_impl(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t num_
   if (shareable) {
     if (vmm_alloc(c->device, sizeof(float) * s->rows_per_shard * K, &s->vmm_pi) ||
         vmm_alloc(c->device, sizeof(float) * s->rows_per_shard, &s->vmm_phi)) {
+      vmm_free(&s->vmm_pi);
       delete s;
       return 1;
     }
     s->d_pi = reinterpret_cast<float*>(s->vmm_pi.ptr);
     s->d_phi = reinterpret_cast<float*>(s->vmm_phi.ptr);
   } else {
-    AMMSB_CHECK_CUDA(cudaMalloc((void**)&s->d_pi, sizeof(float) * s->rows_per_shard * K));
-    AMMSB_CHECK_CUDA(cudaMalloc((void**)&s->d_phi, sizeof(float) * s->rows_per_shard));
+    cudaError_t e = cudaMalloc((void**)&s->d_pi, sizeof(float) * s->rows_per_shard * K);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_phi, sizeof(float) * s->rows_per_shard);
+    if (e != cudaSuccess) {
+      cudaFree(s->d_pi);
+      delete s;
+      AMMSB_CHECK_CUDA(e);
+    }
   }
   s->peer_pi[shard_id] = s->d_pi;
   s->peer_phi[shard_id] = s->d_phi;

@@ -44,6 +44,8 @@ struct ammsb_peer {
 
 #define PEER_FLAG_STRIDE 32u                       // one flag per 128-byte line (in uint32 units)
 #define PEER_HEADER_BYTES (AMMSB_MAX_SHARDS * 128u)
+#define PEER_ERR_WORD 16u                          // second half of flag line 0: epoch of a timed-out wait
+#define PEER_SPIN_LIMIT (1u << 26)                 // x >= 64 ns: more than 4 s
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -61,7 +63,17 @@ __device__ __forceinline__ void peer_signal_and_wait(const PeerView& v, uint32_t
     __threadfence_system();
     st_release_sys(reinterpret_cast<uint32_t*>(v.box[t]) + v.rank * PEER_FLAG_STRIDE, epoch);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(v.box[v.rank]) + t * PEER_FLAG_STRIDE;
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) __nanosleep(40);
+    // bounded: a rank that died (or never launched) must not hang this GPU inside a kernel.  On
+    // expiry the error word of the own mailbox is set (ammsb_peer_check reads it) and the kernel
+    // carries on -- its results are then meaningless, but the process stays controllable.
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+      __nanosleep(64);
+      if (++spins > PEER_SPIN_LIMIT) {
+        atomicExch(reinterpret_cast<uint32_t*>(v.box[v.rank]) + PEER_ERR_WORD, epoch);
+        break;
+      }
+    }
   }
 }
 
@@ -97,6 +109,10 @@ __global__ void __launch_bounds__(256)
 extern "C" int ammsb_peer_create(ammsb_ctx* c, uint32_t world, uint32_t rank, size_t slot_bytes, ammsb_peer** out) {
   AMMSB_REQUIRE(world >= 1 && world <= AMMSB_MAX_SHARDS && rank < world, "bad world / rank");
   AMMSB_REQUIRE(slot_bytes > 0 && slot_bytes % 16 == 0, "slot_bytes must be a positive multiple of 16");
+  int ndev = 0;
+  AMMSB_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+  // one rank per GPU: two ranks' waiting kernels on one device can starve each other
+  AMMSB_REQUIRE((int)world <= ndev, "more ranks than CUDA devices");
   ammsb_peer* p = new ammsb_peer();
   p->ctx = c;
   p->world = world;
@@ -129,6 +145,12 @@ extern "C" int ammsb_peer_attach_fd(ammsb_peer* p, uint32_t peer_rank, int fd) {
   AMMSB_REQUIRE(peer_rank < p->world && peer_rank != p->rank, "bad peer rank");
   if (vmm_import_fd(p->ctx->device, fd, p->bytes, &p->remote[peer_rank])) return 1;
   p->box[peer_rank] = reinterpret_cast<unsigned char*>(p->remote[peer_rank].ptr);
+  return 0;
+}
+
+extern "C" int ammsb_peer_check(ammsb_peer* p, uint32_t* timed_out_epoch) {
+  AMMSB_CHECK_CUDA(cudaSetDevice(p->ctx->device));
+  AMMSB_CHECK_CUDA(cudaMemcpy(timed_out_epoch, p->box[p->rank] + 4 * PEER_ERR_WORD, 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 

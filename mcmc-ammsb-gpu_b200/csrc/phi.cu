@@ -464,7 +464,8 @@ __global__ void __launch_bounds__((WARPS + NW) * 32)
       lsum = warp_sum(lsum);
       if (lane == 0) a.phi_sum[slot] = lsum;
     }
-    if (fast_noise && !a.disable_noise) rng_store(a.pool, (uint64_t)unit * 32 + lane, st);
+    // with producer warps (NW > 0) the state lives in, and is persisted by, the producer
+    if (NW == 0 && fast_noise && !a.disable_noise) rng_store(a.pool, (uint64_t)unit * 32 + lane, st);
   }
 }
 

@@ -16,10 +16,12 @@ extern "C" int ammsb_rng_create(ammsb_ctx* c, uint64_t n, uint64_t sx, uint64_t 
                                 ammsb_rng** out) {
   AMMSB_REQUIRE(n > 0, "empty RNG pool");
   AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ulonglong2* d_state = nullptr;  // before the handle exists: a failed allocation leaks nothing
+  AMMSB_CHECK_CUDA(cudaMalloc((void**)&d_state, sizeof(ulonglong2) * n));
   ammsb_rng* r = new ammsb_rng();
   r->ctx = c;
   r->n = n;
-  AMMSB_CHECK_CUDA(cudaMalloc((void**)&r->d_state, sizeof(ulonglong2) * n));
+  r->d_state = d_state;
   uint64_t blocks = (n + 255) / 256;
   if (blocks > (uint64_t)c->sm_count * 16) blocks = (uint64_t)c->sm_count * 16;
   k_rng_init<<<(unsigned)blocks, 256, 0, c->stream>>>(r->d_state, n, sx, sy);

@@ -236,6 +236,7 @@ bool Learner::Parse(std::istream* in) {
         (!trainingPerplexity_ || trainingPerplexity_->Parse(in)) && heldoutPerplexity_.Parse(in) &&
         ParseMessage(in, &props)))
     return false;
+  if (props.phase != 0 && props.phase != 1) return false;  // indexes samples_[]
   stepCount_ = props.stepCount;
   time_ = props.time;
   samplingTime_ = props.samplingTime;

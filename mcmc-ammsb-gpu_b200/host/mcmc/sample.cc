@@ -500,7 +500,12 @@ bool Sample::Parse(std::istream* in, bool pending) {
   allowed_ = drawn_;
   SampleSlot& slot = *ring[0];
   SampleStorage s;
-  if (!(ParseMessage(in, &s) && ::mcmc::Parse(in, &slot.dev_edges, &queue) &&
+  if (!ParseMessage(in, &s)) return false;
+  // the mini-batch must fit the buffers this Sample was built with (file content is not trusted)
+  if (s.edges.size() % sizeof(Edge) || s.nodes_vec.size() % sizeof(Vertex) ||
+      s.edges.size() > slot.dev_edges.GetSize() || s.nodes_vec.size() > slot.dev_nodes.GetSize())
+    return false;
+  if (!(::mcmc::Parse(in, &slot.dev_edges, &queue) &&
         ::mcmc::Parse(in, &slot.dev_nodes, &queue) && neighbor_sampler.Parse(in)))
     return false;
   slot.edges.resize(s.edges.size() / sizeof(Edge));

@@ -1,5 +1,7 @@
 #include "mcmc/serialize.h"
 
+#include <algorithm>
+
 #include "mcmc/partitioned-alloc.h"
 
 namespace mcmc {
@@ -93,9 +95,27 @@ bool ReadRecord(std::istream* in, std::string* payload) {
   uint64_t n = 0;
   in->read(reinterpret_cast<char*>(&n), sizeof n);
   if (!in->good()) return false;
-  payload->resize(n);
-  in->read(&(*payload)[0], n);
-  return in->good() || (in->eof() && static_cast<uint64_t>(in->gcount()) == n);
+  // the length prefix is file content: never allocate more than the stream can still deliver
+  const std::streampos cur = in->tellg();
+  if (cur != std::streampos(-1)) {
+    in->seekg(0, std::ios::end);
+    const std::streampos last = in->tellg();
+    in->seekg(cur);
+    if (last == std::streampos(-1) || static_cast<uint64_t>(last - cur) < n) return false;
+    payload->resize(n);
+    in->read(&(*payload)[0], n);
+    return static_cast<uint64_t>(in->gcount()) == n;
+  }
+  payload->clear();  // not seekable: grow with what actually arrives
+  const uint64_t kChunk = 64ull << 20;
+  while (payload->size() < n) {
+    const uint64_t want = std::min<uint64_t>(kChunk, n - payload->size());
+    const size_t at = payload->size();
+    payload->resize(at + want);
+    in->read(&(*payload)[at], want);
+    if (static_cast<uint64_t>(in->gcount()) != want) return false;
+  }
+  return true;
 }
 
 bool SerializeBytes(std::ostream* out, const void* data, size_t n) {
@@ -137,15 +157,16 @@ bool ReadRpmProperties(std::istream* in, uint32_t* rows, uint32_t* cols, uint32_
   std::string props;
   if (!ReadRecord(in, &props)) return false;
   wire::Reader r{props.data(), props.data() + props.size()};
-  uint32_t f, t;
+  uint32_t f, t, seen = 0;
   while (r.Next(&f, &t)) {
     if (t != 0) { r.Skip(t); continue; }
     const uint64_t v = r.Varint();
     if (f == 1) *rows = static_cast<uint32_t>(v);
     if (f == 2) *cols = static_cast<uint32_t>(v);
     if (f == 3) *rows_in_block = static_cast<uint32_t>(v);
+    if (f >= 1 && f <= 3) seen |= 1u << f;
   }
-  return r.ok;
+  return r.ok && seen == 0xeu;  // all three are `required` (protos.proto)
 }
 
 bool SerializeRpm(std::ostream* out, RowPartitionedMatrix<Float>* rpm) {
@@ -188,13 +209,13 @@ bool ReadCountAndDoubles(std::istream* in, uint32_t* count, double* d, int n) {
   std::string msg;
   if (!ReadRecord(in, &msg)) return false;
   wire::Reader r{msg.data(), msg.data() + msg.size()};
-  uint32_t f, t;
+  uint32_t f, t, seen = 0;
   while (r.Next(&f, &t)) {
-    if (f == 1 && t == 0) *count = static_cast<uint32_t>(r.Varint());
-    else if (t == 1 && f >= 2 && f < 2u + n) d[f - 2] = r.Double();
+    if (f == 1 && t == 0) { *count = static_cast<uint32_t>(r.Varint()); seen |= 2u; }
+    else if (t == 1 && f >= 2 && f < 2u + n) { d[f - 2] = r.Double(); seen |= 1u << f; }
     else r.Skip(t);
   }
-  return r.ok;
+  return r.ok && seen == ((1u << (2 + n)) - 2u);  // every field is `required` (protos.proto)
 }
 }  // namespace
 
@@ -241,16 +262,16 @@ bool ParseMessage(std::istream* in, SampleStorage* m) {
   std::string msg;
   if (!ReadRecord(in, &msg)) return false;
   wire::Reader r{msg.data(), msg.data() + msg.size()};
-  uint32_t f, t;
+  uint32_t f, t, seen = 0;
   while (r.Next(&f, &t)) {
     const char* d;
     size_t n;
-    if (f == 1 && t == 2 && r.Bytes(&d, &n)) m->edges.assign(d, n);
-    else if (f == 2 && t == 2 && r.Bytes(&d, &n)) m->nodes_vec.assign(d, n);
-    else if (f == 3 && t == 0) m->seed = static_cast<uint32_t>(r.Varint());
+    if (f == 1 && t == 2 && r.Bytes(&d, &n)) { m->edges.assign(d, n); seen |= 2u; }
+    else if (f == 2 && t == 2 && r.Bytes(&d, &n)) { m->nodes_vec.assign(d, n); seen |= 4u; }
+    else if (f == 3 && t == 0) { m->seed = static_cast<uint32_t>(r.Varint()); seen |= 8u; }
     else r.Skip(t);
   }
-  return r.ok;
+  return r.ok && seen == 0xeu;
 }
 
 bool SerializeMessage(std::ostream* out, const LearnerProperties& m) {
@@ -266,7 +287,7 @@ bool ParseMessage(std::istream* in, LearnerProperties* m) {
   std::string msg;
   if (!ReadRecord(in, &msg)) return false;
   wire::Reader r{msg.data(), msg.data() + msg.size()};
-  uint32_t f, t;
+  uint32_t f, t, seen = 0;
   while (r.Next(&f, &t)) {
     if (t == 0) {
       const uint64_t v = r.Varint();
@@ -274,13 +295,15 @@ bool ParseMessage(std::istream* in, LearnerProperties* m) {
       if (f == 2) m->time = v;
       if (f == 3) m->samplingTime = v;
       if (f == 4) m->phase = static_cast<int32_t>(v);
+      if (f >= 1 && f <= 4) seen |= 1u << f;
     } else if (t == 1 && f == 5) {
       m->weight = r.Double();
+      seen |= 1u << 5;
     } else {
       r.Skip(t);
     }
   }
-  return r.ok;
+  return r.ok && seen == 0x3eu;
 }
 
 }  // namespace mcmc

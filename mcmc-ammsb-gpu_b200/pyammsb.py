@@ -405,6 +405,13 @@ class Peer:
     def allreduce_f64(self, d_buf, count, ctx=None):
         _ck(lib().ammsb_peer_allreduce_f64((ctx or self.ctx).h, self.h, d_buf.ptr, count))
 
+    def check(self):
+        """raise if a wait inside an exchange kernel gave up (a peer died or never launched)"""
+        ep = C.c_uint32(0)
+        _ck(lib().ammsb_peer_check(self.h, C.byref(ep)))
+        if ep.value:
+            raise AmmsbError("rank %d: peer exchange number %d timed out" % (self.rank, ep.value))
+
     def free(self):
         if self.h is not None:
             lib().ammsb_peer_destroy(self.h)
