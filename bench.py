@@ -82,6 +82,39 @@ def workload_name(w, world):
              " (%d per GPU)" % w["m"] if world > 1 else "", w["n"]))
 
 
+def sharded_plan(args, w, world):
+    """layout decisions of a multi-GPU run -- a function of the arguments only, so that both
+    arms describe the same run"""
+    mode = args.store
+    if mode == "auto":  # replicate while a full copy (plus mini-batch buffers) is a small part of 180 GB
+        mode = "replicated" if 4.0 * w["N"] * w["K"] <= 48e9 else "partitioned"
+    gmode = args.graph
+    if gmode == "auto":
+        gmode = "device" if w["E"] > 100e6 else "host"
+    return mode, args.collectives, gmode
+
+
+def config_of(args, w, world):
+    """the `config` object of the JSON line: identical in the b200 and the reference arm"""
+    N, K, n, m = w["N"], w["K"], w["n"], w["m"] * world
+    cfg = {"workload": workload_name(w, world),
+           "l2": "inputs larger than L2: pi is %.2f GB and every non-link step gathers %.2f GB of rows"
+                 % (4.0 * N * K / 1e9, bytes_phi(m + 1, n, K) / 1e9),
+           "timing": "b200 arm: CUDA events on the launching stream, steps are whole iterations in stream order, "
+                     "neighbor sampling of the next mini-batch overlaps on a second stream (the Learner::Run "
+                     "schedule), max over ranks; reference arm: host wall clock, CPU only"}
+    if world > 1 or args.graph == "device":
+        mode, coll, gmode = sharded_plan(args, w, world)
+        cfg["graph"] = "built in HBM (csrc/graph.cu)" if gmode == "device" else "built on the host"
+        cfg["parallelism"] = (
+            ("pi/phi node-partitioned over %d GPUs (NVLink peer loads), " % world if mode == "partitioned" else
+             "pi/phi replicated on %d GPUs (fits: %.1f GB), mini-batch slots split over GPUs, updated rows written "
+             "to every copy by NVLink peer stores, " % (world, 4.0 * N * K / 1e9)) +
+            ("beta gradient and perplexity sums all-reduced in rank order and phases ordered by our own kernels "
+             "over NVLink peer memory" if coll == "peer" else "beta gradient and perplexity sums all-reduced (NCCL)"))
+    return cfg
+
+
 # --------------------------------------------------------------------- bytes --
 def bytes_phi(V, n, K):      # SURVEY.md section 8(d): B_phi = V[(n+2)4K + 68n + 8]
     return V * ((n + 2) * 4 * K + n * 68 + 8)
@@ -171,23 +204,46 @@ class ClockSampler:
 
 
 # -------------------------------------------------------- CPU reference legs --
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_reference(w, steps, warmup, seconds_budget, log=lambda *a: None):
     """The reference's CPU implementation of the path on the host cores: its own host sampler
     (sample.cc) + its kernel text (THREAD / EDGE_PER_THREAD variants -- the ones the reference
-    selects for CPU devices, learner.cc:105-114) run as OpenMP loops over work-items.
-    steps=None: run for about `seconds_budget` seconds (cpu_baseline leg)."""
+    selects for CPU devices, learner.cc:105-114) run as OpenMP loops over work-items, on the SAME
+    mini-batch size as the B200 arm.  The run is bounded in time, never in mini-batch size:
+    steps=None runs for about `seconds_budget` seconds (cpu_baseline leg); otherwise `steps`
+    iterations, or as many as fit `seconds_budget` (at least 2)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     import synth
-    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
-    if os.path.exists(ref_path):
-        orc, kind = pyoracle.Oracle(path=ref_path), "reference"
+    fast = os.path.join(ROOT, "oracle", "_ref", "libref_oracle_fast.so")
+    chk = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
+    flags = ""
+    try:
+        flags = [ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")][0]
+    except Exception:
+        pass
+    if os.path.exists(fast) and " avx2" in flags and " fma" in flags:
+        orc, kind = pyoracle.Oracle(path=fast), "reference"
+        build = "timing build of the reference sources: g++ -O3 -ffast-math -mavx2 -mfma -fopenmp"
+    elif os.path.exists(chk):
+        orc, kind = pyoracle.Oracle(path=chk), "reference"
+        build = "checker build of the reference sources: g++ -O2 -ffp-contract=off -fno-fast-math -fopenmp"
     else:
         orc, kind = pyoracle.Oracle(omp=True), "port"
+        build = "oracle port: gcc -O2 -ffp-contract=off -fopenmp"
     L = orc.L
     L.orc_num_threads.restype = C.c_int
+    # launchers (torchrun) export OMP_NUM_THREADS=1: the baseline gets every core of the box
+    L.orc_set_num_threads.argtypes = [C.c_int]
+    L.orc_set_num_threads(host_cores())
     cores = int(L.orc_num_threads())
-    N, E, K, n = w["N"], w["E"], w["K"], w["n"]
+    N, E, K, n, m = w["N"], w["E"], w["K"], w["n"], w["m"]
     t0 = time.time()
     keys = synth.make_edges(N, E, 1)
     training_len = int(np.ceil((1 - w["heldout_ratio"] / 2) * E))  # data.cc:86-88
@@ -202,43 +258,40 @@ def cpu_reference(w, steps, warmup, seconds_budget, log=lambda *a: None):
     theta = rng.standard_gamma(1.0, size=2 * K).astype(np.float32) + np.float32(1e-3)
     beta = orc.theta_to_beta(theta)
     p = orc.make_params(N, E, K, n)
-    log("cpu reference (%s, %d threads): setup %.1fs" % (kind, cores, time.time() - t0))
+    log("cpu reference (%s, %d threads, %s): setup %.1fs" % (kind, cores, build, time.time() - t0))
 
-    # bounded sample: the same iteration at a smaller mini-batch, sized from a calibration step
-    def make_sampler(m_s):
-        if kind == "reference":
-            L.ref_sampler_create.restype = C.c_void_p
-            L.ref_sampler_create.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
-                                             C.c_uint64, C.c_uint64]
-            L.ref_sample.restype = C.c_float
-            L.ref_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p]
-            L.ref_sampler_max_fan_out.restype = C.c_uint64
-            L.ref_sampler_max_fan_out.argtypes = [C.c_void_p]
-            h = C.c_void_p(L.ref_sampler_create(N, E, training.ctypes.data, len(training),
-                                                heldout_links.ctypes.data, len(heldout_links), m_s))
-            cap = max(2 * m_s, 1 + int(L.ref_sampler_max_fan_out(h)))
-            eb, nb = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
-            seed = C.c_uint(12345)
+    if kind == "reference":
+        L.ref_sampler_create.restype = C.c_void_p
+        L.ref_sampler_create.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                         C.c_uint64, C.c_uint64]
+        L.ref_sample.restype = C.c_float
+        L.ref_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
+        L.ref_sampler_max_fan_out.restype = C.c_uint64
+        L.ref_sampler_max_fan_out.argtypes = [C.c_void_p]
+        h = C.c_void_p(L.ref_sampler_create(N, E, training.ctypes.data, len(training),
+                                            heldout_links.ctypes.data, len(heldout_links), m))
+        cap = max(2 * m, 1 + int(L.ref_sampler_max_fan_out(h)))
+        eb, nb = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        seed = C.c_uint(12345)
 
-            def draw():
-                ne, nn = C.c_uint64(0), C.c_uint64(0)
-                wgt = L.ref_sample(h, 0, C.byref(seed), eb.ctypes.data, C.byref(ne), nb.ctypes.data, C.byref(nn))
-                return eb[:ne.value].copy(), nb[:nn.value].copy(), float(wgt)
-            return draw
+        def draw():
+            ne, nn = C.c_uint64(0), C.c_uint64(0)
+            wgt = L.ref_sample(h, 0, C.byref(seed), eb.ctypes.data, C.byref(ne), nb.ctypes.data, C.byref(nn))
+            return eb[:ne.value].copy(), nb[:nn.value].copy(), float(wgt)
+    else:
         import pymcmc  # oracle port: the host sampler is the repo's own (golden-checked) one
-        cfg = pymcmc.Config(K=K, mini_batch_size=m_s, num_node_sample=n, heldout_ratio=w["heldout_ratio"])
+        cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=w["heldout_ratio"])
         cfg.set_graph(N, keys)
         seed = C.c_uint(12345)
 
-        def draw_port():
+        def draw():
             wgt, edges, nodes = cfg.sample("Node", seed)
             return edges, nodes, wgt
-        return draw_port
 
     state = dict(step=0, pools=None)
 
-    def iteration(draw, m_s):
+    def iteration():
         edges, nodes, weight = draw()
         V = len(nodes)
         if state["pools"] is None or state["pools"][0] < V:
@@ -253,54 +306,41 @@ def cpu_reference(w, steps, warmup, seconds_budget, log=lambda *a: None):
                         state.setdefault("bpool", orc.rng_pool(K, 44, 45)))
         return len(edges)
 
-    # calibration: non-link mini-batches dominate, one of 256 edges tells the per-edge cost
-    m_cal = min(256, w["m"])
-    draw = make_sampler(m_cal)
-    t0 = time.perf_counter()
-    e_cal = 0
-    for _ in range(4):
-        e_cal += iteration(draw, m_cal)
-    per_edge = (time.perf_counter() - t0) / max(e_cal, 1)
-    if steps is None:
-        total_steps, warm = None, 1
-        target_step_s = min(2.0, seconds_budget / 8)
-    else:
-        total_steps, warm = steps, warmup
-        target_step_s = min(2.0, 150.0 / max(steps + warmup, 1))
-    m_s = int(min(w["m"], max(64, 2 * target_step_s / per_edge)))  # ~half of the iterations are link (tiny)
-    draw = make_sampler(m_s)
-    for _ in range(warm):
-        iteration(draw, m_s)
+    # warm-up: the CPU has no clocks to ramp; at most 2 untimed iterations (pools, page faults)
+    for _ in range(2 if steps is None else min(max(warmup, 1), 2)):
+        iteration()
     edges_done, iters = 0, 0
     t0 = time.perf_counter()
     while True:
-        edges_done += iteration(draw, m_s)
+        edges_done += iteration()
         iters += 1
-        if total_steps is not None and iters >= total_steps:
+        if steps is not None and iters >= steps:
             break
-        if total_steps is None and time.perf_counter() - t0 >= seconds_budget:
+        if iters >= 2 and time.perf_counter() - t0 >= seconds_budget:
             break
     dt = time.perf_counter() - t0
     sample = ("%d full iterations (host sampler + neighbor sampling + update_phi + update_pi + update_beta, "
-              "THREAD-mode kernels as the reference selects for CPU devices) of the same graph/K/n at "
-              "mini_batch=%d edges (strategy Node), %.1f s of CPU work; per-edge throughput" % (iters, m_s, dt))
+              "THREAD-mode kernels as the reference selects for CPU devices) of the same graph/K/n at the same "
+              "mini_batch=%d edges (strategy Node), %.1f s of CPU work on %d threads; %s"
+              % (iters, m, dt, cores, build))
     return dict(value=edges_done / dt, unit=UNIT, cores=cores, kind=kind, sample=sample,
-                iterations=iters, seconds=dt, edges=edges_done, m_sample=m_s)
+                iterations=iters, seconds=dt, edges=edges_done, build=build)
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # same workload as the B200 arm at this N: the global mini-batch is N x m edges
-    r = cpu_reference(dict(w, m=w["m"] * args.gpus), args.steps, args.warmup, None,
+    # same workload as the B200 arm at this N: the global mini-batch is N x m edges.  The run is
+    # bounded to ~150 s by timing fewer iterations, never by a smaller mini-batch.
+    r = cpu_reference(dict(w, m=w["m"] * args.gpus), args.steps, args.warmup, 150.0,
                       log=lambda *a: print(*a, file=sys.stderr))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(r["iterations"], 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(w, args.gpus), "timing": "host wall clock, CPU only"},
-        "iterations_per_s": r["iterations"] / r["seconds"],
+        "config": config_of(args, w, args.gpus),
+        "iterations_per_s": r["iterations"] / r["seconds"], "iterations_timed": r["iterations"],
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -333,8 +373,8 @@ def run_b200(args, w):
     log = (lambda *a: print(*a, file=sys.stderr, flush=True)) if rank == 0 else (lambda *a: None)
     if world > 1 or args.graph == "device":  # the sharded driver (also on one GPU for device-built graphs)
         import dist as D
-        return D.bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_name,
-                               ClockSampler, cpu_reference)
+        return D.bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config_of(args, w, world),
+                               sharded_plan(args, w, world), ClockSampler)
 
     N, E, K, n, m = w["N"], w["E"], w["K"], w["n"], w["m"]
     t0 = time.time()
@@ -434,8 +474,16 @@ def run_b200(args, w):
     dev_ms = e_start.elapsed_time(e_stop)
     timed = batches[args.warmup:]
     edges_timed = int(sum(len(b[1]) for b in timed))
-    phi_ms = float(sum(a.elapsed_time(b) for a, b in evs))
-    phi_bytes = float(sum(bytes_phi(len(b[2]), n, K) for b in timed))
+    # update_phi launches of the timed region by kernel: non-link mini-batches (V = m + 1 slots)
+    # run k_update_phi_fast / _team (bandwidth-bound), link ones (V = 1 + deg(u) <= #SMs slots)
+    # k_update_phi_split (a latency chain)
+    sms = ctx.sm_count()
+    per_launch = [(len(b[2]), a.elapsed_time(e)) for b, (a, e) in zip(timed, evs)]
+    big_l = [(V, t) for V, t in per_launch if V > sms]
+    small_l = [(V, t) for V, t in per_launch if V <= sms]
+    phi_ms = float(sum(t for _, t in per_launch))
+    phi_big_ms = float(sum(t for _, t in big_l))
+    phi_big_bytes = float(sum(bytes_phi(V, n, K) for V, _ in big_l))
     value = edges_timed / (dev_ms * 1e-3)
 
     # per-stage table on the canonical non-link mini-batch (V = m + 1), each stage timed alone
@@ -484,19 +532,31 @@ def run_b200(args, w):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    # DRAM traffic is an ncu measurement (profiles/): quoted only for the launch shape it was
+    # captured on, scaled by nothing
     traffic = None
-    try:  # DRAM bytes per launch = ncu's (dram read + write) / algorithmic ratio of the committed capture
-        ratio = json.load(open(os.path.join(ROOT, "profiles", "update_phi_traffic.json")))["dram_over_algorithmic"]
-        traffic = round(ratio * phi_bytes / args.steps)
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "update_phi_traffic.json")))["canonical_launch"]
+        if (cap["V"], cap["n"], cap["K"]) == (Vb, n, K):
+            traffic = int(cap["dram_bytes_read"] + cap["dram_bytes_write"])
     except Exception:
         pass
-    achieved = phi_bytes / (phi_ms * 1e-3) / 1e9
-    # `achieved` averages every update_phi launch of the timed region: the non-link mini-batches
-    # (k_update_phi_fast, V = m + 1 slots, bandwidth-bound) and the link ones (k_update_phi_split,
-    # V = 1 + deg(u) slots, a latency chain); canonical_launch is the non-link launch alone
-    roofline = {"bound": "hbm", "kernel": "k_update_phi_fast", "achieved": round(achieved, 1), "peak": peak,
+    kernel = "k_update_phi_fast" if K <= 1024 else "k_update_phi_team"
+    achieved = phi_big_bytes / (phi_big_ms * 1e-3) / 1e9 if big_l else 0.0
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "launches": args.steps, "algorithmic_bytes_per_launch": round(phi_bytes / args.steps), "share_of_step": round(phi_ms / dev_ms, 4),
+                "launches": len(big_l),
+                "algorithmic_bytes_per_launch": round(phi_big_bytes / max(len(big_l), 1)),
+                "avg_launch_ms": round(phi_big_ms / max(len(big_l), 1), 4),
+                "share_of_step": round(phi_big_ms / dev_ms, 4),
+                "what": "non-link mini-batches only (V = m + 1 slots), CUDA events around every launch of the "
+                        "timed region; traffic = ncu dram read + write of one launch of this shape "
+                        "(profiles/update_phi_traffic.json), null for any other shape",
+                "link_launches": {"kernel": "k_update_phi_split", "launches": len(small_l),
+                                  "avg_launch_ms": round(sum(t for _, t in small_l) / max(len(small_l), 1), 4),
+                                  "avg_slots": round(sum(V for V, _ in small_l) / max(len(small_l), 1), 1),
+                                  "bound": "latency (a handful of slots)",
+                                  "share_of_step": round(sum(t for _, t in small_l) / dev_ms, 4)},
                 "canonical_launch": dict(stages["update_phi"], V=Vb, frac=round(stages["update_phi"]["GBps"] / peak, 4))}
     for b in (d_edges_all, d_nodes_all, d_hedges, d_ppx, pws, d_nb, d_nbs[1], d_vec, d_sum, d_ts, d_g, ws, d_theta, d_beta):
         b.free()
@@ -542,12 +602,7 @@ def run_b200(args, w):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(w, 1),
-                   "l2": "inputs larger than L2: pi is %.2f GB and every non-link step gathers %.2f GB of rows"
-                         % (4.0 * N * K / 1e9, bytes_phi(Vb, n, K) / 1e9),
-                   "timing": "CUDA events on the launching stream; steps are whole iterations in stream order; "
-                             "neighbor sampling of the next mini-batch overlaps on a second stream (the "
-                             "Learner::Run schedule)"},
+        "config": config_of(args, w, 1),
         "iterations_per_s": args.steps / (dev_ms * 1e-3),
         "perplexity_eval_s": stages["perplexity"]["ms"] * 1e-3,
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

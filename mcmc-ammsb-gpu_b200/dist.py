@@ -479,8 +479,7 @@ class ShardedLearner:
 
 
 # ------------------------------------------------------------------ bench ----
-def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_name, ClockSampler,
-                  cpu_reference):
+def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, plan, ClockSampler):
     """bench.py --gpus N (N > 1): weak scaling, mini-batch = N x m edges on the same graph."""
     import torch
     import torch.distributed as dist
@@ -494,13 +493,7 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
     N, E, K, n = w["N"], w["E"], w["K"], w["n"]
     m = w["m"] * world
     t0 = time.time()
-    mode = getattr(args, "store", "auto")
-    if mode == "auto":  # replicate while a full copy (plus mini-batch buffers) is a small part of 180 GB
-        mode = "replicated" if 4.0 * N * K <= 48e9 else "partitioned"
-    coll = getattr(args, "collectives", "peer")
-    gmode = getattr(args, "graph", "auto")
-    if gmode == "auto":
-        gmode = "device" if E > 100e6 else "host"
+    mode, coll, gmode = plan  # bench.sharded_plan: a function of the arguments only
     graph = cfg = None
     if gmode == "device":
         # every rank builds the same graph, sets, held-out pairs and adjacency in its own HBM
@@ -666,19 +659,7 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, workload_
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(w, world),
-                       "graph": "built in HBM (csrc/graph.cu)" if graph is not None else "built on the host",
-                       "parallelism": ("pi/phi node-partitioned over %d GPUs (NVLink peer loads), " % world
-                                       if mode == "partitioned" else
-                                       "pi/phi replicated on %d GPUs (fits: %.1f GB), mini-batch slots split over "
-                                       "GPUs, updated rows written to every copy by NVLink peer stores, "
-                                       % (world, 4.0 * N * K / 1e9)) +
-                                      ("beta gradient and perplexity sums all-reduced in rank order and phases ordered "
-                                       "by our own kernels over NVLink peer memory" if coll == "peer" else
-                                       "beta gradient and perplexity sums all-reduced (NCCL)"),
-                       "l2": "inputs larger than L2 (pi %.2f GB, %.2f GB of rows gathered per non-link step)"
-                             % (4.0 * N * K / 1e9, (m + 1) * (n + 2) * 4 * K / 1e9),
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "config": config,
             "iterations_per_s": args.steps / (dev_ms * 1e-3), "perplexity_eval_s": ppx_s, "heldout_perplexity": ppx,
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
         }

@@ -34,6 +34,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1: the timing legs set the count explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* config.cc:57-64: float -> "%e" text -> float literal */
 float orc_round_param(float f) {
   char buf[64];

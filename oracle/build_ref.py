@@ -82,20 +82,30 @@ def main():
     emit("ppx_thread.inc", ppx[0])
     emit("ppx_wg.inc", ppx[1])
 
-    common = ["-O2", "-fPIC", "-w", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"]
-    objs = []
-    for f in ("cuckoo", "data", "sample", "config", "types", "gen-util", "random", "algorithm/sum",
-              "algorithm/normalize"):
-        o = os.path.join(OUT, "host_%s.o" % f.replace("/", "_"))
-        subprocess.check_call([CXX, "-std=c++11"] + common + ["-I", os.path.join(HERE, "stubs"), "-I", REF,
-                               "-c", os.path.join(REF, "mcmc", f + ".cc"), "-o", o])
+    # two builds of the same sources:
+    #   libref_oracle.so       the CHECKER: IEEE arithmetic, no contraction (parity tests)
+    #   libref_oracle_fast.so  the TIMING build for bench.py's CPU legs: -O3 with fast-math, as the
+    #                          reference asks of its own compiler (types.cc:528,532:
+    #                          -cl-fast-relaxed-math / -use_fast_math), AVX2 + FMA (not
+    #                          -march=native: the library is built here and runs on the GPU box's
+    #                          host, whose CPU model is not known at build time)
+    builds = (("libref_oracle.so", "chk", ["-O2", "-ffp-contract=off", "-fno-fast-math"]),
+              ("libref_oracle_fast.so", "fast", ["-O3", "-ffast-math", "-mavx2", "-mfma"]))
+    for lib, tag, opt in builds:
+        common = opt + ["-fPIC", "-w", "-fopenmp"]
+        objs = []
+        for f in ("cuckoo", "data", "sample", "config", "types", "gen-util", "random", "algorithm/sum",
+                  "algorithm/normalize"):
+            o = os.path.join(OUT, "%s_host_%s.o" % (tag, f.replace("/", "_")))
+            subprocess.check_call([CXX, "-std=c++11"] + common + ["-I", os.path.join(HERE, "stubs"), "-I", REF,
+                                   "-c", os.path.join(REF, "mcmc", f + ".cc"), "-o", o])
+            objs.append(o)
+        o = os.path.join(OUT, "%s_ref_api.o" % tag)
+        subprocess.check_call([CXX, "-std=gnu++17"] + common + ["-I", os.path.join(HERE, "stubs"), "-I", REF,
+                               "-I", HERE, "-I", GEN, "-c", os.path.join(HERE, "ref_api.cc"), "-o", o])
         objs.append(o)
-    o = os.path.join(OUT, "ref_api.o")
-    subprocess.check_call([CXX, "-std=gnu++17"] + common + ["-I", os.path.join(HERE, "stubs"), "-I", REF, "-I", HERE,
-                           "-I", GEN, "-c", os.path.join(HERE, "ref_api.cc"), "-o", o])
-    objs.append(o)
-    subprocess.check_call([CXX, "-shared", "-fopenmp", "-o", os.path.join(OUT, "libref_oracle.so")] + objs + ["-lm"])
-    print("built", os.path.join(OUT, "libref_oracle.so"))
+        subprocess.check_call([CXX, "-shared", "-fopenmp", "-o", os.path.join(OUT, lib)] + objs + ["-lm"])
+        print("built", os.path.join(OUT, lib))
     return 0
 
 

@@ -228,6 +228,7 @@ DEFINE_HANDLES(ref_wg)
 extern "C" {
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 // MakeCompileFlags / float_to_string (config.cc:57-83) from the reference's own object
 float orc_round_param(float f) {
