@@ -296,6 +296,60 @@ int ammsb_peer_allreduce_f64(ammsb_ctx* ctx, ammsb_peer* peer, double* d_inout, 
  * wait, 0 if there was none.  Synchronous. */
 int ammsb_peer_check(ammsb_peer* peer, uint32_t* timed_out_epoch);
 
+/* ---- column-sharded pi over the GPUs of one box (csrc/cols.cu): the multi-GPU successor of
+ *      RowPartitionedMatrix (partitioned-alloc.h:14-141) in which partial SUMS cross NVLink, not pi
+ *      rows.  GPU g of `world` (2, 4 or 8) holds, for EVERY row, the columns of the reference
+ *      work-items l = g (mod world) of the default update_phi launch (work-item l owns
+ *      k = l, l+32, ...; phi.cc:214-302) as a local matrix [N][K/world]; phi[N] (row sums) and the
+ *      held-out running means are held identically by every rank; theta/beta [2K] live in a
+ *      mailbox that the peers map, every rank stepping the columns it owns and publishing them.
+ *      The K-wide sums of update_phi / update_pi / update_beta / perplexity are formed as
+ *      per-GPU partials and completed in the reference's WG_SUM tree order (sum.cc:20-42) from
+ *      self-validating 4-byte mailbox words written by peer stores inside the kernels: results
+ *      are bit-identical on every rank, independent of `world`, and update_phi/update_pi are
+ *      bit-identical to ammsb_update_phi/ammsb_update_pi on one GPU.
+ *      One process per GPU exports its mailbox as a file descriptor (export_fd / attach_fd);
+ *      several ranks of one process attach with attach_local.  The step functions take the
+ *      `nv` ranks that live on ctx's device -- 1 in production; world ranks on one GPU is the
+ *      emulation the single-GPU tests use (one cooperative launch over all ranks' data).
+ *      K in {128, 256, 512, 1024}; reproduces the WG launch with phi_wg_size 32. ---- */
+typedef struct ammsb_cols ammsb_cols;
+int ammsb_cols_create(ammsb_ctx* ctx, uint64_t N, uint32_t K, uint32_t world, uint32_t rank,
+                      uint32_t num_neighbors, uint32_t max_nodes, uint32_t max_edges, uint64_t max_pairs,
+                      ammsb_cols** out);
+int ammsb_cols_destroy(ammsb_cols* cols);
+int ammsb_cols_mailbox_bytes(const ammsb_cols* cols, size_t* bytes);
+int ammsb_cols_export_fd(ammsb_cols* cols, int* fd);
+int ammsb_cols_attach_fd(ammsb_cols* cols, uint32_t peer_rank, int fd);
+int ammsb_cols_attach_local(ammsb_cols* cols, uint32_t peer_rank, ammsb_cols* peer);
+int ammsb_cols_init_pi(ammsb_cols* cols, float eta0, float eta1); /* random.cc:131-167 */
+/* host access in the reference's layout: full rows [nrows][K]; write scatters the columns this
+ * rank owns, read fills them in and leaves the other columns of h_rows untouched */
+int ammsb_cols_write_pi(ammsb_cols* cols, uint64_t row0, uint64_t nrows, const float* h_rows);
+int ammsb_cols_read_pi(ammsb_cols* cols, uint64_t row0, uint64_t nrows, float* h_rows);
+int ammsb_cols_write_phi(ammsb_cols* cols, uint64_t row0, uint64_t nrows, const float* h_src);
+int ammsb_cols_read_phi(ammsb_cols* cols, uint64_t row0, uint64_t nrows, float* h_dst);
+int ammsb_cols_write_theta(ammsb_cols* cols, const float* h_theta /* [2K] */, const float* h_beta /* [2K] */);
+int ammsb_cols_read_theta(ammsb_cols* cols, float* h_theta, float* h_beta); /* either may be NULL */
+int ammsb_cols_beta_ptr(ammsb_cols* cols, float** d_theta, float** d_beta);
+int ammsb_cols_read_phi_vec(ammsb_cols* cols, uint32_t V, float* h_rows /* [V][K] */);
+int ammsb_cols_check(ammsb_cols* cols, uint32_t* timed_out); /* 1: an exchange wait gave up */
+/* PhiUpdater (phi.cc:728-763), BetaUpdater (beta.cc:334-384), PerplexityCalculator
+ * (perplexity.cc:251-274) on the column shards; pools[i] is rank i's RNG pool of the operator
+ * (same sizes and seeds as on one GPU: a rank only touches the states of its own lanes/columns).
+ * step_count / call_count also select the mailbox half and must agree on every rank. */
+int ammsb_cols_update_phi(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
+                          const ammsb_phi_opts* opts, ammsb_set* train, const uint32_t* d_nodes,
+                          const uint32_t* d_neighbors, uint32_t V, uint32_t step_count, ammsb_rng* const* pools);
+int ammsb_cols_update_pi(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv, const uint32_t* d_nodes,
+                         uint32_t V, uint32_t step_count);
+int ammsb_cols_update_beta(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
+                           ammsb_set* train, const uint64_t* d_edges, uint32_t E_mb, float scale,
+                           uint32_t step_count, ammsb_rng* const* pools);
+int ammsb_cols_perplexity(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
+                          ammsb_set* heldout, const uint64_t* d_edges, uint32_t H, uint32_t call_count,
+                          double* h_sums /* [nv][4] or NULL */, double* h_avg /* [nv] or NULL */);
+
 /* ---- work-group helpers the reference tests directly (wg-sum-test.cc,
  *      wg-normalize-test.cc): rows of `len` floats, one warp per row, reference
  *      association for wg = 32 (sum.cc:31-42, normalize.cc:13-32). ---- */

@@ -1,0 +1,1371 @@
+// cols.cu -- the COLUMN-SHARDED ("lane-sharded") multi-GPU layout of pi and the kernels that
+// work on it.  The reference is single-device (its only scale mechanism is RowPartitionedMatrix,
+// partitioned-alloc.h:14-141); this file is the multi-GPU successor of phi.cc / beta.cc /
+// perplexity.cc in which WORK PARTIALS cross NVLink instead of pi rows.
+//
+// Layout.  The reference's default update_phi launch gives a mini-batch slot to a work-group of 32
+// work-items; item l owns the columns k = l, l+32, ... and one RNG state (phi.cc:214-302,
+// 740-747).  With G GPUs (2, 4 or 8) GPU g owns the reference lanes l = g (mod G) of EVERY row:
+// LPG = 32/G lanes, K/G columns, held as a local matrix [N][K/G].  Every row access of every
+// kernel is therefore local HBM -- no pi row ever crosses NVLink -- and the Langevin noise of a
+// column is drawn on the GPU that owns it, from the same state as in the reference launch.
+//
+// What crosses NVLink are the K-wide sums: per (slot, neighbor) the partial sum_k probs_k, per slot
+// the partial row sum of the new phi, per mini-batch edge two partial sums, per held-out pair two.
+// The reference's WG_SUM (sum.cc:20-42) adds the 32 lane partials in a tree of strides 16, 8, 4,
+// 2, 1.  Lanes l and l' with l = l' (mod G) are combined by the strides >= G, all inside one GPU
+// (a sub-warp shuffle tree); the remaining strides G/2 .. 1 combine the G per-GPU partials.  Every
+// GPU receives every other GPU's partial and adds them in that same tree order, so the full sum is
+// bit-identical on every GPU AND bit-identical to what the one-warp-per-slot kernel of phi.cu
+// computes on one GPU: the result does not depend on G.
+//
+// The exchange is fused into the kernels (no collective call, no barrier kernel): a partial is a
+// single 4-byte store into a mailbox slot of the peer (mapped peer memory, NVLink), and a mailbox
+// word is self-validating -- it holds the sentinel 0xffffffff (a NaN pattern no partial can have)
+// until the value arrives, and the consumer re-arms it after reading.  No flags, no fences, no
+// ordering requirement between words.  Mailbox halves alternate with the step parity, so a word is
+// re-armed two steps before it is written again.
+//
+// k_cols_phi keeps the pi row pieces of a (slot, neighbor) in shared memory across the exchange:
+// a warp runs G slots at once (LPG lanes each, the same per-lane arithmetic as phi.cu's lane),
+// stages one neighbor piece per slot and trip with TMA bulk copies into a ring of R stages, forms
+// the partial sums of stage t (phase A), and D trips later -- when the peers' partials have crossed
+// the switch -- finishes stage t - D (phase B: gradient accumulation) from the same staged piece.
+// HBM traffic is the algorithmic traffic; NVLink carries 4 bytes per (slot, neighbor, peer).
+//
+// Emulation: a launch may compute several ranks ("virtual ranks") of one GPU -- one cooperative
+// launch over all ranks' shards and mailboxes -- which is how the one-GPU tests pin the G-rank
+// protocol, G-invariance and parity with phi.cu bit for bit.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+#define COLS_SENTINEL 0xffffffffu
+#define COLS_SPIN_LIMIT (1u << 22)
+#define COLS_HDR_BYTES 256u
+
+struct ColsRankView {
+  float* pi;        // [N][KG]   this rank's columns of every row
+  float* phi;       // [N]       row sums (every rank holds the same values)
+  float* phi_vec;   // [Vcap][KG] update_phi output, local column order
+  float* ppx;       // [Hcap]    running mean per held-out pair (every rank the same values)
+  unsigned char* box[AMMSB_MAX_SHARDS];  // every rank's mailbox as mapped on this rank's device
+  ulonglong2* pool;  // RNG pool of the current operator (phi: V*32 states, beta: K states)
+  float* ws;         // beta partial sums [ctas][2][KG]
+  double* ws_d;      // perplexity partial sums [ctas][4]
+  uint32_t rank;
+};
+
+// offsets (bytes) inside a mailbox; every region is [2 halves][G sources][cap words]
+struct ColsBoxLayout {
+  size_t theta, beta;          // [2K] floats each (interleaved like the reference's buffers)
+  size_t S, R, B, P;           // region bases
+  size_t S_src, R_src, B_src, P_src;   // bytes per source
+  size_t bytes;
+};
+
+struct ammsb_cols {
+  ammsb_ctx* ctx = nullptr;
+  uint64_t N = 0;
+  uint32_t K = 0, G = 1, rank = 0, n = 0;
+  uint32_t Vcap = 0, Ecap = 0;
+  uint64_t Hcap = 0;
+  uint32_t KG = 0;
+  float *d_pi = nullptr, *d_phi = nullptr, *d_phi_vec = nullptr, *d_ppx = nullptr, *d_ws = nullptr;
+  double* d_ws_d = nullptr;
+  ColsBoxLayout lay;
+  VmmAlloc local, remote[AMMSB_MAX_SHARDS];
+  unsigned char* box[AMMSB_MAX_SHARDS] = {nullptr};
+  uint32_t ws_ctas = 0;
+  ColsRankView view(ulonglong2* pool) const {
+    ColsRankView v;
+    v.pi = d_pi; v.phi = d_phi; v.phi_vec = d_phi_vec; v.ppx = d_ppx;
+    for (int i = 0; i < AMMSB_MAX_SHARDS; ++i) v.box[i] = box[i];
+    v.pool = pool; v.ws = d_ws; v.ws_d = d_ws_d; v.rank = rank;
+    return v;
+  }
+};
+
+// ---- geometry shared by host and device ----
+// group-pass id of a slot: the warp sub-group that owns unit u = slot % units handles its slots
+// u, u + units, ... (passes); G consecutive units form a group.
+__host__ __device__ __forceinline__ uint32_t cols_groups(uint32_t V, uint32_t units, uint32_t G) {
+  const uint32_t active = units < V ? units : V;
+  return (active + G - 1) / G;
+}
+__host__ __device__ __forceinline__ uint32_t cols_passes(uint32_t V, uint32_t units) {
+  return units ? (V + units - 1) / units : 0;
+}
+static uint32_t cols_units(uint32_t V) { return V < 65535u ? V : 65535u; }  // phi.cc:740-747, WG modes
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static ColsBoxLayout cols_layout(uint32_t K, uint32_t G, uint32_t n, uint32_t Vcap, uint32_t Ecap, uint64_t Hcap) {
+  ColsBoxLayout l;
+  size_t off = COLS_HDR_BYTES;
+  l.theta = off; off += align_up(sizeof(float) * 2 * K, 256);
+  l.beta = off; off += align_up(sizeof(float) * 2 * K, 256);
+  const uint32_t units = cols_units(Vcap);
+  const size_t gp = (size_t)cols_groups(Vcap, units, G) * cols_passes(Vcap, units);
+  l.S_src = align_up(gp * n * G * 4, 256);
+  l.R_src = align_up(gp * G * 4, 256);
+  l.B_src = align_up(((size_t)Ecap + G) * 2 * 4, 256);
+  l.P_src = align_up((Hcap + G) * 2 * 4, 256);
+  l.S = off; off += 2 * (size_t)G * l.S_src;
+  l.R = off; off += 2 * (size_t)G * l.R_src;
+  l.B = off; off += 2 * (size_t)G * l.B_src;
+  l.P = off; off += 2 * (size_t)G * l.P_src;
+  l.bytes = off;
+  return l;
+}
+
+// local float index of global column k on its owner (see the header comment):
+//   l = k % 32, i = k / 32, rank = l % G, li = l / G, c = ((i / 4) * LPG + li) * 4 + i % 4
+__host__ __device__ __forceinline__ uint32_t cols_local_index(uint32_t k, uint32_t G) {
+  const uint32_t l = k & 31, i = k >> 5, li = l / G, LPG = 32 / G;
+  return ((i >> 2) * LPG + li) * 4 + (i & 3);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ld_mbox(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_mbox(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t partial_bits(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return b == COLS_SENTINEL ? 0x7fc00000u : b;  // a NaN stays a NaN, never the sentinel
+}
+// wait for a mailbox word, re-arm it; *err is set when the wait gives up
+__device__ __forceinline__ float poll_mbox(uint32_t* p, uint32_t* err) {
+  uint32_t v = ld_mbox(p), spins = 0;
+  while (v == COLS_SENTINEL) {
+    if (++spins > COLS_SPIN_LIMIT) {
+      atomicExch(err, 1u);
+      break;
+    }
+    v = ld_mbox(p);
+  }
+  st_mbox(p, COLS_SENTINEL);
+  return __uint_as_float(v);
+}
+
+// Combine the G per-rank partials in the reference's tree order (strides G/2 .. 1 of WG_SUM).
+// On entry lane `li` of every LPG-lane sub-group holds, for G > LPG, the partials of ranks li
+// and li + LPG (v0, v1); for G <= LPG the lanes li < G hold the partial of rank li in v0.  On exit
+// every lane of the sub-group holds the full sum.
+template <int G>
+__device__ __forceinline__ float cols_rank_tree(float v0, float v1, uint32_t lane) {
+  constexpr int LPG = 32 / G;
+  float v;
+  if (G > LPG) {
+    v = v0 + v1;  // stride LPG = G/2 (G = 8)
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  } else {
+    const uint32_t li = lane & (LPG - 1);
+    v = __shfl_sync(FULL_MASK, v0, (lane & ~(uint32_t)(LPG - 1)) | (li & (G - 1)));
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  }
+  return v;
+}
+
+struct ColsPhiArgs {
+  ColsRankView r[AMMSB_MAX_SHARDS];
+  SetView set;
+  ColsBoxLayout lay;
+  const uint32_t* nodes;
+  const uint32_t* neighbors;
+  uint32_t nv, ctas_per_rank;
+  uint32_t V, n, units;
+  uint32_t R, D, MB;  // ring depth, A -> B distance (trips), metadata buffers
+  uint32_t parity, disable_noise, loopback;
+  float eps_t, alpha, epsilon, Nn;
+};
+
+// bytes of shared memory per warp / per CTA (host and device agree through these)
+template <int KPL, int G>
+struct ColsPhiSmem {
+  static constexpr int LPG = 32 / G;
+  static constexpr int KG = KPL * LPG;
+  static constexpr int PIECE = KG * 4;
+  static constexpr int PSTRIDE = PIECE + ((LPG == 4 && (PIECE % 128) != 64) ? 64 : 0);
+  static constexpr int STAGE = G * PSTRIDE;
+  static constexpr int OWN = G * PIECE;
+  static constexpr int META = G * 32 * 4 + 4 * G * 4;  // nb[G][32], ymask[G], slot[G], node[G], phi_sum[G]
+  __host__ __device__ static size_t per_warp(uint32_t R, uint32_t MB) {
+    return (size_t)R * STAGE + OWN + (size_t)MB * META + (size_t)R * G * 4 + ((size_t)R + 1) * 8 + 64;
+  }
+};
+
+template <int KPL, int G>
+__global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ ColsPhiArgs a) {
+  using SM = ColsPhiSmem<KPL, G>;
+  constexpr int LPG = SM::LPG, KG = SM::KG, Q = KPL / 4;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const uint32_t sub = lane / LPG, li = lane % LPG;
+  const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
+  const ColsRankView& me = a.r[vr];
+  const uint32_t rank = me.rank;
+  const uint32_t n = a.n, R = a.R, D = a.D, MB = a.MB;
+
+  // ---- shared memory: ziggurat tables | per warp: ring, own pieces, metadata, self partials, barriers
+  uint32_t* s_zig = reinterpret_cast<uint32_t*>(s_raw);
+  const ZigShared zig{s_zig};
+  zig_stage(s_zig);
+  const size_t pw = (SM::per_warp(R, MB) + 127) / 128 * 128;
+  unsigned char* wbase = s_raw + 1536 + (size_t)wib * pw;
+  unsigned char* s_ring = wbase;
+  float* s_own = reinterpret_cast<float*>(s_ring + (size_t)R * SM::STAGE);
+  uint32_t* s_meta = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_own) + SM::OWN);
+  float* s_self = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_meta) + (size_t)MB * SM::META);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(s_self + (size_t)R * G) + 7) / 8 * 8);  // [R] stages, [R] = own pieces
+  if (lane == 0) {
+    for (uint32_t s = 0; s <= R; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  unsigned char* mybox = me.box[rank];
+  uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
+  const float* beta = reinterpret_cast<const float*>(mybox + a.lay.beta);
+  const size_t half_S = (size_t)a.parity * G * a.lay.S_src, half_R = (size_t)a.parity * G * a.lay.R_src;
+
+  // f_k = beta_k - epsilon for the thread's columns k = l + 32 i, l = rank + G li  (phi.cc:237-239)
+  const uint32_t l_ref = rank + G * li;
+  float fb[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) fb[i] = beta[2 * (l_ref + 32 * i) + 1] - a.epsilon;
+  const float e_link = a.epsilon, e_non = 1.0f - a.epsilon;
+  const float half_eps = a.eps_t / 2;
+
+  // ---- this warp's group-passes ----
+  const uint32_t active_units = a.units < a.V ? a.units : a.V;
+  const uint32_t ngroups = (active_units + G - 1) / G;
+  const uint32_t passes = (a.V + a.units - 1) / a.units;
+  const uint32_t gwarp = cta * warps + wib, total_warps = a.ctas_per_rank * warps;
+  const uint32_t my_groups = ngroups > gwarp ? (ngroups - gwarp + total_warps - 1) / total_warps : 0;
+  const uint32_t X = my_groups * passes;  // group-passes of this warp, in order (group, pass)
+  const uint32_t T = X * n;               // stages (trips): stage t = group-pass t / n, neighbor t % n
+  const uint32_t nseg = (n + 31) / 32;
+
+  // slot of (group-pass x, sub-group s); 0xffffffff when the sub-group is idle there
+  auto slot_of = [&](uint32_t x, uint32_t s) -> uint32_t {
+    const uint32_t group = gwarp + (x / passes) * total_warps, pass = x % passes;
+    const uint32_t unit = group * G + s;
+    const uint32_t slot = unit + pass * a.units;
+    return (unit < active_units && slot < a.V) ? slot : 0xffffffffu;
+  };
+  auto gpi_of = [&](uint32_t x) -> uint32_t {  // global group-pass id: the mailbox index
+    return (gwarp + (x / passes) * total_warps) * passes + x % passes;
+  };
+  auto meta_of = [&](uint32_t x, uint32_t seg) -> uint32_t* {
+    return s_meta + (size_t)((x * nseg + seg) % MB) * (SM::META / 4);
+  };
+
+  // metadata of a segment (<= 32 neighbors of the G slots of a group-pass): neighbor ids, the
+  // cuckoo answers y (phi.cc:230-234), slot / node / phi_sum of every sub-group
+  auto prep_segment = [&](uint32_t x, uint32_t seg) {
+    uint32_t* m = meta_of(x, seg);
+    uint32_t* m_nb = m;
+    uint32_t* m_y = m + G * 32;
+    uint32_t* m_slot = m_y + G;
+    uint32_t* m_node = m_slot + G;
+    float* m_phi = reinterpret_cast<float*>(m_node + G);
+    const uint32_t j0 = seg * 32, cnt = min(32u, n - j0);
+    uint32_t my_node = 0;
+    if (lane < G) {
+      const uint32_t slot = slot_of(x, lane);
+      m_slot[lane] = slot;
+      if (slot != 0xffffffffu) {
+        my_node = __ldg(&a.nodes[slot]);
+        m_node[lane] = my_node;
+        m_phi[lane] = me.phi[my_node];
+      } else {
+        m_node[lane] = 0;
+        m_phi[lane] = 1.0f;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+      const uint32_t slot = slot_of(x, s);  // warp-uniform
+      const uint32_t node = __shfl_sync(FULL_MASK, my_node, s);
+      bool y = false;
+      uint32_t nb = 0;
+      if (slot != 0xffffffffu && lane < cnt) {
+        nb = __ldg(&a.neighbors[(size_t)slot * n + j0 + lane]);
+        y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+      }
+      m_nb[s * 32 + lane] = nb;
+      const uint32_t mask = __ballot_sync(FULL_MASK, y);
+      if (lane == 0) m_y[s] = mask;
+    }
+    __syncwarp();
+  };
+
+  // LOAD(t): request the G neighbor pieces of stage t (and, at j = 0, the own pieces of the group-pass)
+  auto load_stage = [&](uint32_t t) {
+    const uint32_t x = t / n, j = t % n;
+    if ((j & 31) == 0) prep_segment(x, j >> 5);
+    const uint32_t* m = meta_of(x, j >> 5);
+    const uint32_t slot = m[G * 32 + G + sub];
+    const uint32_t act = __ballot_sync(FULL_MASK, slot != 0xffffffffu && li == 0);
+    const uint32_t nact = __popc(act);
+    const uint32_t b = t % R;
+    if (j == 0) {
+      if (lane == 0) mbar_expect_tx(&bars[R], nact * SM::PIECE);
+      __syncwarp();
+      if (li == 0 && slot != 0xffffffffu)
+        bulk_g2s(s_own + (size_t)sub * KG, me.pi + (size_t)m[G * 32 + 2 * G + sub] * KG, SM::PIECE, &bars[R]);
+    }
+    if (lane == 0) mbar_expect_tx(&bars[b], nact * SM::PIECE);
+    __syncwarp();
+    if (li == 0 && slot != 0xffffffffu) {
+      const uint32_t nb = m[sub * 32 + (j & 31)];
+      bulk_g2s(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE, me.pi + (size_t)nb * KG, SM::PIECE, &bars[b]);
+    }
+  };
+
+  float ownA[KPL], ownB[KPL], g[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) ownA[i] = ownB[i] = g[i] = 0.f;
+  Rng st;
+  st.x = st.y = 0;
+  uint32_t own_phase = 0;
+
+  for (uint32_t t = 0; t < R && t < T; ++t) load_stage(t);
+
+  for (uint32_t it = 0; it < T + D; ++it) {
+    // ------------------------------------------------------------ phase B of stage it - D ----
+    if (it >= D) {
+      const uint32_t t = it - D, x = t / n, j = t % n, b = t % R;
+      const uint32_t* m = meta_of(x, j >> 5);
+      const uint32_t slot = m[G * 32 + G + sub];
+      const bool live = slot != 0xffffffffu;
+      const float phi_sum = __uint_as_float(m[G * 32 + 3 * G + sub]);
+      const bool y = (m[G * 32 + sub] >> (j & 31)) & 1;
+      if (j == 0) {  // the B side enters group-pass x: A is still inside it (D < n)
+#pragma unroll
+        for (int i = 0; i < KPL; ++i) {
+          ownB[i] = ownA[i];
+          g[i] = 0.f;
+        }
+        if (x % passes == 0 && !a.disable_noise) {  // a new group: its units' RNG states
+          const uint32_t s0 = slot_of(x, sub);      // pass 0 slot == unit
+          if (s0 != 0xffffffffu) st = rng_load(me.pool, (uint64_t)s0 * 32 + l_ref);
+        }
+      }
+      // the G partials of (slot, j): own from the ring, the peers' from the mailbox
+      const size_t idx = ((size_t)gpi_of(x) * n + j) * G + sub;
+      const float mine = s_self[b * G + sub];
+      float v0 = 0.f, v1 = 0.f;
+      if (live) {
+        if (li < G) {
+          v0 = (li == rank || a.loopback)
+                   ? mine
+                   : poll_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)li * a.lay.S_src) + idx, err);
+        }
+        if (G > LPG) {
+          const uint32_t p1 = li + LPG;
+          v1 = (p1 == rank || a.loopback)
+                   ? mine
+                   : poll_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p1 * a.lay.S_src) + idx, err);
+        }
+      }
+      const float S = cols_rank_tree<G>(v0, v1, lane);
+      // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
+      const float inv = 1.0f / (S * phi_sum);
+      const float rphi = 1.0f / phi_sum;
+      const float e = y ? e_link : e_non;
+      const uint32_t sgn = y ? 0u : 0x80000000u;
+      const float4* row = reinterpret_cast<const float4*>(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE);
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const float4 r4 = row[q * LPG + li];
+        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = 4 * q + c;
+          const float tk = fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e);
+          g[i] += fmaf(tk, inv, -rphi);
+        }
+      }
+      __syncwarp();  // every lane is done with stage buffer b
+      if (j == n - 1) {
+        // ---- Langevin step of the group-pass (phi.cc:266-274), noise in the state's draw order ----
+        float* out = me.phi_vec + (size_t)(live ? slot : 0) * KG;
+        float lsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          float o[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = 4 * q + c;
+            const float noise = (a.disable_noise || !live) ? 1.0f : rng_randn_t(st, zig);
+            o[c] = phi_langevin(ownB[i], phi_sum, g[i], noise, half_eps, a.eps_t, a.alpha, a.Nn);
+            lsum += o[c];
+          }
+          if (live) *reinterpret_cast<float4*>(out + (size_t)(q * LPG + li) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+#pragma unroll
+        for (int o = LPG / 2; o > 0; o >>= 1) lsum += __shfl_xor_sync(FULL_MASK, lsum, o);
+        // this rank's partial row sum to every rank (its own mailbox included): update_pi reads them
+        if (live) {
+          const size_t ridx = (size_t)gpi_of(x) * G + sub;
+          const uint32_t bits = partial_bits(lsum);
+          for (uint32_t p = li; p < G; p += LPG)  // loopback: all G source regions of the own mailbox
+            st_mbox(reinterpret_cast<uint32_t*>(me.box[a.loopback ? rank : p] + a.lay.R + half_R +
+                                                (size_t)(a.loopback ? p : rank) * a.lay.R_src) + ridx,
+                    bits);
+        }
+        if (x % passes == passes - 1 && !a.disable_noise) {  // the group is finished: persist its states
+          const uint32_t s0 = slot_of(x - (passes - 1), sub);
+          if (s0 != 0xffffffffu) rng_store(me.pool, (uint64_t)s0 * 32 + l_ref, st);
+        }
+      }
+      if (t + R < T) load_stage(t + R);
+    }
+    // ---------------------------------------------------------------- phase A of stage it ----
+    if (it < T) {
+      const uint32_t t = it, x = t / n, j = t % n, b = t % R;
+      const uint32_t* m = meta_of(x, j >> 5);
+      const uint32_t slot = m[G * 32 + G + sub];
+      const bool live = slot != 0xffffffffu;
+      const bool y = (m[G * 32 + sub] >> (j & 31)) & 1;
+      if (j == 0) {  // own pieces of the group-pass into registers
+        mbar_wait(&bars[R], own_phase);
+        own_phase ^= 1;
+        const float4* o4 = reinterpret_cast<const float4*>(s_own + (size_t)sub * KG);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float4 v = live ? o4[q * LPG + li] : make_float4(0.f, 0.f, 0.f, 0.f);
+          ownA[4 * q] = v.x; ownA[4 * q + 1] = v.y; ownA[4 * q + 2] = v.z; ownA[4 * q + 3] = v.w;
+        }
+        __syncwarp();  // s_own may be refilled by the next group-pass's request
+      }
+      mbar_wait(&bars[b], (t / R) & 1);
+      const float e = y ? e_link : e_non;
+      const uint32_t sgn = y ? 0u : 0x80000000u;
+      const float4* row = reinterpret_cast<const float4*>(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE);
+      float S = 0.f;
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float4 r4 = row[q * LPG + li];
+          const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = 4 * q + c;
+            const float tk = fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e);
+            S = fmaf(ownA[i], tk, S);
+          }
+        }
+      }
+      // strides 16 .. G of WG_SUM: the lanes of this GPU
+#pragma unroll
+      for (int o = LPG / 2; o > 0; o >>= 1) S += __shfl_xor_sync(FULL_MASK, S, o);
+      if (li == 0) s_self[b * G + sub] = S;
+      if (live && !a.loopback) {
+        const size_t idx = ((size_t)gpi_of(x) * n + j) * G + sub;
+        const uint32_t bits = partial_bits(S);
+        for (uint32_t p = li; p < G; p += LPG)
+          if (p != rank)
+            st_mbox(reinterpret_cast<uint32_t*>(me.box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + idx, bits);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- update_pi on the column shards (phi.cc:154-197): pi[node][own columns] = phi_vec / sum ----
+struct ColsPiArgs {
+  ColsRankView r[AMMSB_MAX_SHARDS];
+  ColsBoxLayout lay;
+  const uint32_t* nodes;
+  uint32_t nv, ctas_per_rank, G, KG;
+  uint32_t V, units, parity;
+};
+
+__global__ void __launch_bounds__(256) k_cols_pi(const __grid_constant__ ColsPiArgs a) {
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
+  const ColsRankView& me = a.r[vr];
+  const uint32_t G = a.G, KG = a.KG;
+  unsigned char* mybox = me.box[me.rank];
+  uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
+  const uint32_t passes = (a.V + a.units - 1) / a.units;
+  const size_t half_R = (size_t)a.parity * G * a.lay.R_src;
+  for (uint32_t slot = cta * warps + wib; slot < a.V; slot += a.ctas_per_rank * warps) {
+    const uint32_t pass = slot / a.units, unit = slot - pass * a.units;
+    const size_t ridx = ((size_t)(unit / G) * passes + pass) * G + unit % G;
+    float v = 0.f;
+    if (lane < G) v = poll_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.R + half_R + (size_t)lane * a.lay.R_src) + ridx, err);
+    for (uint32_t o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);  // strides G/2 .. 1 of WG_SUM
+    const float sum = __shfl_sync(FULL_MASK, v, 0);
+    const uint32_t node = __ldg(&a.nodes[slot]);
+    const float4* src = reinterpret_cast<const float4*>(me.phi_vec + (size_t)slot * KG);
+    float4* dst = reinterpret_cast<float4*>(me.pi + (size_t)node * KG);
+    for (uint32_t f = lane; f < KG / 4; f += 32) {
+      float4 x = src[f];
+      x.x = __fdiv_rn(x.x, sum);
+      x.y = __fdiv_rn(x.y, sum);
+      x.z = __fdiv_rn(x.z, sum);
+      x.w = __fdiv_rn(x.w, sum);
+      dst[f] = x;
+    }
+    if (lane == 0) me.phi[node] = sum;
+  }
+}
+
+// ---- update_beta on the column shards (beta.cc:30-137, 334-384) ----
+// A sub-group of LPG lanes per mini-batch edge, G edges per warp trip.  The two K-wide sums of an
+// edge (sum pi_u pi_v and sum probs) are exchanged as partials like in k_cols_phi; both row pieces
+// stay in registers across the exchange.  Accumulators A_k = sum_{y=0} p_k / S, B_k = sum_{y=1} p_k / S
+// per thread, combined across sub-groups, warps and CTAs in a fixed order.
+struct ColsBetaArgs {
+  ColsRankView r[AMMSB_MAX_SHARDS];
+  SetView set;
+  ColsBoxLayout lay;
+  const uint64_t* edges;
+  uint32_t nv, ctas_per_rank;
+  uint32_t E_mb, parity, loopback;
+  float epsilon;
+};
+
+template <int KPL, int G>
+__global__ void __launch_bounds__(128) k_cols_beta(const __grid_constant__ ColsBetaArgs a) {
+  constexpr int LPG = 32 / G, KG = KPL * LPG, Q = KPL / 4, WARPS = 4;
+  __shared__ float s_acc[2][KG];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t sub = lane / LPG, li = lane % LPG;
+  const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
+  const ColsRankView& me = a.r[vr];
+  const uint32_t rank = me.rank;
+  unsigned char* mybox = me.box[rank];
+  uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
+  const float* beta = reinterpret_cast<const float*>(mybox + a.lay.beta);
+  const size_t half_B = (size_t)a.parity * G * a.lay.B_src;
+  const uint32_t l_ref = rank + G * li;
+  float bk[KPL], accA[KPL], accB[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    bk[i] = beta[2 * (l_ref + 32 * i) + 1];
+    accA[i] = accB[i] = 0.f;
+  }
+  const uint32_t trips = (a.E_mb + G - 1) / G;
+  for (uint32_t tr = cta * WARPS + wib; tr < trips; tr += a.ctas_per_rank * WARPS) {
+    const uint32_t e = tr * G + sub;
+    const bool live = e < a.E_mb;
+    float q[KPL];
+    bool y = false;
+    float pi_sum = 0.f, probs_sum = 0.f;
+    if (live) {
+      const uint64_t edge = __ldg(&a.edges[e]);
+      const uint32_t u = (uint32_t)(edge >> 32), v = (uint32_t)(edge & 0xffffffffu);
+      const float4* pa = reinterpret_cast<const float4*>(me.pi + (size_t)u * KG);
+      const float4* pb = reinterpret_cast<const float4*>(me.pi + (size_t)v * KG);
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq) {
+        const float4 x = ldg_stream4(reinterpret_cast<const float*>(pa + qq * LPG + li));
+        const float4 z = ldg_stream4(reinterpret_cast<const float*>(pb + qq * LPG + li));
+        q[4 * qq] = x.x * z.x; q[4 * qq + 1] = x.y * z.y; q[4 * qq + 2] = x.z * z.z; q[4 * qq + 3] = x.w * z.w;
+      }
+      y = set_has(a.set, make_edge(min(u, v), max(u, v)));
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        pi_sum += q[i];
+        q[i] *= y ? bk[i] : 1.0f - bk[i];  // probs_k (beta.cc:116-120)
+        probs_sum += q[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) q[i] = 0.f;
+    }
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) {
+      pi_sum += __shfl_xor_sync(FULL_MASK, pi_sum, o);
+      probs_sum += __shfl_xor_sync(FULL_MASK, probs_sum, o);
+    }
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (live) {
+      const size_t idx = (size_t)e * 2;
+      if (!a.loopback) {
+        const uint32_t pb_ = partial_bits(pi_sum), qb_ = partial_bits(probs_sum);
+        for (uint32_t p = li; p < G; p += LPG)
+          if (p != rank) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(me.box[p] + a.lay.B + half_B + (size_t)rank * a.lay.B_src) + idx;
+            st_mbox(dst, pb_);
+            st_mbox(dst + 1, qb_);
+          }
+      }
+      if (li < G) {
+        if (li == rank || a.loopback) {
+          a0 = pi_sum; b0 = probs_sum;
+        } else {
+          uint32_t* src = reinterpret_cast<uint32_t*>(mybox + a.lay.B + half_B + (size_t)li * a.lay.B_src) + idx;
+          a0 = poll_mbox(src, err); b0 = poll_mbox(src + 1, err);
+        }
+      }
+      if (G > LPG) {
+        const uint32_t p1 = li + LPG;
+        if (p1 == rank || a.loopback) {
+          a1 = pi_sum; b1 = probs_sum;
+        } else {
+          uint32_t* src = reinterpret_cast<uint32_t*>(mybox + a.lay.B + half_B + (size_t)p1 * a.lay.B_src) + idx;
+          a1 = poll_mbox(src, err); b1 = poll_mbox(src + 1, err);
+        }
+      }
+    }
+    pi_sum = cols_rank_tree<G>(a0, a1, lane);
+    probs_sum = cols_rank_tree<G>(b0, b1, lane);
+    // prob_0 = (y ? EPSILON : 1 - EPSILON) * (1 - pi_sum)   (beta.cc:124-125)
+    probs_sum += (y ? a.epsilon : 1.0f - a.epsilon) * (1.0f - pi_sum);
+    const float rS = live ? 1.0f / probs_sum : 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      if (y) accB[i] = fmaf(q[i], rS, accB[i]);
+      else accA[i] = fmaf(q[i], rS, accA[i]);
+    }
+  }
+  // combine: sub-groups of a warp (shuffle tree over the sub-group index), then the CTA's warps in
+  // warp order, then (k_cols_beta_reduce) the CTAs in order
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+#pragma unroll
+    for (int o = LPG; o < 32; o <<= 1) {
+      accA[i] += __shfl_xor_sync(FULL_MASK, accA[i], o);
+      accB[i] += __shfl_xor_sync(FULL_MASK, accB[i], o);
+    }
+  }
+  for (uint32_t w = 0; w < WARPS; ++w) {
+    if (wib == w && sub == 0) {
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const uint32_t c = ((i >> 2) * LPG + li) * 4 + (i & 3);
+        if (w == 0) {
+          s_acc[0][c] = accA[i];
+          s_acc[1][c] = accB[i];
+        } else {
+          s_acc[0][c] += accA[i];
+          s_acc[1][c] += accB[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* out = me.ws + (size_t)cta * 2 * KG;
+  for (uint32_t c = threadIdx.x; c < 2 * KG; c += blockDim.x) out[c] = s_acc[c / KG][c % KG];
+}
+
+// fixed-order sum over the CTAs' partials, gradient and Langevin step of the own columns'
+// theta (beta.cc:39-82), beta = normalised theta; the new values are published to every rank's
+// theta / beta arrays (a rank only ever READS its own columns in kernels, the host reads all).
+struct ColsThetaArgs {
+  ColsRankView r[AMMSB_MAX_SHARDS];
+  ColsBoxLayout lay;
+  uint32_t nv, G, K, P;
+  float eps_t, eta0, eta1, scale;
+};
+
+__device__ __forceinline__ void cols_theta_step(float t0, float t1, float g0, float g1, uint32_t k, float eps_t,
+                                                float eta0, float eta1, float scale, ulonglong2* pool, float* out4) {
+  Rng s = rng_load(pool, k);
+  const float half = __fdiv_rn(eps_t, 2.0f);
+  const float r0 = rng_randn(s);
+  const float f0 = __fsqrt_rn(__fmul_rn(eps_t, t0));
+  t0 = fabsf(__fadd_rn(__fadd_rn(t0, __fmul_rn(half, __fadd_rn(__fsub_rn(eta0, t0), __fmul_rn(scale, g0)))),
+                       __fmul_rn(f0, r0)));
+  t0 = fmaxf(t0, 1e-24f);
+  const float r1 = rng_randn(s);
+  const float f1 = __fsqrt_rn(__fmul_rn(eps_t, t1));
+  t1 = fabsf(__fadd_rn(__fadd_rn(t1, __fmul_rn(half, __fadd_rn(__fsub_rn(eta1, t1), __fmul_rn(scale, g1)))),
+                       __fmul_rn(f1, r1)));
+  t1 = fmaxf(t1, 1e-24f);
+  rng_store(pool, k, s);
+  const float sum = __fadd_rn(__fadd_rn(0.f, t0), t1);
+  out4[0] = t0;
+  out4[1] = t1;
+  out4[2] = __fdiv_rn(t0, sum);
+  out4[3] = __fdiv_rn(t1, sum);
+}
+
+__global__ void __launch_bounds__(128) k_cols_theta(const __grid_constant__ ColsThetaArgs a) {
+  const uint32_t KG = a.K / a.G, LPG = 32 / a.G;
+  const uint32_t per_rank = (KG + blockDim.x - 1) / blockDim.x;
+  const uint32_t vr = blockIdx.x / per_rank;
+  const uint32_t c = (blockIdx.x % per_rank) * blockDim.x + threadIdx.x;
+  if (c >= KG) return;
+  const ColsRankView& me = a.r[vr];
+  // local index c -> global column k
+  const uint32_t f = c >> 2, e = c & 3, q = f / LPG, li = f % LPG;
+  const uint32_t k = (me.rank + a.G * li) + 32 * (4 * q + e);
+  float A = 0.f, B = 0.f;
+  for (uint32_t p = 0; p < a.P; ++p) {
+    A += me.ws[(size_t)p * 2 * KG + c];
+    B += me.ws[(size_t)p * 2 * KG + KG + c];
+  }
+  unsigned char* mybox = me.box[me.rank];
+  const float* theta = reinterpret_cast<const float*>(mybox + a.lay.theta);
+  const float t0 = theta[2 * k], t1 = theta[2 * k + 1];
+  const float ts = __fadd_rn(t0, t1);
+  const float rts = __fdiv_rn(1.0f, ts);
+  const float g0 = A * (__fdiv_rn(1.0f, t0) - rts) + B * (0.0f - rts);
+  const float g1 = A * (0.0f - rts) + B * (__fdiv_rn(1.0f, t1) - rts);
+  float o[4];
+  cols_theta_step(t0, t1, g0, g1, k, a.eps_t, a.eta0, a.eta1, a.scale, me.pool, o);
+  for (uint32_t p = 0; p < a.G; ++p) {
+    if (me.box[p] == nullptr) continue;
+    float* th = reinterpret_cast<float*>(me.box[p] + a.lay.theta);
+    float* be = reinterpret_cast<float*>(me.box[p] + a.lay.beta);
+    *reinterpret_cast<float2*>(th + 2 * k) = make_float2(o[0], o[1]);
+    *reinterpret_cast<float2*>(be + 2 * k) = make_float2(o[2], o[3]);
+  }
+}
+
+// ---- held-out perplexity on the column shards (perplexity.cc:14-83, 251-274) ----
+// Sub-group per pair; the two K-wide sums are exchanged; EVERY rank then finishes every pair
+// (running mean, log, the four sums) -- redundant scalar work instead of a second exchange, and the
+// replicated ppx_per_edge arrays stay identical.
+struct ColsPpxArgs {
+  ColsRankView r[AMMSB_MAX_SHARDS];
+  SetView set;
+  ColsBoxLayout lay;
+  const uint64_t* edges;
+  uint32_t nv, ctas_per_rank;
+  uint32_t H, parity, call_count, loopback;
+  float epsilon;
+};
+
+template <int KPL, int G>
+__global__ void __launch_bounds__(128) k_cols_ppx(const __grid_constant__ ColsPpxArgs a) {
+  constexpr int LPG = 32 / G, KG = KPL * LPG, Q = KPL / 4, WARPS = 4;
+  __shared__ double s_part[WARPS][4];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t sub = lane / LPG, li = lane % LPG;
+  const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
+  const ColsRankView& me = a.r[vr];
+  const uint32_t rank = me.rank;
+  unsigned char* mybox = me.box[rank];
+  uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
+  const float* beta = reinterpret_cast<const float*>(mybox + a.lay.beta);
+  const size_t half_P = (size_t)a.parity * G * a.lay.P_src;
+  const uint32_t l_ref = rank + G * li;
+  float bk[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) bk[i] = beta[2 * (l_ref + 32 * i) + 1];
+  double link_lik = 0.0, non_lik = 0.0;
+  uint32_t link_cnt = 0, non_cnt = 0;
+  const uint32_t trips = (a.H + G - 1) / G;
+  for (uint32_t tr = cta * WARPS + wib; tr < trips; tr += a.ctas_per_rank * WARPS) {
+    const uint32_t i = tr * G + sub;
+    const bool live = i < a.H;
+    float sb = 0.f, sq = 0.f;
+    bool is_edge = false;
+    if (live) {
+      const uint64_t e = __ldg(&a.edges[i]);
+      const uint32_t u = (uint32_t)(e >> 32), v = (uint32_t)(e & 0xffffffffu);
+      const float4* pa = reinterpret_cast<const float4*>(me.pi + (size_t)u * KG);
+      const float4* pb = reinterpret_cast<const float4*>(me.pi + (size_t)v * KG);
+      is_edge = set_has(a.set, e);  // membership of the key as stored (perplexity.cc:45-47)
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq) {
+        const float4 x = ldg_stream4(reinterpret_cast<const float*>(pa + qq * LPG + li));
+        const float4 z = ldg_stream4(reinterpret_cast<const float*>(pb + qq * LPG + li));
+        const float f0 = x.x * z.x, f1 = x.y * z.y, f2 = x.z * z.z, f3 = x.w * z.w;
+        sq += f0; sq += f1; sq += f2; sq += f3;
+        sb = fmaf(f0, bk[4 * qq], sb);
+        sb = fmaf(f1, bk[4 * qq + 1], sb);
+        sb = fmaf(f2, bk[4 * qq + 2], sb);
+        sb = fmaf(f3, bk[4 * qq + 3], sb);
+      }
+    }
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) {
+      sb += __shfl_xor_sync(FULL_MASK, sb, o);
+      sq += __shfl_xor_sync(FULL_MASK, sq, o);
+    }
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (live) {
+      const size_t idx = (size_t)i * 2;
+      if (!a.loopback) {
+        const uint32_t x0 = partial_bits(sb), x1 = partial_bits(sq);
+        for (uint32_t p = li; p < G; p += LPG)
+          if (p != rank) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(me.box[p] + a.lay.P + half_P + (size_t)rank * a.lay.P_src) + idx;
+            st_mbox(dst, x0);
+            st_mbox(dst + 1, x1);
+          }
+      }
+      if (li < G) {
+        if (li == rank || a.loopback) {
+          a0 = sb; b0 = sq;
+        } else {
+          uint32_t* src = reinterpret_cast<uint32_t*>(mybox + a.lay.P + half_P + (size_t)li * a.lay.P_src) + idx;
+          a0 = poll_mbox(src, err); b0 = poll_mbox(src + 1, err);
+        }
+      }
+      if (G > LPG) {
+        const uint32_t p1 = li + LPG;
+        if (p1 == rank || a.loopback) {
+          a1 = sb; b1 = sq;
+        } else {
+          uint32_t* src = reinterpret_cast<uint32_t*>(mybox + a.lay.P + half_P + (size_t)p1 * a.lay.P_src) + idx;
+          a1 = poll_mbox(src, err); b1 = poll_mbox(src + 1, err);
+        }
+      }
+    }
+    sb = cols_rank_tree<G>(a0, a1, lane);
+    sq = cols_rank_tree<G>(b0, b1, lane);
+    if (live && li == 0) {
+      // calculate_edge_likelihood, perplexity.cc:16-40
+      float s = is_edge ? sb : (sq - sb) + (1.0f - sq) * (1.0f - a.epsilon);
+      if (s < 1.0e-30f) s = 1.0e-30f;
+      float ppx = me.ppx[i];  // running mean over calls, perplexity.cc:51-52
+      ppx = __fdiv_rn(__fadd_rn(__fmul_rn(ppx, (float)(a.call_count - 1)), s), (float)a.call_count);
+      me.ppx[i] = ppx;
+      const float lg = logf(ppx);
+      if (is_edge) {
+        link_lik += (double)lg;
+        ++link_cnt;
+      } else {
+        non_lik += (double)lg;
+        ++non_cnt;
+      }
+    }
+  }
+  double c0 = (double)link_cnt, c1 = (double)non_cnt;
+  link_lik = warp_sum_d(link_lik);
+  non_lik = warp_sum_d(non_lik);
+  c0 = warp_sum_d(c0);
+  c1 = warp_sum_d(c1);
+  if (lane == 0) {
+    s_part[wib][0] = link_lik; s_part[wib][1] = non_lik; s_part[wib][2] = c0; s_part[wib][3] = c1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int w = 0; w < WARPS; ++w) s += s_part[w][threadIdx.x];
+    me.ws_d[(size_t)cta * 4 + threadIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_cols_ppx_reduce(const __grid_constant__ ColsPpxArgs a, uint32_t P) {
+  const ColsRankView& me = a.r[blockIdx.x];
+  const uint32_t q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (uint32_t p = lane; p < P; p += 32) s += me.ws_d[(size_t)p * 4 + q];
+  s = warp_sum_d(s);
+  if (lane == 0) me.ws_d[(size_t)P * 4 + q] = s;
+}
+
+// ---- init / host access ----
+// RandomGammaAndNormalize (random.cc:131-167) on the column shards: every rank walks the whole
+// gamma stream of every row (group per row, state = group*32 + lane, pool seeded {11,113}) -- the
+// row sum needs all 32 lanes, and recomputing them is cheaper than an exchange at set-up -- and
+// stores the columns of its own lanes.
+__global__ void k_cols_init_pi(float* pi, float* phi, uint32_t N, uint32_t K, uint32_t G, uint32_t rank, uint32_t groups,
+                               float eta0, float eta1) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= groups) return;
+  const uint64_t id = (uint64_t)warp * 32 + lane;
+  Rng s;
+  s.x = 11 + id;
+  s.y = 113 + id;
+  const uint32_t KG = K / G, LPG = 32 / G;
+  const bool mine = lane % G == rank;
+  const uint32_t li = lane / G;
+  for (uint32_t row = warp; row < N; row += groups) {
+    float* r = pi + (size_t)row * KG;
+    float lsum = 0.f;
+    for (uint32_t i = 0; i < K / 32; ++i) {
+      const float g = rng_gamma(s, eta0, eta1);
+      lsum = __fadd_rn(lsum, g);
+      if (mine) r[((i >> 2) * LPG + li) * 4 + (i & 3)] = g;
+    }
+    const float sum = warp_sum(lsum);
+    if (mine)
+      for (uint32_t i = 0; i < K / 32; ++i) {
+        float* p = &r[((i >> 2) * LPG + li) * 4 + (i & 3)];
+        *p = __fdiv_rn(*p, sum);
+      }
+    if (lane == 0) phi[row] = sum;
+  }
+}
+
+// full rows [nrows][K] (global column order) <-> the shard's own columns
+__global__ void k_cols_scatter(float* pi, const float* full, uint64_t row0, uint64_t nrows, uint32_t K, uint32_t G,
+                               uint32_t rank, bool gather, float* full_out) {
+  const uint32_t KG = K / G;
+  const uint64_t total = nrows * KG;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = i / KG;
+    const uint32_t c = (uint32_t)(i % KG);
+    const uint32_t LPG = 32 / G, f = c >> 2, e = c & 3, q = f / LPG, li = f % LPG;
+    const uint32_t k = (rank + G * li) + 32 * (4 * q + e);
+    if (gather) full_out[r * K + k] = pi[(row0 + r) * KG + c];
+    else pi[(row0 + r) * KG + c] = full[r * K + k];
+  }
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------ host API ----
+
+static int cols_check_shape(uint32_t K, uint32_t G) {
+  AMMSB_REQUIRE(G == 2 || G == 4 || G == 8, "column-sharded layout: world must be 2, 4 or 8");
+  AMMSB_REQUIRE(K == 128 || K == 256 || K == 512 || K == 1024, "column-sharded layout: K must be 128, 256, 512 or 1024");
+  return 0;
+}
+
+extern "C" int ammsb_cols_create(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t world, uint32_t rank,
+                                 uint32_t num_neighbors, uint32_t max_nodes, uint32_t max_edges, uint64_t max_pairs,
+                                 ammsb_cols** out) {
+  if (cols_check_shape(K, world)) return 1;
+  AMMSB_REQUIRE(rank < world, "rank out of range");
+  AMMSB_REQUIRE(N > 0 && N < 0xffffffffull, "N must fit a 32-bit Vertex (types.h:32)");
+  AMMSB_REQUIRE(num_neighbors >= 8 && max_nodes > 0, "num_neighbors must be >= 8");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ammsb_cols* s = new ammsb_cols();
+  s->ctx = c;
+  s->N = N; s->K = K; s->G = world; s->rank = rank; s->n = num_neighbors;
+  s->Vcap = max_nodes; s->Ecap = max_edges; s->Hcap = max_pairs;
+  s->KG = K / world;
+  s->lay = cols_layout(K, world, num_neighbors, max_nodes, max_edges, max_pairs);
+  s->ws_ctas = (uint32_t)c->sm_count * 8;
+  cudaError_t e = cudaMalloc((void**)&s->d_pi, sizeof(float) * N * s->KG);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_phi, sizeof(float) * N);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_phi_vec, sizeof(float) * (size_t)max_nodes * s->KG);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ppx, sizeof(float) * (max_pairs ? max_pairs : 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ws, sizeof(float) * 2 * s->KG * (size_t)s->ws_ctas);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ws_d, sizeof(double) * 4 * ((size_t)s->ws_ctas + 1));
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ppx, 0, sizeof(float) * (max_pairs ? max_pairs : 1), c->stream);
+  if (e != cudaSuccess || vmm_alloc(c->device, s->lay.bytes, &s->local)) {
+    cudaFree(s->d_pi); cudaFree(s->d_phi); cudaFree(s->d_phi_vec); cudaFree(s->d_ppx); cudaFree(s->d_ws); cudaFree(s->d_ws_d);
+    delete s;
+    if (e != cudaSuccess) AMMSB_CHECK_CUDA(e);
+    return 1;
+  }
+  s->box[rank] = reinterpret_cast<unsigned char*>(s->local.ptr);
+  // every mailbox word starts armed (sentinel); the header (error word) and theta/beta start at 0
+  AMMSB_CHECK_CUDA(cudaMemsetAsync(s->box[rank], 0xff, s->lay.bytes, c->stream));
+  AMMSB_CHECK_CUDA(cudaMemsetAsync(s->box[rank], 0, s->lay.S, c->stream));
+  AMMSB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  *out = s;
+  return 0;
+}
+
+extern "C" int ammsb_cols_destroy(ammsb_cols* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->ctx->device);
+  for (int i = 0; i < AMMSB_MAX_SHARDS; ++i) vmm_free(&s->remote[i]);
+  vmm_free(&s->local);
+  cudaFree(s->d_pi); cudaFree(s->d_phi); cudaFree(s->d_phi_vec); cudaFree(s->d_ppx); cudaFree(s->d_ws); cudaFree(s->d_ws_d);
+  delete s;
+  return 0;
+}
+
+extern "C" int ammsb_cols_mailbox_bytes(const ammsb_cols* s, size_t* bytes) {
+  *bytes = s->lay.bytes;
+  return 0;
+}
+
+extern "C" int ammsb_cols_export_fd(ammsb_cols* s, int* fd) { return vmm_export_fd(s->local, fd); }
+
+extern "C" int ammsb_cols_attach_fd(ammsb_cols* s, uint32_t peer_rank, int fd) {
+  AMMSB_REQUIRE(peer_rank < s->G && peer_rank != s->rank, "bad peer rank");
+  if (vmm_import_fd(s->ctx->device, fd, s->lay.bytes, &s->remote[peer_rank])) return 1;
+  s->box[peer_rank] = reinterpret_cast<unsigned char*>(s->remote[peer_rank].ptr);
+  return 0;
+}
+
+// same process: another rank's mailbox by direct (peer) access -- also how one GPU emulates G ranks
+extern "C" int ammsb_cols_attach_local(ammsb_cols* s, uint32_t peer_rank, ammsb_cols* peer) {
+  AMMSB_REQUIRE(peer_rank < s->G && peer_rank != s->rank && peer->rank == peer_rank, "bad peer rank");
+  AMMSB_REQUIRE(peer->N == s->N && peer->K == s->K && peer->G == s->G && peer->lay.bytes == s->lay.bytes,
+                "peer does not match");
+  AMMSB_CHECK_CUDA(cudaSetDevice(s->ctx->device));
+  if (peer->ctx->device != s->ctx->device) {
+    int can = 0;
+    AMMSB_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, s->ctx->device, peer->ctx->device));
+    AMMSB_REQUIRE(can, "devices are not peer-accessible");
+    if (vmm_grant(s->ctx->device, peer->local)) return 1;
+  }
+  s->box[peer_rank] = peer->box[peer_rank];
+  return 0;
+}
+
+extern "C" int ammsb_cols_init_pi(ammsb_cols* s, float eta0, float eta1) {
+  ammsb_ctx* c = s->ctx;
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  const uint32_t groups = s->N < 65535 ? (uint32_t)s->N : 65535u;
+  k_cols_init_pi<<<(groups * 32 + 127) / 128, 128, 0, c->stream>>>(s->d_pi, s->d_phi, (uint32_t)s->N, s->K, s->G, s->rank,
+                                                                  groups, eta0, eta1);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int cols_rows_io(ammsb_cols* s, uint64_t row0, uint64_t nrows, float* h, bool gather) {
+  AMMSB_REQUIRE(row0 + nrows <= s->N, "rows out of range");
+  ammsb_ctx* c = s->ctx;
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  const uint64_t chunk = (64ull << 20) / (sizeof(float) * s->K) + 1;
+  float* d_full = nullptr;
+  AMMSB_CHECK_CUDA(cudaMalloc((void**)&d_full, sizeof(float) * s->K * (nrows < chunk ? nrows : chunk)));
+  int rc = 0;
+  for (uint64_t r = 0; r < nrows && !rc; r += chunk) {
+    const uint64_t cnt = nrows - r < chunk ? nrows - r : chunk;
+    if (gather) {
+      // columns of other ranks keep what the caller's buffer holds: start from the host content
+      rc = ammsb_h2d(c, d_full, h + r * s->K, sizeof(float) * cnt * s->K);
+      if (rc) break;
+    } else {
+      rc = ammsb_h2d(c, d_full, h + r * s->K, sizeof(float) * cnt * s->K);
+      if (rc) break;
+    }
+    k_cols_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(s->d_pi, d_full, row0 + r, cnt, s->K, s->G, s->rank, gather, d_full);
+    g_launch_count.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) { rc = 1; ammsb_set_error("k_cols_scatter launch failed"); break; }
+    if (gather) rc = ammsb_d2h(c, h + r * s->K, d_full, sizeof(float) * cnt * s->K);
+    else if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = 1; ammsb_set_error("scatter failed"); }
+  }
+  cudaFree(d_full);
+  return rc;
+}
+
+extern "C" int ammsb_cols_write_pi(ammsb_cols* s, uint64_t row0, uint64_t nrows, const float* h_rows) {
+  return cols_rows_io(s, row0, nrows, const_cast<float*>(h_rows), false);
+}
+extern "C" int ammsb_cols_read_pi(ammsb_cols* s, uint64_t row0, uint64_t nrows, float* h_rows) {
+  return cols_rows_io(s, row0, nrows, h_rows, true);
+}
+extern "C" int ammsb_cols_write_phi(ammsb_cols* s, uint64_t row0, uint64_t nrows, const float* h) {
+  AMMSB_REQUIRE(row0 + nrows <= s->N, "rows out of range");
+  return ammsb_h2d(s->ctx, s->d_phi + row0, h, sizeof(float) * nrows);
+}
+extern "C" int ammsb_cols_read_phi(ammsb_cols* s, uint64_t row0, uint64_t nrows, float* h) {
+  AMMSB_REQUIRE(row0 + nrows <= s->N, "rows out of range");
+  return ammsb_d2h(s->ctx, h, s->d_phi + row0, sizeof(float) * nrows);
+}
+extern "C" int ammsb_cols_write_theta(ammsb_cols* s, const float* h_theta, const float* h_beta) {
+  int rc = ammsb_h2d(s->ctx, s->box[s->rank] + s->lay.theta, h_theta, sizeof(float) * 2 * s->K);
+  if (!rc) rc = ammsb_h2d(s->ctx, s->box[s->rank] + s->lay.beta, h_beta, sizeof(float) * 2 * s->K);
+  return rc;
+}
+extern "C" int ammsb_cols_read_theta(ammsb_cols* s, float* h_theta, float* h_beta) {
+  int rc = 0;
+  if (h_theta) rc = ammsb_d2h(s->ctx, h_theta, s->box[s->rank] + s->lay.theta, sizeof(float) * 2 * s->K);
+  if (!rc && h_beta) rc = ammsb_d2h(s->ctx, h_beta, s->box[s->rank] + s->lay.beta, sizeof(float) * 2 * s->K);
+  return rc;
+}
+extern "C" int ammsb_cols_beta_ptr(ammsb_cols* s, float** d_theta, float** d_beta) {
+  if (d_theta) *d_theta = reinterpret_cast<float*>(s->box[s->rank] + s->lay.theta);
+  if (d_beta) *d_beta = reinterpret_cast<float*>(s->box[s->rank] + s->lay.beta);
+  return 0;
+}
+extern "C" int ammsb_cols_read_phi_vec(ammsb_cols* s, uint32_t V, float* h_rows /* [V][K], own columns filled */) {
+  AMMSB_REQUIRE(V <= s->Vcap, "V exceeds the capacity");
+  ammsb_ctx* c = s->ctx;
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  float* d_full = nullptr;
+  AMMSB_CHECK_CUDA(cudaMalloc((void**)&d_full, sizeof(float) * (size_t)V * s->K));
+  int rc = ammsb_h2d(c, d_full, h_rows, sizeof(float) * (size_t)V * s->K);
+  if (!rc) {
+    k_cols_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(s->d_phi_vec, d_full, 0, V, s->K, s->G, s->rank, true, d_full);
+    g_launch_count.fetch_add(1);
+    rc = ammsb_d2h(c, h_rows, d_full, sizeof(float) * (size_t)V * s->K);
+  }
+  cudaFree(d_full);
+  return rc;
+}
+// 0 = no exchange wait has timed out on this rank so far
+extern "C" int ammsb_cols_check(ammsb_cols* s, uint32_t* timed_out) {
+  return ammsb_d2h(s->ctx, timed_out, s->box[s->rank], 4);
+}
+
+static int cols_ready(ammsb_cols* const* ranks, uint32_t nv) {
+  AMMSB_REQUIRE(nv >= 1 && nv <= AMMSB_MAX_SHARDS, "bad number of ranks in one launch");
+  for (uint32_t i = 0; i < nv; ++i) {
+    AMMSB_REQUIRE(ranks[i] && ranks[i]->ctx->device == ranks[0]->ctx->device && ranks[i]->G == ranks[0]->G &&
+                      ranks[i]->K == ranks[0]->K && ranks[i]->N == ranks[0]->N,
+                  "ranks of one launch must live on one device and agree in shape");
+    for (uint32_t p = 0; p < ranks[i]->G; ++p) AMMSB_REQUIRE(ranks[i]->box[p] != nullptr, "a peer mailbox is not attached");
+  }
+  return 0;
+}
+
+template <class Kern, class Args>
+static int cols_launch_coop(ammsb_ctx* c, Kern kern, const Args& a, uint32_t grid, uint32_t block, size_t smem) {
+  void* params[] = {const_cast<Args*>(&a)};
+  AMMSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(block), params, smem,
+                                               c->stream));
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+struct ColsTune {  // launch shape of k_cols_phi, overridable for A/B measurements
+  uint32_t warps, R, D;
+};
+static ColsTune cols_tune(uint32_t KPL, uint32_t G, uint32_t n) {
+  ColsTune t;
+  t.warps = 6; t.R = 6; t.D = 3;
+  if (const char* e = getenv("AMMSB_COLS_WARPS")) t.warps = (uint32_t)atoi(e);
+  if (const char* e = getenv("AMMSB_COLS_R")) t.R = (uint32_t)atoi(e);
+  if (const char* e = getenv("AMMSB_COLS_D")) t.D = (uint32_t)atoi(e);
+  if (t.R > n) t.R = n;
+  if (t.R < 2) t.R = 2;
+  if (t.D >= t.R) t.D = t.R - 1;
+  if (t.D < 1) t.D = 1;  // phase B of a stage runs after its phase A
+  if (t.warps < 1) t.warps = 1;
+  if (t.warps > 8) t.warps = 8;
+  return t;
+}
+
+template <int KPL, int G>
+static int cols_phi_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv) {
+  using SM = ColsPhiSmem<KPL, G>;
+  const ColsTune t = cols_tune(KPL, G, a.n);
+  a.R = t.R;
+  a.D = t.D;
+  const uint32_t min_seg = a.n % 32 ? a.n % 32 : 32;
+  a.MB = 2 + (t.R - 1 + min_seg - 1) / min_seg;
+  uint32_t warps = t.warps;
+  size_t smem;
+  for (;; --warps) {
+    smem = 1536 + (size_t)warps * ((SM::per_warp(a.R, a.MB) + 127) / 128 * 128);
+    if (smem <= c->smem_optin || warps == 1) break;
+  }
+  AMMSB_REQUIRE(smem <= c->smem_optin, "column update_phi: shared memory request exceeds the device limit");
+  auto kern = k_cols_phi<KPL, G>;
+  static bool attr_set[64] = {false};  // per device
+  if (!attr_set[c->device & 63]) {
+    AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    attr_set[c->device & 63] = true;
+  }
+  int occ = 0;
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+  AMMSB_REQUIRE(occ > 0, "column update_phi: kernel does not fit on an SM");
+  const uint32_t resident = (uint32_t)occ * c->sm_count;
+  const uint32_t active = a.units < a.V ? a.units : a.V;
+  const uint32_t ngroups = (active + G - 1) / G;
+  uint32_t ctas = resident / nv;
+  // no more warps than groups, and an even share of groups per warp (a static schedule: the
+  // slowest warp ends the kernel)
+  const uint32_t want_warps = ngroups;
+  if (ctas * warps > want_warps) ctas = (want_warps + warps - 1) / warps;
+  if (ctas > 0) {
+    const uint32_t per = (ngroups + ctas * warps - 1) / (ctas * warps);
+    const uint32_t need = (ngroups + per - 1) / per;  // warps that get `per` groups (the last maybe fewer)
+    ctas = (need + warps - 1) / warps;
+  }
+  AMMSB_REQUIRE(ctas > 0, "column update_phi: no resident CTA available per rank");
+  a.ctas_per_rank = ctas;
+  a.nv = nv;
+  return cols_launch_coop(c, kern, a, ctas * nv, warps * 32, smem);
+}
+
+extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
+                                     const ammsb_phi_opts* o, ammsb_set* train, const uint32_t* d_nodes,
+                                     const uint32_t* d_neighbors, uint32_t V, uint32_t step_count,
+                                     ammsb_rng* const* pools) {
+  if (cols_ready(ranks, nv)) return 1;
+  const ammsb_cols* s0 = ranks[0];
+  AMMSB_REQUIRE(V > 0, "mini-batch nodes size = 0!");  // phi.cc:732
+  AMMSB_REQUIRE(V <= s0->Vcap, "mini-batch larger than the capacity the store was created with");
+  AMMSB_REQUIRE(p->K == s0->K && p->N == s0->N && p->num_neighbors == s0->n, "params do not match the store");
+  AMMSB_REQUIRE(o->mode == AMMSB_MODE_WG && o->wg == 32, "the column layout reproduces the WG launch with wg = 32");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ColsPhiArgs a;
+  memset(&a, 0, sizeof a);
+  a.units = cols_units(V);
+  const uint64_t states = (uint64_t)a.units * 32;
+  for (uint32_t i = 0; i < nv; ++i) {
+    AMMSB_REQUIRE(o->disable_noise || (pools && pools[i] && pools[i]->n >= states), "Num seeds smaller than global threads");
+    a.r[i] = ranks[i]->view(pools && pools[i] ? pools[i]->d_state : nullptr);
+  }
+  a.set = train->view();
+  a.lay = s0->lay;
+  a.nodes = d_nodes;
+  a.neighbors = d_neighbors;
+  a.V = V;
+  a.n = p->num_neighbors;
+  a.parity = step_count & 1;
+  a.disable_noise = o->disable_noise;
+  a.loopback = getenv("AMMSB_COLS_LOOPBACK") != nullptr;
+  a.eps_t = ammsb_eps_t(p, step_count);
+  a.alpha = p->alpha;
+  a.epsilon = p->epsilon;
+  a.Nn = (1.0f * p->N) / p->num_neighbors;  // phi.cc:113
+  const uint32_t kpl = p->K / 32, G = s0->G;
+#define COLS_PHI_CASE(KPL_, G_) \
+  if (kpl == KPL_ && G == G_) return cols_phi_launch<KPL_, G_>(c, a, nv);
+  COLS_PHI_CASE(4, 2) COLS_PHI_CASE(4, 4) COLS_PHI_CASE(4, 8)
+  COLS_PHI_CASE(8, 2) COLS_PHI_CASE(8, 4) COLS_PHI_CASE(8, 8)
+  COLS_PHI_CASE(16, 2) COLS_PHI_CASE(16, 4) COLS_PHI_CASE(16, 8)
+  COLS_PHI_CASE(32, 2) COLS_PHI_CASE(32, 4) COLS_PHI_CASE(32, 8)
+#undef COLS_PHI_CASE
+  AMMSB_REQUIRE(false, "unsupported (K, world) for the column layout");
+  return 1;
+}
+
+extern "C" int ammsb_cols_update_pi(ammsb_ctx* c, ammsb_cols* const* ranks, uint32_t nv, const uint32_t* d_nodes,
+                                    uint32_t V, uint32_t step_count) {
+  if (cols_ready(ranks, nv)) return 1;
+  AMMSB_REQUIRE(V > 0 && V <= ranks[0]->Vcap, "bad mini-batch size");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ColsPiArgs a;
+  memset(&a, 0, sizeof a);
+  for (uint32_t i = 0; i < nv; ++i) a.r[i] = ranks[i]->view(nullptr);
+  a.lay = ranks[0]->lay;
+  a.nodes = d_nodes;
+  a.nv = nv;
+  a.G = ranks[0]->G;
+  a.KG = ranks[0]->KG;
+  a.V = V;
+  a.units = cols_units(V);
+  a.parity = step_count & 1;
+  uint32_t ctas = (V + 7) / 8;
+  const uint32_t cap = (uint32_t)c->sm_count * 4 / nv;  // every CTA resident: peers' partials may still be in flight
+  if (ctas > cap) ctas = cap ? cap : 1;
+  a.ctas_per_rank = ctas;
+  k_cols_pi<<<ctas * nv, 256, 0, c->stream>>>(a);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int KPL, int G>
+static int cols_beta_launch(ammsb_ctx* c, ColsBetaArgs& a, uint32_t nv, uint32_t ws_ctas) {
+  const uint32_t trips = (a.E_mb + G - 1) / G;
+  uint32_t ctas = (trips + 3) / 4;
+  int occ = 0;  // every CTA must be resident: its warps wait for the same warps of the peers
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cols_beta<KPL, G>, 128, 0));
+  uint32_t cap = (uint32_t)c->sm_count * (uint32_t)occ / nv;
+  if (cap > ws_ctas) cap = ws_ctas;
+  if (ctas > cap) ctas = cap;
+  if (ctas == 0) ctas = 1;
+  a.ctas_per_rank = ctas;
+  a.nv = nv;
+  return cols_launch_coop(c, k_cols_beta<KPL, G>, a, ctas * nv, 128, 0);
+}
+
+extern "C" int ammsb_cols_update_beta(ammsb_ctx* c, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
+                                      ammsb_set* train, const uint64_t* d_edges, uint32_t E_mb, float scale,
+                                      uint32_t step_count, ammsb_rng* const* pools) {
+  if (cols_ready(ranks, nv)) return 1;
+  const ammsb_cols* s0 = ranks[0];
+  AMMSB_REQUIRE(p->K == s0->K && p->N == s0->N, "params do not match the store");
+  AMMSB_REQUIRE(E_mb <= s0->Ecap, "mini-batch larger than the capacity the store was created with");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ColsBetaArgs a;
+  memset(&a, 0, sizeof a);
+  for (uint32_t i = 0; i < nv; ++i) {
+    AMMSB_REQUIRE(pools && pools[i] && pools[i]->n >= p->K, "beta RNG pool smaller than K");
+    a.r[i] = ranks[i]->view(pools[i]->d_state);
+  }
+  a.set = train->view();
+  a.lay = s0->lay;
+  a.edges = d_edges;
+  a.E_mb = E_mb;
+  a.parity = step_count & 1;
+  a.loopback = getenv("AMMSB_COLS_LOOPBACK") != nullptr;
+  a.epsilon = p->epsilon;
+  const uint32_t kpl = p->K / 32, G = s0->G;
+  int rc = 1;
+  bool found = false;
+#define COLS_BETA_CASE(KPL_, G_) \
+  if (!found && kpl == KPL_ && G == G_) { found = true; rc = cols_beta_launch<KPL_, G_>(c, a, nv, s0->ws_ctas); }
+  COLS_BETA_CASE(4, 2) COLS_BETA_CASE(4, 4) COLS_BETA_CASE(4, 8)
+  COLS_BETA_CASE(8, 2) COLS_BETA_CASE(8, 4) COLS_BETA_CASE(8, 8)
+  COLS_BETA_CASE(16, 2) COLS_BETA_CASE(16, 4) COLS_BETA_CASE(16, 8)
+  COLS_BETA_CASE(32, 2) COLS_BETA_CASE(32, 4) COLS_BETA_CASE(32, 8)
+#undef COLS_BETA_CASE
+  AMMSB_REQUIRE(found, "unsupported (K, world) for the column layout");
+  if (rc) return rc;
+  ColsThetaArgs t;
+  memset(&t, 0, sizeof t);
+  for (uint32_t i = 0; i < nv; ++i) t.r[i] = a.r[i];
+  t.lay = s0->lay;
+  t.nv = nv;
+  t.G = G;
+  t.K = p->K;
+  t.P = a.ctas_per_rank;
+  t.eps_t = ammsb_eps_t(p, step_count);
+  t.eta0 = p->eta0;
+  t.eta1 = p->eta1;
+  t.scale = scale;
+  const uint32_t per_rank = (s0->KG + 127) / 128;
+  k_cols_theta<<<per_rank * nv, 128, 0, c->stream>>>(t);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int KPL, int G>
+static int cols_ppx_launch(ammsb_ctx* c, ColsPpxArgs& a, uint32_t nv, uint32_t ws_ctas) {
+  const uint32_t trips = (a.H + G - 1) / G;
+  uint32_t ctas = (trips + 3) / 4;
+  int occ = 0;
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cols_ppx<KPL, G>, 128, 0));
+  uint32_t cap = (uint32_t)c->sm_count * (uint32_t)occ / nv;
+  if (cap > ws_ctas) cap = ws_ctas;
+  if (ctas > cap) ctas = cap;
+  if (ctas == 0) ctas = 1;
+  a.ctas_per_rank = ctas;
+  a.nv = nv;
+  if (cols_launch_coop(c, k_cols_ppx<KPL, G>, a, ctas * nv, 128, 0)) return 1;
+  k_cols_ppx_reduce<<<nv, 128, 0, c->stream>>>(a, ctas);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ammsb_cols_perplexity(ammsb_ctx* c, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
+                                     ammsb_set* heldout, const uint64_t* d_edges, uint32_t H, uint32_t call_count,
+                                     double* h_sums /* [nv][4] or NULL */, double* h_avg /* [nv] or NULL */) {
+  if (cols_ready(ranks, nv)) return 1;
+  const ammsb_cols* s0 = ranks[0];
+  AMMSB_REQUIRE(p->K == s0->K && p->N == s0->N, "params do not match the store");
+  AMMSB_REQUIRE(H <= s0->Hcap, "more held-out pairs than the capacity the store was created with");
+  AMMSB_REQUIRE(call_count >= 1, "call_count is 1-based (perplexity.cc:252)");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ColsPpxArgs a;
+  memset(&a, 0, sizeof a);
+  for (uint32_t i = 0; i < nv; ++i) a.r[i] = ranks[i]->view(nullptr);
+  a.set = heldout->view();
+  a.lay = s0->lay;
+  a.edges = d_edges;
+  a.H = H;
+  a.parity = call_count & 1;
+  a.call_count = call_count;
+  a.loopback = getenv("AMMSB_COLS_LOOPBACK") != nullptr;
+  a.epsilon = p->epsilon;
+  const uint32_t kpl = p->K / 32, G = s0->G;
+  int rc = 1;
+  bool found = false;
+#define COLS_PPX_CASE(KPL_, G_) \
+  if (!found && kpl == KPL_ && G == G_) { found = true; rc = cols_ppx_launch<KPL_, G_>(c, a, nv, s0->ws_ctas); }
+  COLS_PPX_CASE(4, 2) COLS_PPX_CASE(4, 4) COLS_PPX_CASE(4, 8)
+  COLS_PPX_CASE(8, 2) COLS_PPX_CASE(8, 4) COLS_PPX_CASE(8, 8)
+  COLS_PPX_CASE(16, 2) COLS_PPX_CASE(16, 4) COLS_PPX_CASE(16, 8)
+  COLS_PPX_CASE(32, 2) COLS_PPX_CASE(32, 4) COLS_PPX_CASE(32, 8)
+#undef COLS_PPX_CASE
+  AMMSB_REQUIRE(found, "unsupported (K, world) for the column layout");
+  if (rc) return rc;
+  if (!h_sums && !h_avg) return 0;
+  for (uint32_t i = 0; i < nv; ++i) {
+    double sums[4];
+    rc = ammsb_d2h(c, sums, ranks[i]->d_ws_d + (size_t)a.ctas_per_rank * 4, sizeof sums);
+    if (rc) return rc;
+    if (h_sums) for (int q = 0; q < 4; ++q) h_sums[4 * i + q] = sums[q];
+    double avg = 0.0;  // perplexity.cc:264-273
+    if (sums[2] + sums[3] != 0) avg = (sums[0] + sums[1]) / (sums[2] + sums[3]);
+    if (h_avg) h_avg[i] = -avg;
+  }
+  return 0;
+}

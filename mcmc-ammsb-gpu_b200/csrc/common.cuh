@@ -289,6 +289,17 @@ __device__ __forceinline__ float eps_t_of(float a, float b, float c, uint32_t st
   return __fmul_rn(a, powf(__fadd_rn(1.0f, __fdiv_rn((float)step, b)), -c));
 }
 
+// The Langevin step of one phi element (phi.cc:266-274) as ONE expression with explicit FMA
+// contraction, shared by every production update_phi kernel (single-GPU and column-sharded), so
+// that they round identically: phi' = max(|phi + eps/2 (alpha - phi + N/n g) + sqrt(eps phi) xi|, 1e-24)
+__device__ __forceinline__ float phi_langevin(float pi_k, float phi_sum, float g, float noise, float half_eps,
+                                              float eps_t, float alpha, float Nn) {
+  const float phi_k = pi_k * phi_sum;
+  const float drift = fmaf(Nn, g, alpha - phi_k);
+  const float v = fmaf(sqrtf(eps_t * phi_k), noise, fmaf(half_eps, drift, phi_k));
+  return fmaxf(fabsf(v), 1e-24f);
+}
+
 // Butterfly all-reduce.  For every lane the result has the association of the
 // reference's WG_SUM tree with WG_SIZE 32 (sum.cc:20-29: aux[l] += aux[l+p2],
 // p2 = 16,8,4,2,1) because fp32 addition is commutative.

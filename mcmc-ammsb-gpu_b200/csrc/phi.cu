@@ -448,10 +448,7 @@ __global__ void __launch_bounds__((WARPS + NW) * 32)
         const uint32_t k = lane + 32 * i;
         if (EXACT || k < K) {
           const float noise = a.disable_noise ? 1.0f : s_noise[k];
-          const float phi_k = s_own[k] * phi_sum;
-          float v = fabsf(phi_k + half_eps * (a.alpha - phi_k + a.Nn * g[i]) +
-                          sqrtf(a.eps_t * phi_k) * noise);
-          v = fmaxf(v, 1e-24f);
+          const float v = phi_langevin(s_own[k], phi_sum, g[i], noise, half_eps, a.eps_t, a.alpha, a.Nn);
           out[k] = v;
           lsum += v;
         }
@@ -687,9 +684,7 @@ __global__ void __launch_bounds__(192) k_update_phi_team(const __grid_constant__
       const uint32_t kk = lane + 32 * i;
       if (EXACT || kk < KS) {
         const float noise = a.disable_noise ? 1.0f : nz[kk];
-        const float phi_k = s_own[kk] * phi_sum;
-        float v = fabsf(phi_k + half_eps * (a.alpha - phi_k + a.Nn * g[i]) + sqrtf(a.eps_t * phi_k) * noise);
-        v = fmaxf(v, 1e-24f);
+        const float v = phi_langevin(s_own[kk], phi_sum, g[i], noise, half_eps, a.eps_t, a.alpha, a.Nn);
         out[kk] = v;
         lsum += v;
       }
@@ -843,9 +838,7 @@ __global__ void __launch_bounds__((WPS + 1) * 32) k_update_phi_split(const __gri
 #pragma unroll
     for (int w = 0; w < WPS; ++w) gk += s_stage_all[(size_t)w * R * K + k];
     const float noise = a.disable_noise ? 1.0f : s_noise[k];
-    const float phi_k = s_own[k] * phi_sum;
-    float v = fabsf(phi_k + half_eps * (a.alpha - phi_k + a.Nn * gk) + sqrtf(a.eps_t * phi_k) * noise);
-    v = fmaxf(v, 1e-24f);
+    const float v = phi_langevin(s_own[k], phi_sum, gk, noise, half_eps, a.eps_t, a.alpha, a.Nn);
     out[k] = v;
     s_noise[k] = v;  // this thread's own column: no other reader of the noise value
   }

@@ -137,6 +137,18 @@ int vmm_import_fd(int device, int fd, size_t bytes, VmmAlloc* out) {
   return 0;
 }
 
+int vmm_grant(int device, const VmmAlloc& a) {
+  Driver* d = GetDriver();
+  AMMSB_REQUIRE(d != nullptr, "CUDA virtual-memory-management driver API is not available");
+  CUmemAccessDesc acc;
+  memset(&acc, 0, sizeof acc);
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  VMM_CHECK(d->memSetAccess(a.ptr, a.size, &acc, 1));
+  return 0;
+}
+
 int vmm_free(VmmAlloc* a) {
   Driver* d = GetDriver();
   if (!d || !a->ptr) return 0;

@@ -15,5 +15,7 @@ size_t vmm_rounded_size(int device, size_t bytes, size_t* granularity);
 int vmm_alloc(int device, size_t bytes, VmmAlloc* out);
 int vmm_export_fd(const VmmAlloc& a, int* fd);
 int vmm_import_fd(int device, int fd, size_t bytes, VmmAlloc* out);
+// same process: let another device of this process access the mapping (direct peer access)
+int vmm_grant(int device, const VmmAlloc& a);
 int vmm_free(VmmAlloc* a);
 #endif

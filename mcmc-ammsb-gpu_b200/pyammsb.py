@@ -498,3 +498,122 @@ class Store:
         if self.h is not None:
             lib().ammsb_store_destroy(self.h)
             self.h = None
+
+
+# ------------------------------------------------------------ column-sharded layout ----
+def cols_local_index(k, G):
+    """local float index of global column k on its owner rank (k % 32) % G -- csrc/cols.cu"""
+    k = np.asarray(k)
+    l, i = k & 31, k >> 5
+    return ((i >> 2) * (32 // G) + l // G) * 4 + (i & 3)
+
+
+def cols_owner(k, G):
+    return (np.asarray(k) & 31) % G
+
+
+class Cols:
+    """one rank's share of the column-sharded pi (csrc/cols.cu): the columns of the reference
+    work-items l = rank (mod world), as [N][K/world], plus the mailbox the peers write into"""
+
+    def __init__(self, ctx, N, K, world, rank, n, max_nodes, max_edges, max_pairs):
+        h = C.c_void_p()
+        _ck(lib().ammsb_cols_create(ctx.h, C.c_uint64(N), K, world, rank, n, max_nodes, max_edges,
+                                    C.c_uint64(max_pairs), C.byref(h)))
+        self.h, self.ctx, self.N, self.K, self.world, self.rank = h, ctx, N, K, world, rank
+
+    def export_fd(self):
+        fd = C.c_int(-1)
+        _ck(lib().ammsb_cols_export_fd(self.h, C.byref(fd)))
+        return fd.value
+
+    def attach_fd(self, peer_rank, fd):
+        _ck(lib().ammsb_cols_attach_fd(self.h, peer_rank, fd))
+
+    def attach_local(self, peer):
+        _ck(lib().ammsb_cols_attach_local(self.h, peer.rank, peer.h))
+
+    def mailbox_bytes(self):
+        n = C.c_size_t(0)
+        _ck(lib().ammsb_cols_mailbox_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def init_pi(self, eta0=1.0, eta1=1.0):
+        _ck(lib().ammsb_cols_init_pi(self.h, C.c_float(eta0), C.c_float(eta1)))
+
+    def write_pi(self, arr, row0=0):
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1, self.K)
+        _ck(lib().ammsb_cols_write_pi(self.h, C.c_uint64(row0), C.c_uint64(arr.shape[0]), _p(arr)))
+
+    def read_pi(self, out, row0=0):
+        """fills the columns this rank owns into out[nrows, K] (other columns untouched)"""
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape[1] == self.K
+        _ck(lib().ammsb_cols_read_pi(self.h, C.c_uint64(row0), C.c_uint64(out.shape[0]), _p(out)))
+        return out
+
+    def write_phi(self, arr, row0=0):
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        _ck(lib().ammsb_cols_write_phi(self.h, C.c_uint64(row0), C.c_uint64(arr.size), _p(arr)))
+
+    def read_phi(self, row0=0, nrows=None):
+        out = np.empty(self.N if nrows is None else nrows, dtype=np.float32)
+        _ck(lib().ammsb_cols_read_phi(self.h, C.c_uint64(row0), C.c_uint64(out.size), _p(out)))
+        return out
+
+    def write_theta(self, theta, beta):
+        theta = np.ascontiguousarray(theta, dtype=np.float32)
+        beta = np.ascontiguousarray(beta, dtype=np.float32)
+        assert theta.size == 2 * self.K and beta.size == 2 * self.K
+        _ck(lib().ammsb_cols_write_theta(self.h, _p(theta), _p(beta)))
+
+    def read_theta(self):
+        theta, beta = np.empty(2 * self.K, np.float32), np.empty(2 * self.K, np.float32)
+        _ck(lib().ammsb_cols_read_theta(self.h, _p(theta), _p(beta)))
+        return theta, beta
+
+    def beta_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _ck(lib().ammsb_cols_beta_ptr(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def read_phi_vec(self, out):
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape[1] == self.K
+        _ck(lib().ammsb_cols_read_phi_vec(self.h, out.shape[0], _p(out)))
+        return out
+
+    def check(self):
+        t = C.c_uint32(0)
+        _ck(lib().ammsb_cols_check(self.h, C.byref(t)))
+        if t.value:
+            raise AmmsbError("rank %d: a column-layout exchange wait timed out" % self.rank)
+
+    def free(self):
+        if self.h is not None:
+            lib().ammsb_cols_destroy(self.h)
+            self.h = None
+
+
+def _handles(objs):
+    return (C.c_void_p * len(objs))(*[o.h if o is not None else None for o in objs])
+
+
+def cols_update_phi(ctx, ranks, p, opts, train, d_nodes, d_neighbors, V, step, pools):
+    _ck(lib().ammsb_cols_update_phi(ctx.h, _handles(ranks), len(ranks), C.byref(p), C.byref(opts), train.h,
+                                    d_nodes.ptr, d_neighbors.ptr, V, step, _handles(pools)))
+
+
+def cols_update_pi(ctx, ranks, d_nodes, V, step):
+    _ck(lib().ammsb_cols_update_pi(ctx.h, _handles(ranks), len(ranks), d_nodes.ptr, V, step))
+
+
+def cols_update_beta(ctx, ranks, p, train, d_edges, E_mb, scale, step, pools):
+    _ck(lib().ammsb_cols_update_beta(ctx.h, _handles(ranks), len(ranks), C.byref(p), train.h, d_edges.ptr, E_mb,
+                                     C.c_float(scale), step, _handles(pools)))
+
+
+def cols_perplexity(ctx, ranks, p, heldout, d_edges, H, call_count, want=True):
+    nv = len(ranks)
+    sums, avg = np.zeros((nv, 4), np.float64), np.zeros(nv, np.float64)
+    _ck(lib().ammsb_cols_perplexity(ctx.h, _handles(ranks), nv, C.byref(p), heldout.h, d_edges.ptr, H, call_count,
+                                    _p(sums) if want else None, _p(avg) if want else None))
+    return avg, sums
