@@ -322,6 +322,10 @@ int ammsb_cols_mailbox_bytes(const ammsb_cols* cols, size_t* bytes);
 int ammsb_cols_export_fd(ammsb_cols* cols, int* fd);
 int ammsb_cols_attach_fd(ammsb_cols* cols, uint32_t peer_rank, int fd);
 int ammsb_cols_attach_local(ammsb_cols* cols, uint32_t peer_rank, ammsb_cols* peer);
+/* timing diagnostics only (with AMMSB_COLS_LOOPBACK=1 in the environment the kernels neither
+ * send to nor wait for a peer): unattached peer mailboxes alias the own one, so that one rank's
+ * share of a step can be timed on one GPU; the results of such a run are meaningless */
+int ammsb_cols_alias_self(ammsb_cols* cols);
 int ammsb_cols_init_pi(ammsb_cols* cols, float eta0, float eta1); /* random.cc:131-167 */
 /* host access in the reference's layout: full rows [nrows][K]; write scatters the columns this
  * rank owns, read fills them in and leaves the other columns of h_rows untouched */

@@ -205,6 +205,16 @@ struct ColsPhiSmem {
   }
 };
 
+// One cursor over this warp's stages.  The three cursors of k_cols_phi (LOAD, phase A, phase B)
+// walk the same sequence -- the warp's live group-passes in (group, pass) order, n stages each --
+// at fixed distances; everything a stage needs is kept incrementally (no divisions per stage).
+struct ColsCursor {
+  uint32_t group, pass;  // current group-pass; group >= ngroups: exhausted
+  uint32_t j;            // neighbor index within the group-pass
+  uint32_t buf;          // ring buffer of the stage (stage number mod R)
+  uint32_t meta;         // metadata buffer of the current segment (segment number mod MB)
+};
+
 template <int KPL, int G>
 __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ ColsPhiArgs a) {
   using SM = ColsPhiSmem<KPL, G>;
@@ -213,9 +223,12 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const uint32_t sub = lane / LPG, li = lane % LPG;
   const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
-  const ColsRankView& me = a.r[vr];
-  const uint32_t rank = me.rank;
+  const uint32_t rank = a.r[vr].rank;
   const uint32_t n = a.n, R = a.R, D = a.D, MB = a.MB;
+  float* const my_pi = a.r[vr].pi;
+  const float* const my_phi = a.r[vr].phi;
+  float* const my_vec = a.r[vr].phi_vec;
+  ulonglong2* const my_pool = a.r[vr].pool;
 
   // ---- shared memory: ziggurat tables | per warp: ring, own pieces, metadata, self partials, barriers
   uint32_t* s_zig = reinterpret_cast<uint32_t*>(s_raw);
@@ -235,10 +248,28 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
   }
   __syncthreads();
 
-  unsigned char* mybox = me.box[rank];
+  unsigned char* mybox = a.r[vr].box[rank];
   uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
   const float* beta = reinterpret_cast<const float*>(mybox + a.lay.beta);
   const size_t half_S = (size_t)a.parity * G * a.lay.S_src, half_R = (size_t)a.parity * G * a.lay.R_src;
+  // mailbox words this lane writes (its sub-group's partial to the ranks p = li, li + LPG) and reads
+  uint32_t* send0 = nullptr;
+  uint32_t* send1 = nullptr;
+  uint32_t* poll0 = nullptr;
+  uint32_t* poll1 = nullptr;
+  if (li < G) {
+    if (li != rank && !a.loopback) {
+      send0 = reinterpret_cast<uint32_t*>(a.r[vr].box[li] + a.lay.S + half_S + (size_t)rank * a.lay.S_src);
+      poll0 = reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)li * a.lay.S_src);
+    }
+  }
+  if (G > LPG) {
+    const uint32_t p1 = li + LPG;
+    if (p1 != rank && !a.loopback) {
+      send1 = reinterpret_cast<uint32_t*>(a.r[vr].box[p1] + a.lay.S + half_S + (size_t)rank * a.lay.S_src);
+      poll1 = reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p1 * a.lay.S_src);
+    }
+  }
 
   // f_k = beta_k - epsilon for the thread's columns k = l + 32 i, l = rank + G li  (phi.cc:237-239)
   const uint32_t l_ref = rank + G * li;
@@ -253,51 +284,61 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
   const uint32_t ngroups = (active_units + G - 1) / G;
   const uint32_t passes = (a.V + a.units - 1) / a.units;
   const uint32_t gwarp = cta * warps + wib, total_warps = a.ctas_per_rank * warps;
-  const uint32_t my_groups = ngroups > gwarp ? (ngroups - gwarp + total_warps - 1) / total_warps : 0;
-  const uint32_t X = my_groups * passes;  // group-passes of this warp, in order (group, pass)
-  const uint32_t T = X * n;               // stages (trips): stage t = group-pass t / n, neighbor t % n
-  const uint32_t nseg = (n + 31) / 32;
 
-  // slot of (group-pass x, sub-group s); 0xffffffff when the sub-group is idle there
-  auto slot_of = [&](uint32_t x, uint32_t s) -> uint32_t {
-    const uint32_t group = gwarp + (x / passes) * total_warps, pass = x % passes;
+  // a group-pass with no live slot is skipped by every cursor (slot of sub-group 0 is its smallest)
+  auto gp_live = [&](uint32_t group, uint32_t pass) -> bool {
+    return group < ngroups && (size_t)group * G + (size_t)pass * a.units < a.V;
+  };
+  auto next_gp = [&](uint32_t& group, uint32_t& pass) {
+    do {
+      if (++pass == passes) {
+        pass = 0;
+        group += total_warps;
+      }
+    } while (group < ngroups && !gp_live(group, pass));
+  };
+  auto step_cursor = [&](ColsCursor& c) {  // one stage on
+    if (++c.buf == R) c.buf = 0;
+    if (++c.j == n) {
+      c.j = 0;
+      next_gp(c.group, c.pass);
+      if (++c.meta == MB) c.meta = 0;
+    } else if ((c.j & 31) == 0) {
+      if (++c.meta == MB) c.meta = 0;
+    }
+  };
+  auto slot_of = [&](uint32_t group, uint32_t pass, uint32_t s) -> uint32_t {
     const uint32_t unit = group * G + s;
     const uint32_t slot = unit + pass * a.units;
     return (unit < active_units && slot < a.V) ? slot : 0xffffffffu;
   };
-  auto gpi_of = [&](uint32_t x) -> uint32_t {  // global group-pass id: the mailbox index
-    return (gwarp + (x / passes) * total_warps) * passes + x % passes;
-  };
-  auto meta_of = [&](uint32_t x, uint32_t seg) -> uint32_t* {
-    return s_meta + (size_t)((x * nseg + seg) % MB) * (SM::META / 4);
-  };
 
   // metadata of a segment (<= 32 neighbors of the G slots of a group-pass): neighbor ids, the
   // cuckoo answers y (phi.cc:230-234), slot / node / phi_sum of every sub-group
-  auto prep_segment = [&](uint32_t x, uint32_t seg) {
-    uint32_t* m = meta_of(x, seg);
+  auto prep_segment = [&](const ColsCursor& c) {
+    uint32_t* m = s_meta + (size_t)c.meta * (SM::META / 4);
     uint32_t* m_nb = m;
     uint32_t* m_y = m + G * 32;
     uint32_t* m_slot = m_y + G;
     uint32_t* m_node = m_slot + G;
     float* m_phi = reinterpret_cast<float*>(m_node + G);
-    const uint32_t j0 = seg * 32, cnt = min(32u, n - j0);
+    const uint32_t j0 = c.j, cnt = min(32u, n - j0);
     uint32_t my_node = 0;
     if (lane < G) {
-      const uint32_t slot = slot_of(x, lane);
+      const uint32_t slot = slot_of(c.group, c.pass, lane);
       m_slot[lane] = slot;
       if (slot != 0xffffffffu) {
         my_node = __ldg(&a.nodes[slot]);
         m_node[lane] = my_node;
-        m_phi[lane] = me.phi[my_node];
+        m_phi[lane] = my_phi[my_node];
       } else {
         m_node[lane] = 0;
         m_phi[lane] = 1.0f;
       }
     }
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < G; ++s) {
-      const uint32_t slot = slot_of(x, s);  // warp-uniform
+      const uint32_t slot = slot_of(c.group, c.pass, s);  // warp-uniform
       const uint32_t node = __shfl_sync(FULL_MASK, my_node, s);
       bool y = false;
       uint32_t nb = 0;
@@ -312,152 +353,76 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
     __syncwarp();
   };
 
-  // LOAD(t): request the G neighbor pieces of stage t (and, at j = 0, the own pieces of the group-pass)
-  auto load_stage = [&](uint32_t t) {
-    const uint32_t x = t / n, j = t % n;
-    if ((j & 31) == 0) prep_segment(x, j >> 5);
-    const uint32_t* m = meta_of(x, j >> 5);
-    const uint32_t slot = m[G * 32 + G + sub];
-    const uint32_t act = __ballot_sync(FULL_MASK, slot != 0xffffffffu && li == 0);
-    const uint32_t nact = __popc(act);
-    const uint32_t b = t % R;
-    if (j == 0) {
-      if (lane == 0) mbar_expect_tx(&bars[R], nact * SM::PIECE);
-      __syncwarp();
-      if (li == 0 && slot != 0xffffffffu)
-        bulk_g2s(s_own + (size_t)sub * KG, me.pi + (size_t)m[G * 32 + 2 * G + sub] * KG, SM::PIECE, &bars[R]);
-    }
-    if (lane == 0) mbar_expect_tx(&bars[b], nact * SM::PIECE);
-    __syncwarp();
-    if (li == 0 && slot != 0xffffffffu) {
-      const uint32_t nb = m[sub * 32 + (j & 31)];
-      bulk_g2s(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE, me.pi + (size_t)nb * KG, SM::PIECE, &bars[b]);
-    }
-  };
+  ColsCursor cl, ca, cb;  // LOAD, phase A, phase B
+  cl.group = gwarp;
+  cl.pass = 0;
+  cl.j = cl.buf = cl.meta = 0;
+  if (cl.group < ngroups && !gp_live(cl.group, 0)) next_gp(cl.group, cl.pass);
+  ca = cb = cl;
 
   float ownA[KPL], ownB[KPL], g[KPL];
 #pragma unroll
   for (int i = 0; i < KPL; ++i) ownA[i] = ownB[i] = g[i] = 0.f;
   Rng st;
   st.x = st.y = 0;
-  uint32_t own_phase = 0;
+  uint32_t own_phase = 0, ring_phase = 0;  // parities to wait on (bit b: stage buffer b)
+  // per-segment / per-group-pass state of the A and B sides
+  uint32_t ymaskA = 0, ymaskB = 0, slotB = 0xffffffffu;
+  bool liveA = false, liveB = false;
+  float phi_sumB = 1.0f, rphiB = 1.0f;
+  size_t sidxA = 0, sidxB = 0;  // mailbox index of (group-pass, j = 0, sub)
 
-  for (uint32_t t = 0; t < R && t < T; ++t) load_stage(t);
-
-  for (uint32_t it = 0; it < T + D; ++it) {
-    // ------------------------------------------------------------ phase B of stage it - D ----
-    if (it >= D) {
-      const uint32_t t = it - D, x = t / n, j = t % n, b = t % R;
-      const uint32_t* m = meta_of(x, j >> 5);
-      const uint32_t slot = m[G * 32 + G + sub];
-      const bool live = slot != 0xffffffffu;
-      const float phi_sum = __uint_as_float(m[G * 32 + 3 * G + sub]);
-      const bool y = (m[G * 32 + sub] >> (j & 31)) & 1;
-      if (j == 0) {  // the B side enters group-pass x: A is still inside it (D < n)
+  for (int it = (int)D - (int)R;; ++it) {
+    // ------------------------------------------------------- phase B of the stage D trips back ----
+    if (it >= (int)D) {
+      if (cb.group >= ngroups) break;
+      const uint32_t j = cb.j, b = cb.buf;
+      if ((j & 31) == 0) {
+        const uint32_t* m = s_meta + (size_t)cb.meta * (SM::META / 4);
+        ymaskB = m[G * 32 + sub];
+        if (j == 0) {  // the B side enters a group-pass: A is still inside it (D < n)
+          slotB = m[G * 32 + G + sub];
+          liveB = slotB != 0xffffffffu;
+          phi_sumB = __uint_as_float(m[G * 32 + 3 * G + sub]);
+          rphiB = 1.0f / phi_sumB;
+          sidxB = ((size_t)cb.group * passes + cb.pass) * n * G + sub;
 #pragma unroll
-        for (int i = 0; i < KPL; ++i) {
-          ownB[i] = ownA[i];
-          g[i] = 0.f;
-        }
-        if (x % passes == 0 && !a.disable_noise) {  // a new group: its units' RNG states
-          const uint32_t s0 = slot_of(x, sub);      // pass 0 slot == unit
-          if (s0 != 0xffffffffu) st = rng_load(me.pool, (uint64_t)s0 * 32 + l_ref);
+          for (int i = 0; i < KPL; ++i) {
+            ownB[i] = ownA[i];
+            g[i] = 0.f;
+          }
+          if (cb.pass == 0 && !a.disable_noise) {  // a new group: its units' RNG states (pass 0: slot == unit)
+            const uint32_t unit = cb.group * G + sub;
+            if (unit < active_units) st = rng_load(my_pool, (uint64_t)unit * 32 + l_ref);
+          }
         }
       }
+      const bool y = (ymaskB >> (j & 31)) & 1;
       // the G partials of (slot, j): own from the ring, the peers' from the mailbox
-      const size_t idx = ((size_t)gpi_of(x) * n + j) * G + sub;
       const float mine = s_self[b * G + sub];
-      float v0 = 0.f, v1 = 0.f;
-      if (live) {
-        if (li < G) {
-          v0 = (li == rank || a.loopback)
-                   ? mine
-                   : poll_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)li * a.lay.S_src) + idx, err);
-        }
-        if (G > LPG) {
-          const uint32_t p1 = li + LPG;
-          v1 = (p1 == rank || a.loopback)
-                   ? mine
-                   : poll_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p1 * a.lay.S_src) + idx, err);
-        }
+      float v0 = (li < G) ? mine : 0.f, v1 = (G > LPG) ? mine : 0.f;
+      if (liveB) {
+        const size_t idx = sidxB + (size_t)j * G;
+        if (poll0) v0 = poll_mbox(poll0 + idx, err);
+        if (G > LPG && poll1) v1 = poll_mbox(poll1 + idx, err);
       }
       const float S = cols_rank_tree<G>(v0, v1, lane);
       // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
-      const float inv = 1.0f / (S * phi_sum);
-      const float rphi = 1.0f / phi_sum;
-      const float e = y ? e_link : e_non;
-      const uint32_t sgn = y ? 0u : 0x80000000u;
+      const float inv = 1.0f / (S * phi_sumB);
+      const float nrphi = -rphiB;
       const float4* row = reinterpret_cast<const float4*>(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE);
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const float4 r4 = row[q * LPG + li];
-        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int i = 4 * q + c;
-          const float tk = fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e);
-          g[i] += fmaf(tk, inv, -rphi);
-        }
-      }
-      __syncwarp();  // every lane is done with stage buffer b
-      if (j == n - 1) {
-        // ---- Langevin step of the group-pass (phi.cc:266-274), noise in the state's draw order ----
-        float* out = me.phi_vec + (size_t)(live ? slot : 0) * KG;
-        float lsum = 0.f;
+      if (!__any_sync(FULL_MASK, y)) {  // no training link among the G pairs (the usual case)
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          float o[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int i = 4 * q + c;
-            const float noise = (a.disable_noise || !live) ? 1.0f : rng_randn_t(st, zig);
-            o[c] = phi_langevin(ownB[i], phi_sum, g[i], noise, half_eps, a.eps_t, a.alpha, a.Nn);
-            lsum += o[c];
-          }
-          if (live) *reinterpret_cast<float4*>(out + (size_t)(q * LPG + li) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+          const float4 r4 = row[q * LPG + li];
+          g[4 * q] += fmaf(fmaf(r4.x, -fb[4 * q], e_non), inv, nrphi);
+          g[4 * q + 1] += fmaf(fmaf(r4.y, -fb[4 * q + 1], e_non), inv, nrphi);
+          g[4 * q + 2] += fmaf(fmaf(r4.z, -fb[4 * q + 2], e_non), inv, nrphi);
+          g[4 * q + 3] += fmaf(fmaf(r4.w, -fb[4 * q + 3], e_non), inv, nrphi);
         }
-#pragma unroll
-        for (int o = LPG / 2; o > 0; o >>= 1) lsum += __shfl_xor_sync(FULL_MASK, lsum, o);
-        // this rank's partial row sum to every rank (its own mailbox included): update_pi reads them
-        if (live) {
-          const size_t ridx = (size_t)gpi_of(x) * G + sub;
-          const uint32_t bits = partial_bits(lsum);
-          for (uint32_t p = li; p < G; p += LPG)  // loopback: all G source regions of the own mailbox
-            st_mbox(reinterpret_cast<uint32_t*>(me.box[a.loopback ? rank : p] + a.lay.R + half_R +
-                                                (size_t)(a.loopback ? p : rank) * a.lay.R_src) + ridx,
-                    bits);
-        }
-        if (x % passes == passes - 1 && !a.disable_noise) {  // the group is finished: persist its states
-          const uint32_t s0 = slot_of(x - (passes - 1), sub);
-          if (s0 != 0xffffffffu) rng_store(me.pool, (uint64_t)s0 * 32 + l_ref, st);
-        }
-      }
-      if (t + R < T) load_stage(t + R);
-    }
-    // ---------------------------------------------------------------- phase A of stage it ----
-    if (it < T) {
-      const uint32_t t = it, x = t / n, j = t % n, b = t % R;
-      const uint32_t* m = meta_of(x, j >> 5);
-      const uint32_t slot = m[G * 32 + G + sub];
-      const bool live = slot != 0xffffffffu;
-      const bool y = (m[G * 32 + sub] >> (j & 31)) & 1;
-      if (j == 0) {  // own pieces of the group-pass into registers
-        mbar_wait(&bars[R], own_phase);
-        own_phase ^= 1;
-        const float4* o4 = reinterpret_cast<const float4*>(s_own + (size_t)sub * KG);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const float4 v = live ? o4[q * LPG + li] : make_float4(0.f, 0.f, 0.f, 0.f);
-          ownA[4 * q] = v.x; ownA[4 * q + 1] = v.y; ownA[4 * q + 2] = v.z; ownA[4 * q + 3] = v.w;
-        }
-        __syncwarp();  // s_own may be refilled by the next group-pass's request
-      }
-      mbar_wait(&bars[b], (t / R) & 1);
-      const float e = y ? e_link : e_non;
-      const uint32_t sgn = y ? 0u : 0x80000000u;
-      const float4* row = reinterpret_cast<const float4*>(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE);
-      float S = 0.f;
-      if (live) {
+      } else {
+        const float e = y ? e_link : e_non;
+        const uint32_t sgn = y ? 0u : 0x80000000u;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const float4 r4 = row[q * LPG + li];
@@ -465,8 +430,113 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int i = 4 * q + c;
-            const float tk = fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e);
-            S = fmaf(ownA[i], tk, S);
+            g[i] += fmaf(fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e), inv, nrphi);
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with stage buffer b
+      if (j == n - 1) {
+        // ---- Langevin step of the group-pass (phi.cc:266-274), noise in the state's draw order ----
+        float* out = my_vec + (size_t)(liveB ? slotB : 0) * KG;
+        float lsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          float o[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = 4 * q + c;
+            const float noise = (a.disable_noise || !liveB) ? 1.0f : rng_randn_t(st, zig);
+            o[c] = phi_langevin(ownB[i], phi_sumB, g[i], noise, half_eps, a.eps_t, a.alpha, a.Nn);
+            lsum += o[c];
+          }
+          if (liveB) *reinterpret_cast<float4*>(out + (size_t)(q * LPG + li) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+#pragma unroll
+        for (int o = LPG / 2; o > 0; o >>= 1) lsum += __shfl_xor_sync(FULL_MASK, lsum, o);
+        // this rank's partial row sum to every rank (its own mailbox included): update_pi reads them
+        if (liveB) {
+          const size_t ridx = ((size_t)cb.group * passes + cb.pass) * G + sub;
+          const uint32_t bits = partial_bits(lsum);
+          for (uint32_t p = li; p < G; p += LPG)  // loopback: all G source regions of the own mailbox
+            st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[a.loopback ? rank : p] + a.lay.R + half_R +
+                                                (size_t)(a.loopback ? p : rank) * a.lay.R_src) + ridx,
+                    bits);
+        }
+        uint32_t ng = cb.group, np = cb.pass;
+        next_gp(ng, np);
+        if (ng != cb.group && !a.disable_noise) {  // the group is finished: persist its states
+          const uint32_t unit = cb.group * G + sub;
+          if (unit < active_units) rng_store(my_pool, (uint64_t)unit * 32 + l_ref, st);
+        }
+      }
+      step_cursor(cb);
+    }
+    // ------------------------------------------------- LOAD of the stage R - D trips ahead of A ----
+    if (cl.group < ngroups) {
+      const uint32_t j = cl.j, b = cl.buf;
+      if ((j & 31) == 0) prep_segment(cl);
+      const uint32_t* m = s_meta + (size_t)cl.meta * (SM::META / 4);
+      const uint32_t slot = m[G * 32 + G + sub];
+      const bool issue = slot != 0xffffffffu && li == 0;
+      const uint32_t nact = __popc(__ballot_sync(FULL_MASK, issue));
+      if (j == 0) {  // the own pieces of the group-pass
+        if (lane == 0) mbar_expect_tx(&bars[R], nact * SM::PIECE);
+        __syncwarp();
+        if (issue) bulk_g2s(s_own + (size_t)sub * KG, my_pi + (size_t)m[G * 32 + 2 * G + sub] * KG, SM::PIECE, &bars[R]);
+      }
+      if (lane == 0) mbar_expect_tx(&bars[b], nact * SM::PIECE);
+      __syncwarp();
+      if (issue) {
+        const uint32_t nb = m[sub * 32 + (j & 31)];
+        bulk_g2s(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE, my_pi + (size_t)nb * KG, SM::PIECE, &bars[b]);
+      }
+      step_cursor(cl);
+    }
+    // ---------------------------------------------------------------------------- phase A ----
+    if (it >= 0 && ca.group < ngroups) {
+      const uint32_t j = ca.j, b = ca.buf;
+      if ((j & 31) == 0) {
+        const uint32_t* m = s_meta + (size_t)ca.meta * (SM::META / 4);
+        ymaskA = m[G * 32 + sub];
+        if (j == 0) {  // own pieces of the group-pass into registers
+          liveA = m[G * 32 + G + sub] != 0xffffffffu;
+          sidxA = ((size_t)ca.group * passes + ca.pass) * n * G + sub;
+          mbar_wait(&bars[R], own_phase);
+          own_phase ^= 1;
+          const float4* o4 = reinterpret_cast<const float4*>(s_own + (size_t)sub * KG);
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const float4 v = liveA ? o4[q * LPG + li] : make_float4(0.f, 0.f, 0.f, 0.f);
+            ownA[4 * q] = v.x; ownA[4 * q + 1] = v.y; ownA[4 * q + 2] = v.z; ownA[4 * q + 3] = v.w;
+          }
+          __syncwarp();  // s_own may be refilled by the next group-pass's request
+        }
+      }
+      const bool y = (ymaskA >> (j & 31)) & 1;
+      mbar_wait(&bars[b], (ring_phase >> b) & 1);
+      ring_phase ^= 1u << b;
+      const float4* row = reinterpret_cast<const float4*>(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE);
+      float S = 0.f;
+      if (!__any_sync(FULL_MASK, y)) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float4 r4 = row[q * LPG + li];
+          S = fmaf(ownA[4 * q], fmaf(r4.x, -fb[4 * q], e_non), S);
+          S = fmaf(ownA[4 * q + 1], fmaf(r4.y, -fb[4 * q + 1], e_non), S);
+          S = fmaf(ownA[4 * q + 2], fmaf(r4.z, -fb[4 * q + 2], e_non), S);
+          S = fmaf(ownA[4 * q + 3], fmaf(r4.w, -fb[4 * q + 3], e_non), S);
+        }
+      } else {
+        const float e = y ? e_link : e_non;
+        const uint32_t sgn = y ? 0u : 0x80000000u;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float4 r4 = row[q * LPG + li];
+          const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = 4 * q + c;
+            S = fmaf(ownA[i], fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e), S);
           }
         }
       }
@@ -474,14 +544,14 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
 #pragma unroll
       for (int o = LPG / 2; o > 0; o >>= 1) S += __shfl_xor_sync(FULL_MASK, S, o);
       if (li == 0) s_self[b * G + sub] = S;
-      if (live && !a.loopback) {
-        const size_t idx = ((size_t)gpi_of(x) * n + j) * G + sub;
+      if (liveA) {
+        const size_t idx = sidxA + (size_t)j * G;
         const uint32_t bits = partial_bits(S);
-        for (uint32_t p = li; p < G; p += LPG)
-          if (p != rank)
-            st_mbox(reinterpret_cast<uint32_t*>(me.box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + idx, bits);
+        if (send0) st_mbox(send0 + idx, bits);
+        if (G > LPG && send1) st_mbox(send1 + idx, bits);
       }
       __syncwarp();
+      step_cursor(ca);
     }
   }
 }
@@ -1000,6 +1070,15 @@ extern "C" int ammsb_cols_attach_local(ammsb_cols* s, uint32_t peer_rank, ammsb_
     if (vmm_grant(s->ctx->device, peer->local)) return 1;
   }
   s->box[peer_rank] = peer->box[peer_rank];
+  return 0;
+}
+
+// timing diagnostics (AMMSB_COLS_LOOPBACK=1: the kernels then neither send to nor wait for a peer):
+// every unattached peer mailbox pointer becomes an alias of the own mailbox, so that ONE rank's
+// share of a G-GPU step can be timed on one GPU.  Results of such a run are meaningless.
+extern "C" int ammsb_cols_alias_self(ammsb_cols* s) {
+  for (uint32_t p = 0; p < s->G; ++p)
+    if (s->box[p] == nullptr) s->box[p] = s->box[s->rank];
   return 0;
 }
 

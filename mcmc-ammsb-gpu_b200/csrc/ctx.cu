@@ -206,6 +206,11 @@ SetView ammsb_set::view() const {
   v.num_bins = num_bins;
   v.p1 = kSetPrimes[prime_idx][0];
   v.p2 = kSetPrimes[prime_idx][1];
+  // ceil(2^128 / num_bins) for the divide-free exact remainder (set_mod, common.cuh); wraps to 0
+  // for num_bins == 1, for which the remainder formula then yields 0 as it should
+  const unsigned __int128 m = ~static_cast<unsigned __int128>(0) / num_bins + 1;
+  v.m_hi = static_cast<uint64_t>(m >> 64);
+  v.m_lo = static_cast<uint64_t>(m);
   return v;
 }
 

@@ -533,6 +533,10 @@ class Cols:
     def attach_local(self, peer):
         _ck(lib().ammsb_cols_attach_local(self.h, peer.rank, peer.h))
 
+    def alias_self(self):
+        """timing diagnostics only (AMMSB_COLS_LOOPBACK): every unattached peer mailbox = the own one"""
+        _ck(lib().ammsb_cols_alias_self(self.h))
+
     def mailbox_bytes(self):
         n = C.c_size_t(0)
         _ck(lib().ammsb_cols_mailbox_bytes(self.h, C.byref(n)))
