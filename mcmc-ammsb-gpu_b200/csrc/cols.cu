@@ -75,6 +75,8 @@ struct ammsb_cols {
   uint64_t Hcap = 0;
   uint32_t KG = 0;
   float *d_pi = nullptr, *d_phi = nullptr, *d_phi_vec = nullptr, *d_ppx = nullptr, *d_ws = nullptr;
+  float* d_nz = nullptr;  // Langevin noise rows of the groups in flight: [resident warps][G][KG]
+  size_t nz_warps = 0;
   double* d_ws_d = nullptr;
   ColsBoxLayout lay;
   VmmAlloc local, remote[AMMSB_MAX_SHARDS];
@@ -156,6 +158,29 @@ __device__ __forceinline__ float poll_mbox(uint32_t* p, uint32_t* err) {
   return __uint_as_float(v);
 }
 
+// 16-byte asynchronous copy global -> shared (L1 bypassed) and its completion on an mbarrier
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one attempt at a mailbox word (sentinel = not there yet)
+__device__ __forceinline__ uint32_t peek_mbox(const uint32_t* p) { return ld_mbox(p); }
+// finish a poll whose first attempt returned `v`; re-arms the word
+__device__ __forceinline__ float finish_poll(uint32_t* p, uint32_t v, uint32_t* err) {
+  uint32_t spins = 0;
+  while (v == COLS_SENTINEL) {
+    if (++spins > COLS_SPIN_LIMIT) {
+      atomicExch(err, 1u);
+      break;
+    }
+    v = ld_mbox(p);
+  }
+  st_mbox(p, COLS_SENTINEL);
+  return __uint_as_float(v);
+}
+
 // Combine the G per-rank partials in the reference's tree order (strides G/2 .. 1 of WG_SUM).
 // On entry lane `li` of every LPG-lane sub-group holds, for G > LPG, the partials of ranks li
 // and li + LPG (v0, v1); for G <= LPG the lanes li < G hold the partial of rank li in v0.  On exit
@@ -187,6 +212,7 @@ struct ColsPhiArgs {
   uint32_t V, n, units;
   uint32_t R, D, MB;  // ring depth, A -> B distance (trips), metadata buffers
   uint32_t parity, disable_noise, loopback;
+  uint32_t debug;  // timing ablations (AMMSB_COLS_DEBUG): 1 no cuckoo, 2 no phase A math, 4 no phase B math, 8 no loads, 16 no Langevin step
   float eps_t, alpha, epsilon, Nn;
 };
 
@@ -199,7 +225,7 @@ struct ColsPhiSmem {
   static constexpr int PSTRIDE = PIECE + ((LPG == 4 && (PIECE % 128) != 64) ? 64 : 0);
   static constexpr int STAGE = G * PSTRIDE;
   static constexpr int OWN = G * PIECE;
-  static constexpr int META = G * 32 * 4 + 4 * G * 4;  // nb[G][32], ymask[G], slot[G], node[G], phi_sum[G]
+  static constexpr int META = G * 32 * 4 + 4 * G * 4;  // nb[32][G], ymask[G], slot[G], node[G], phi_sum[G]
   __host__ __device__ static size_t per_warp(uint32_t R, uint32_t MB) {
     return (size_t)R * STAGE + OWN + (size_t)MB * META + (size_t)R * G * 4 + ((size_t)R + 1) * 8 + 64;
   }
@@ -207,15 +233,43 @@ struct ColsPhiSmem {
 
 // One cursor over this warp's stages.  The three cursors of k_cols_phi (LOAD, phase A, phase B)
 // walk the same sequence -- the warp's live group-passes in (group, pass) order, n stages each --
-// at fixed distances; everything a stage needs is kept incrementally (no divisions per stage).
+// at fixed distances, NB stages (a "trip") at a time; everything a trip needs is kept
+// incrementally (no divisions).
 struct ColsCursor {
   uint32_t group, pass;  // current group-pass; group >= ngroups: exhausted
-  uint32_t j;            // neighbor index within the group-pass
-  uint32_t buf;          // ring buffer of the stage (stage number mod R)
+  uint32_t j;            // first neighbor index of the trip within the group-pass
+  uint32_t buf;          // ring buffer of the trip's first stage
   uint32_t meta;         // metadata buffer of the current segment (segment number mod MB)
 };
 
-template <int KPL, int G>
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16_u32(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's most recent copy groups are still in flight
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
+
+// NB = stages per trip: the loop body handles NB consecutive neighbors in each of its three parts,
+// which amortises the per-stage control over NB stages and gives the sum chains NB-fold ILP.
+// Requires n % NB == 0, R % NB == 0, D % NB == 0.
+template <int KPL, int G, int NB>
 __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ ColsPhiArgs a) {
   using SM = ColsPhiSmem<KPL, G>;
   constexpr int LPG = SM::LPG, KG = SM::KG, Q = KPL / 4;
@@ -240,13 +294,8 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
   float* s_own = reinterpret_cast<float*>(s_ring + (size_t)R * SM::STAGE);
   uint32_t* s_meta = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s_own) + SM::OWN);
   float* s_self = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_meta) + (size_t)MB * SM::META);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(
-      (reinterpret_cast<uintptr_t>(s_self + (size_t)R * G) + 7) / 8 * 8);  // [R] stages, [R] = own pieces
-  if (lane == 0) {
-    for (uint32_t s = 0; s <= R; ++s) mbar_init(&bars[s], 1);
-    mbar_fence_init();
-  }
   __syncthreads();
+  const uint32_t ring_u32 = smem_u32(s_ring), own_u32 = smem_u32(s_own);
 
   unsigned char* mybox = a.r[vr].box[rank];
   uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
@@ -297,9 +346,11 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
       }
     } while (group < ngroups && !gp_live(group, pass));
   };
-  auto step_cursor = [&](ColsCursor& c) {  // one stage on
-    if (++c.buf == R) c.buf = 0;
-    if (++c.j == n) {
+  auto step_cursor = [&](ColsCursor& c) {  // one trip on
+    c.buf += NB;
+    if (c.buf == R) c.buf = 0;
+    c.j += NB;
+    if (c.j == n) {
       c.j = 0;
       next_gp(c.group, c.pass);
       if (++c.meta == MB) c.meta = 0;
@@ -336,7 +387,7 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
         m_phi[lane] = 1.0f;
       }
     }
-#pragma unroll 1
+#pragma unroll 4
     for (int s = 0; s < G; ++s) {
       const uint32_t slot = slot_of(c.group, c.pass, s);  // warp-uniform
       const uint32_t node = __shfl_sync(FULL_MASK, my_node, s);
@@ -344,9 +395,9 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
       uint32_t nb = 0;
       if (slot != 0xffffffffu && lane < cnt) {
         nb = __ldg(&a.neighbors[(size_t)slot * n + j0 + lane]);
-        y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+        if (!(a.debug & 1)) y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
       }
-      m_nb[s * 32 + lane] = nb;
+      m_nb[lane * G + s] = nb;
       const uint32_t mask = __ballot_sync(FULL_MASK, y);
       if (lane == 0) m_y[s] = mask;
     }
@@ -365,16 +416,20 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
   for (int i = 0; i < KPL; ++i) ownA[i] = ownB[i] = g[i] = 0.f;
   Rng st;
   st.x = st.y = 0;
-  uint32_t own_phase = 0, ring_phase = 0;  // parities to wait on (bit b: stage buffer b)
   // per-segment / per-group-pass state of the A and B sides
   uint32_t ymaskA = 0, ymaskB = 0, slotB = 0xffffffffu;
   bool liveA = false, liveB = false;
   float phi_sumB = 1.0f, rphiB = 1.0f;
   size_t sidxA = 0, sidxB = 0;  // mailbox index of (group-pass, j = 0, sub)
+  uint32_t pk0[NB], pk1[NB];    // early look at the next trip's mailbox words
+#pragma unroll
+  for (int u = 0; u < NB; ++u) pk0[u] = pk1[u] = COLS_SENTINEL;
+  const uint32_t row_off = sub * SM::PSTRIDE + li * 16;  // this thread's first float4 within a stage
 
-  for (int it = (int)D - (int)R;; ++it) {
-    // ------------------------------------------------------- phase B of the stage D trips back ----
-    if (it >= (int)D) {
+  const int trips_D = (int)(D / NB), trips_R = (int)(R / NB);
+  for (int it = trips_D - trips_R;; ++it) {
+    // ------------------------------------------------ phase B of the trip D stages back ----
+    if (it >= trips_D) {
       if (cb.group >= ngroups) break;
       const uint32_t j = cb.j, b = cb.buf;
       if ((j & 31) == 0) {
@@ -397,45 +452,92 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
           }
         }
       }
-      const bool y = (ymaskB >> (j & 31)) & 1;
-      // the G partials of (slot, j): own from the ring, the peers' from the mailbox
-      const float mine = s_self[b * G + sub];
-      float v0 = (li < G) ? mine : 0.f, v1 = (G > LPG) ? mine : 0.f;
-      if (liveB) {
+      // the G partials of every (slot, j + u): own from the ring, the peers' from the mailbox.  The
+      // first look at this trip's words was taken one trip ago (pk*): the L2 round trip of a poll is
+      // off the critical path.
+      float S[NB];
+      {
+        float v0[NB], v1[NB];
         const size_t idx = sidxB + (size_t)j * G;
-        if (poll0) v0 = poll_mbox(poll0 + idx, err);
-        if (G > LPG && poll1) v1 = poll_mbox(poll1 + idx, err);
-      }
-      const float S = cols_rank_tree<G>(v0, v1, lane);
-      // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
-      const float inv = 1.0f / (S * phi_sumB);
-      const float nrphi = -rphiB;
-      const float4* row = reinterpret_cast<const float4*>(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE);
-      if (!__any_sync(FULL_MASK, y)) {  // no training link among the G pairs (the usual case)
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const float4 r4 = row[q * LPG + li];
-          g[4 * q] += fmaf(fmaf(r4.x, -fb[4 * q], e_non), inv, nrphi);
-          g[4 * q + 1] += fmaf(fmaf(r4.y, -fb[4 * q + 1], e_non), inv, nrphi);
-          g[4 * q + 2] += fmaf(fmaf(r4.z, -fb[4 * q + 2], e_non), inv, nrphi);
-          g[4 * q + 3] += fmaf(fmaf(r4.w, -fb[4 * q + 3], e_non), inv, nrphi);
+        for (int u = 0; u < NB; ++u) {
+          const float mine = s_self[(b + u) * G + sub];
+          v0[u] = (li < G) ? mine : 0.f;
+          v1[u] = (G > LPG) ? mine : 0.f;
+        }
+        if (liveB) {
+          uint32_t w0[NB], w1[NB];
+#pragma unroll
+          for (int u = 0; u < NB; ++u) {
+            w0[u] = pk0[u];
+            w1[u] = pk1[u];
+          }
+          if (j == 0) {
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+              if (poll0) w0[u] = peek_mbox(poll0 + idx + u * G);
+              if (G > LPG && poll1) w1[u] = peek_mbox(poll1 + idx + u * G);
+            }
+          }
+          if (j + NB < n) {
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+              if (poll0) pk0[u] = peek_mbox(poll0 + idx + (NB + u) * G);
+              if (G > LPG && poll1) pk1[u] = peek_mbox(poll1 + idx + (NB + u) * G);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < NB; ++u) {
+            if (poll0) v0[u] = finish_poll(poll0 + idx + u * G, w0[u], err);
+            if (G > LPG && poll1) v1[u] = finish_poll(poll1 + idx + u * G, w1[u], err);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) S[u] = cols_rank_tree<G>(v0[u], v1[u], lane);
+      }
+      // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
+      float inv[NB];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) inv[u] = 1.0f / (S[u] * phi_sumB);
+      const float nrphi = -rphiB;
+      const uint32_t ybits = (ymaskB >> (j & 31)) & ((1u << NB) - 1u);
+      const unsigned char* base = s_ring + (size_t)b * SM::STAGE + row_off;
+      if (a.debug & 4) {
+      } else if (!__any_sync(FULL_MASK, ybits != 0)) {  // no training link among the pairs (the usual case)
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {  // neighbor order: the gradient is summed as on one GPU
+          const float4* row = reinterpret_cast<const float4*>(base + (size_t)u * SM::STAGE);
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const float4 r4 = row[q * LPG];
+            g[4 * q] += fmaf(fmaf(r4.x, -fb[4 * q], e_non), inv[u], nrphi);
+            g[4 * q + 1] += fmaf(fmaf(r4.y, -fb[4 * q + 1], e_non), inv[u], nrphi);
+            g[4 * q + 2] += fmaf(fmaf(r4.z, -fb[4 * q + 2], e_non), inv[u], nrphi);
+            g[4 * q + 3] += fmaf(fmaf(r4.w, -fb[4 * q + 3], e_non), inv[u], nrphi);
+          }
         }
       } else {
-        const float e = y ? e_link : e_non;
-        const uint32_t sgn = y ? 0u : 0x80000000u;
+#pragma unroll 1
+        for (int u = 0; u < NB; ++u) {
+          const bool y = (ybits >> u) & 1;
+          const float e = y ? e_link : e_non;
+          const uint32_t sgn = y ? 0u : 0x80000000u;
+          const float4* row = reinterpret_cast<const float4*>(base + (size_t)u * SM::STAGE);
+          const float iu = inv[u];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const float4 r4 = row[q * LPG + li];
-          const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+          for (int q = 0; q < Q; ++q) {
+            const float4 r4 = row[q * LPG];
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int i = 4 * q + c;
-            g[i] += fmaf(fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e), inv, nrphi);
+            for (int c = 0; c < 4; ++c) {
+              const int i = 4 * q + c;
+              g[i] += fmaf(fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e), iu, nrphi);
+            }
           }
         }
       }
-      __syncwarp();  // every lane is done with stage buffer b
-      if (j == n - 1) {
+      __syncwarp();  // every lane is done with the trip's stage buffers
+      if (j + NB == n && !(a.debug & 16)) {
         // ---- Langevin step of the group-pass (phi.cc:266-274), noise in the state's draw order ----
         float* out = my_vec + (size_t)(liveB ? slotB : 0) * KG;
         float lsum = 0.f;
@@ -471,38 +573,52 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
       }
       step_cursor(cb);
     }
-    // ------------------------------------------------- LOAD of the stage R - D trips ahead of A ----
+    // ------------------------------------------------- LOAD of the trip R - D stages ahead of A ----
     if (cl.group < ngroups) {
       const uint32_t j = cl.j, b = cl.buf;
       if ((j & 31) == 0) prep_segment(cl);
       const uint32_t* m = s_meta + (size_t)cl.meta * (SM::META / 4);
-      const uint32_t slot = m[G * 32 + G + sub];
-      const bool issue = slot != 0xffffffffu && li == 0;
-      const uint32_t nact = __popc(__ballot_sync(FULL_MASK, issue));
-      if (j == 0) {  // the own pieces of the group-pass
-        if (lane == 0) mbar_expect_tx(&bars[R], nact * SM::PIECE);
-        __syncwarp();
-        if (issue) bulk_g2s(s_own + (size_t)sub * KG, my_pi + (size_t)m[G * 32 + 2 * G + sub] * KG, SM::PIECE, &bars[R]);
+      // Every lane copies 16-byte chunks (cp.async, L1 bypassed): chunk c*32 + lane of a stage's G
+      // pieces.  An idle sub-group's id is 0 -- row 0 is copied and ignored -- so nothing here is
+      // predicated.  Each lane's copies arrive on the stage barrier when they have landed.
+      constexpr int CP = SM::PIECE / 16;      // chunks per piece
+      constexpr int NC = (G * CP + 31) / 32;  // copies per lane and stage
+      if (j == 0) {                           // the own pieces of the group-pass
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t gc = c * 32 + lane, s = gc / CP, w = gc % CP;
+          if (NC * 32 == G * CP || gc < G * CP)
+            cp_async16_u32(own_u32 + s * SM::PIECE + w * 16, my_pi + (size_t)m[G * 32 + 2 * G + s] * KG + w * 4);
+        }
       }
-      if (lane == 0) mbar_expect_tx(&bars[b], nact * SM::PIECE);
-      __syncwarp();
-      if (issue) {
-        const uint32_t nb = m[sub * 32 + (j & 31)];
-        bulk_g2s(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE, my_pi + (size_t)nb * KG, SM::PIECE, &bars[b]);
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const uint32_t* ids = m + ((j & 31) + u) * G;
+        const uint32_t dst = ring_u32 + (b + u) * SM::STAGE;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t gc = c * 32 + lane, s = gc / CP, w = gc % CP;
+          if ((NC * 32 == G * CP || gc < G * CP) && !(a.debug & 8))
+            cp_async16_u32(dst + s * SM::PSTRIDE + w * 16, my_pi + (size_t)ids[s] * KG + w * 4);
+        }
       }
       step_cursor(cl);
     }
+    // one copy group per iteration, also when nothing was requested: phase A counts groups
+    cp_async_commit();
     // ---------------------------------------------------------------------------- phase A ----
     if (it >= 0 && ca.group < ngroups) {
       const uint32_t j = ca.j, b = ca.buf;
+      // the trip's pieces (and at j = 0 the own pieces) were requested R - D stages ago: all but
+      // the (R - D) / NB youngest groups of every lane have landed
+      cp_async_wait_pending((uint32_t)(trips_R - trips_D));
+      __syncwarp();
       if ((j & 31) == 0) {
         const uint32_t* m = s_meta + (size_t)ca.meta * (SM::META / 4);
         ymaskA = m[G * 32 + sub];
         if (j == 0) {  // own pieces of the group-pass into registers
           liveA = m[G * 32 + G + sub] != 0xffffffffu;
           sidxA = ((size_t)ca.group * passes + ca.pass) * n * G + sub;
-          mbar_wait(&bars[R], own_phase);
-          own_phase ^= 1;
           const float4* o4 = reinterpret_cast<const float4*>(s_own + (size_t)sub * KG);
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
@@ -512,47 +628,372 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
           __syncwarp();  // s_own may be refilled by the next group-pass's request
         }
       }
-      const bool y = (ymaskA >> (j & 31)) & 1;
-      mbar_wait(&bars[b], (ring_phase >> b) & 1);
-      ring_phase ^= 1u << b;
-      const float4* row = reinterpret_cast<const float4*>(s_ring + (size_t)b * SM::STAGE + (size_t)sub * SM::PSTRIDE);
-      float S = 0.f;
-      if (!__any_sync(FULL_MASK, y)) {
+      const uint32_t ybits = (ymaskA >> (j & 31)) & ((1u << NB) - 1u);
+      const unsigned char* base = s_ring + (size_t)b * SM::STAGE + row_off;
+      float S[NB];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) S[u] = 0.f;
+      if (a.debug & 2) {
+      } else if (!__any_sync(FULL_MASK, ybits != 0)) {
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          const float4 r4 = row[q * LPG + li];
-          S = fmaf(ownA[4 * q], fmaf(r4.x, -fb[4 * q], e_non), S);
-          S = fmaf(ownA[4 * q + 1], fmaf(r4.y, -fb[4 * q + 1], e_non), S);
-          S = fmaf(ownA[4 * q + 2], fmaf(r4.z, -fb[4 * q + 2], e_non), S);
-          S = fmaf(ownA[4 * q + 3], fmaf(r4.w, -fb[4 * q + 3], e_non), S);
+#pragma unroll
+          for (int u = 0; u < NB; ++u) {  // NB independent chains, each in the order of one GPU's lane
+            const float4 r4 = reinterpret_cast<const float4*>(base + (size_t)u * SM::STAGE)[q * LPG];
+            S[u] = fmaf(ownA[4 * q], fmaf(r4.x, -fb[4 * q], e_non), S[u]);
+            S[u] = fmaf(ownA[4 * q + 1], fmaf(r4.y, -fb[4 * q + 1], e_non), S[u]);
+            S[u] = fmaf(ownA[4 * q + 2], fmaf(r4.z, -fb[4 * q + 2], e_non), S[u]);
+            S[u] = fmaf(ownA[4 * q + 3], fmaf(r4.w, -fb[4 * q + 3], e_non), S[u]);
+          }
         }
       } else {
-        const float e = y ? e_link : e_non;
-        const uint32_t sgn = y ? 0u : 0x80000000u;
+#pragma unroll 1
+        for (int u = 0; u < NB; ++u) {
+          const bool y = (ybits >> u) & 1;
+          const float e = y ? e_link : e_non;
+          const uint32_t sgn = y ? 0u : 0x80000000u;
+          const float4* row = reinterpret_cast<const float4*>(base + (size_t)u * SM::STAGE);
+          float Su = 0.f;
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          const float4 r4 = row[q * LPG + li];
-          const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+          for (int q = 0; q < Q; ++q) {
+            const float4 r4 = row[q * LPG];
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int i = 4 * q + c;
-            S = fmaf(ownA[i], fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e), S);
+            for (int c = 0; c < 4; ++c) {
+              const int i = 4 * q + c;
+              Su = fmaf(ownA[i], fmaf(rr[c], __uint_as_float(__float_as_uint(fb[i]) ^ sgn), e), Su);
+            }
           }
+#pragma unroll
+          for (int v = 0; v < NB; ++v)
+            if (v == u) S[v] = Su;
         }
       }
       // strides 16 .. G of WG_SUM: the lanes of this GPU
 #pragma unroll
-      for (int o = LPG / 2; o > 0; o >>= 1) S += __shfl_xor_sync(FULL_MASK, S, o);
-      if (li == 0) s_self[b * G + sub] = S;
+      for (int o = LPG / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < NB; ++u) S[u] += __shfl_xor_sync(FULL_MASK, S[u], o);
+      }
+      if (li == 0) {
+#pragma unroll
+        for (int u = 0; u < NB; ++u) s_self[(b + u) * G + sub] = S[u];
+      }
       if (liveA) {
         const size_t idx = sidxA + (size_t)j * G;
-        const uint32_t bits = partial_bits(S);
-        if (send0) st_mbox(send0 + idx, bits);
-        if (G > LPG && send1) st_mbox(send1 + idx, bits);
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const uint32_t bits = partial_bits(S[u]);
+          if (send0) st_mbox(send0 + idx + u * G, bits);
+          if (G > LPG && send1) st_mbox(send1 + idx + u * G, bits);
+        }
       }
       __syncwarp();
       step_cursor(ca);
     }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_cols_phi2 -- update_phi on the column shards, slot-at-a-time mapping.
+//
+// A warp owns a group of G consecutive units (the reference work-groups that own the slots and
+// their RNG states) and takes the group's slots one after the other.  For a slot it stages the
+// own piece and the pieces of (up to) 32 sampled neighbors in shared memory (cp.async, 16 bytes
+// per lane, a piece per instruction: coalesced) and keeps them there across the exchange:
+//   phase A   lane b owns NEIGHBOR b: it walks the K/G local columns with LPG independent
+//             accumulators -- one per reference lane li, each summed over i in the order of that
+//             lane on one GPU -- and combines them with the strides >= G of the WG_SUM tree, all
+//             in registers: the 32 partial sums of the slot are ready without a single shuffle.
+//   exchange  one coalesced 128-byte store per peer (the 32 partials of the slot), then each lane
+//             collects its neighbor's G partials and finishes the tree (strides G/2 .. 1).
+//   phase B   lane f owns COLUMNS (float4 f of the piece): the gradient is accumulated neighbor
+//             by neighbor as on one GPU, then the Langevin step and the partial row sum.
+// The Langevin noise of the group's G slots is drawn at the start of the group with lane = (slot,
+// reference lane) -- every lane busy, states advanced in the reference's order -- into a scratch
+// row in global memory (it stays in L2) that the Langevin step reads back.
+// Register use is small (no per-column state lives across phases), so 12+ warps share an SM and
+// hide each other's load and exchange latencies; the instruction stream has no per-neighbor
+// control flow.
+struct ColsPhi2Smem {
+  __host__ __device__ static size_t pstr(uint32_t KG) { return (size_t)KG * 4 + 16; }  // piece stride: conflict-free float4 rows
+  __host__ __device__ static size_t per_warp(uint32_t KG) { return (33 * pstr(KG) + 128 + 127) / 128 * 128; }
+  __host__ __device__ static size_t per_cta(uint32_t KG) { return 1536 + (((size_t)KG * 4 + 127) / 128 * 128); }
+};
+
+template <int KPL, int G>
+__global__ void __launch_bounds__(384, 1) k_cols_phi2(const __grid_constant__ ColsPhiArgs a, float* __restrict__ nz_scratch) {
+  constexpr int LPG = 32 / G, KG = KPL * LPG, F4 = KG / 4;
+  constexpr int PSTR = KG * 4 + 16;
+  constexpr int FPL = (F4 + 31) / 32;  // float4 per lane in the column phases
+  constexpr int PPI = F4 >= 32 ? 1 : 32 / F4;  // pieces per copy instruction
+  constexpr int IPP = F4 >= 32 ? F4 / 32 : 1;  // copy instructions per piece
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
+  const uint32_t rank = a.r[vr].rank;
+  const uint32_t n = a.n;
+  float* const my_pi = a.r[vr].pi;
+  const float* const my_phi = a.r[vr].phi;
+  float* const my_vec = a.r[vr].phi_vec;
+  ulonglong2* const my_pool = a.r[vr].pool;
+
+  uint32_t* s_zig = reinterpret_cast<uint32_t*>(s_raw);
+  const ZigShared zig{s_zig};
+  zig_stage(s_zig);
+  float* s_fb = reinterpret_cast<float*>(s_raw + 1536);  // beta_k - epsilon, local column order
+  unsigned char* mybox = a.r[vr].box[rank];
+  uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
+  {
+    const float* beta = reinterpret_cast<const float*>(mybox + a.lay.beta);
+    for (uint32_t c = threadIdx.x; c < KG; c += blockDim.x) {
+      const uint32_t f = c >> 2, e = c & 3, q = f / LPG, li = f % LPG;
+      const uint32_t k = (rank + G * li) + 32 * (4 * q + e);
+      s_fb[c] = beta[2 * k + 1] - a.epsilon;  // phi.cc:237-239
+    }
+  }
+  __syncthreads();
+  unsigned char* wbase = s_raw + ColsPhi2Smem::per_cta(KG) + (size_t)wib * ColsPhi2Smem::per_warp(KG);
+  unsigned char* s_rows = wbase;                                   // [32] neighbor pieces
+  unsigned char* s_own = wbase + 32 * PSTR;                        // own piece, later the new phi piece
+  float* s_inv = reinterpret_cast<float*>(wbase + 33 * PSTR);      // [32] 1 / (probs_sum * phi_sum)
+  const uint32_t rows_u32 = smem_u32(s_rows);
+
+  const size_t half_S = (size_t)a.parity * G * a.lay.S_src, half_R = (size_t)a.parity * G * a.lay.R_src;
+  const float e_link = a.epsilon, e_non = 1.0f - a.epsilon;
+  const float half_eps = a.eps_t / 2;
+
+  const uint32_t active_units = a.units < a.V ? a.units : a.V;
+  const uint32_t ngroups = (active_units + G - 1) / G;
+  const uint32_t passes = (a.V + a.units - 1) / a.units;
+  const uint32_t gwarp = cta * warps + wib, total_warps = a.ctas_per_rank * warps;
+  float* const my_nz = nz_scratch + ((size_t)vr * total_warps + gwarp) * G * KG;  // [G][KG]
+
+  // noise lanes: lane = (slot s_n of the group, reference lane li_n)
+  const uint32_t s_n = lane / LPG, li_n = lane % LPG, l_ref = rank + G * li_n;
+
+  for (uint32_t group = gwarp; group < ngroups; group += total_warps) {
+    Rng st;
+    st.x = st.y = 0;
+    const uint32_t unit_n = group * G + s_n;
+    if (!a.disable_noise && unit_n < active_units) st = rng_load(my_pool, (uint64_t)unit_n * 32 + l_ref);
+    for (uint32_t pass = 0; pass < passes; ++pass) {
+      if ((size_t)group * G + (size_t)pass * a.units >= a.V) break;  // no live slot in this and later passes
+      // ---- the Langevin noise of the group-pass's G slots (phi.cc:266-274 draw order) ----
+      {
+        const uint32_t slot_n = unit_n + pass * a.units;
+        if (!a.disable_noise && unit_n < active_units && slot_n < a.V && !(a.debug & 16)) {
+          float* row = my_nz + (size_t)s_n * KG;
+#pragma unroll 4
+          for (int i = 0; i < KPL; ++i) row[((i >> 2) * LPG + li_n) * 4 + (i & 3)] = rng_randn_t(st, zig);
+        }
+        __syncwarp();
+      }
+      for (uint32_t s = 0; s < (uint32_t)G; ++s) {
+        const uint32_t unit = group * G + s, slot = unit + pass * a.units;
+        if (unit >= active_units || slot >= a.V) break;  // warp-uniform; later sub-slots are dead too
+        const uint32_t node = __ldg(&a.nodes[slot]);
+        const float phi_sum = my_phi[node];
+        const float rphi = 1.0f / phi_sum;
+        const size_t ridx = ((size_t)group * passes + pass) * G + s;
+        float4 g4[FPL];
+#pragma unroll
+        for (int r = 0; r < FPL; ++r) g4[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+          const uint32_t cnt = min(32u, n - c0);
+          // ---- stage the pieces: neighbor b of the chunk -> row b; the own piece -> row 32 ----
+          uint32_t nb = node;
+          if (lane < cnt) nb = __ldg(&a.neighbors[(size_t)slot * n + c0 + lane]);
+          if (!(a.debug & 8)) {
+            if (F4 >= 32) {
+#pragma unroll 8
+              for (uint32_t r = 0; r < 32; ++r) {
+                const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
+                if (r < cnt) {
+#pragma unroll
+                  for (int h = 0; h < IPP; ++h)
+                    cp_async16_u32(rows_u32 + r * PSTR + (h * 32 + lane) * 16, my_pi + (size_t)id * KG + (h * 32 + lane) * 4);
+                }
+              }
+              if (c0 == 0) {
+#pragma unroll
+                for (int h = 0; h < IPP; ++h)
+                  cp_async16_u32(rows_u32 + 32 * PSTR + (h * 32 + lane) * 16, my_pi + (size_t)node * KG + (h * 32 + lane) * 4);
+              }
+            } else {
+              const uint32_t sub = lane / F4, w = lane % F4;
+#pragma unroll 8
+              for (uint32_t r0 = 0; r0 < 32; r0 += PPI) {
+                const uint32_t r = r0 + sub;
+                const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
+                if (r < cnt) cp_async16_u32(rows_u32 + r * PSTR + w * 16, my_pi + (size_t)id * KG + w * 4);
+              }
+              if (c0 == 0 && lane < F4) cp_async16_u32(rows_u32 + 32 * PSTR + lane * 16, my_pi + (size_t)node * KG + lane * 4);
+            }
+          }
+          cp_async_commit();
+          // the cuckoo answer for this lane's neighbor while the pieces travel (phi.cc:230-234)
+          bool y = false;
+          if (lane < cnt && !(a.debug & 1)) y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+          const uint32_t ymask = __ballot_sync(FULL_MASK, y);
+          cp_async_wait_pending(0);
+          __syncwarp();
+
+          // ---- phase A: lane b = neighbor b; LPG chains, one per reference lane of this GPU ----
+          float S = 0.f;
+          if (!(a.debug & 2)) {
+            float ch[LPG];
+#pragma unroll
+            for (int t = 0; t < LPG; ++t) ch[t] = 0.f;
+            const float4* own4 = reinterpret_cast<const float4*>(s_own);
+            const float4* fb4 = reinterpret_cast<const float4*>(s_fb);
+            const float4* row4 = reinterpret_cast<const float4*>(s_rows + (size_t)(lane < cnt ? lane : 0) * PSTR);
+            if (ymask == 0) {  // no training link among the chunk's pairs (the usual case)
+#pragma unroll
+              for (int f = 0; f < F4; ++f) {
+                const float4 o = own4[f], fb = fb4[f], r = row4[f];
+                float& acc = ch[f % LPG];
+                acc = fmaf(o.x, fmaf(-r.x, fb.x, e_non), acc);  // fma(r, -f, e) == fma(-r, f, e) bit for bit
+                acc = fmaf(o.y, fmaf(-r.y, fb.y, e_non), acc);
+                acc = fmaf(o.z, fmaf(-r.z, fb.z, e_non), acc);
+                acc = fmaf(o.w, fmaf(-r.w, fb.w, e_non), acc);
+              }
+            } else {
+              const float e = y ? e_link : e_non;
+              const float sg = y ? 1.0f : -1.0f;
+#pragma unroll
+              for (int f = 0; f < F4; ++f) {
+                const float4 o = own4[f], fb = fb4[f], r = row4[f];
+                float& acc = ch[f % LPG];
+                acc = fmaf(o.x, fmaf(r.x * sg, fb.x, e), acc);
+                acc = fmaf(o.y, fmaf(r.y * sg, fb.y, e), acc);
+                acc = fmaf(o.z, fmaf(r.z * sg, fb.z, e), acc);
+                acc = fmaf(o.w, fmaf(r.w * sg, fb.w, e), acc);
+              }
+            }
+            // strides 16 .. G of WG_SUM over the reference lanes l = rank + G li: li strides LPG/2 .. 1
+#pragma unroll
+            for (int o = LPG / 2; o > 0; o >>= 1) {
+#pragma unroll
+              for (int t = 0; t < o; ++t) ch[t] += ch[t + o];
+            }
+            S = ch[0];
+          }
+          // ---- exchange: the slot's partials to every peer; collect this neighbor's G partials ----
+          const size_t sidx = ridx * n + c0 + lane;
+          float P[G];
+#pragma unroll
+          for (int p = 0; p < G; ++p) P[p] = S;
+          if (lane < cnt && !a.loopback) {
+            const uint32_t bits = partial_bits(S);
+#pragma unroll
+            for (int p = 0; p < G; ++p)
+              if ((uint32_t)p != rank)
+                st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + sidx, bits);
+            uint32_t w[G];
+#pragma unroll
+            for (int p = 0; p < G; ++p)
+              if ((uint32_t)p != rank)
+                w[p] = peek_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p * a.lay.S_src) + sidx);
+#pragma unroll
+            for (int p = 0; p < G; ++p)
+              if ((uint32_t)p != rank)
+                P[p] = finish_poll(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p * a.lay.S_src) + sidx, w[p], err);
+          }
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) {  // strides G/2 .. 1 of WG_SUM
+#pragma unroll
+            for (int p = 0; p < o; ++p) P[p] += P[p + o];
+          }
+          // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
+          s_inv[lane] = 1.0f / (P[0] * phi_sum);
+          __syncwarp();
+
+          // ---- phase B: lane = columns (float4 f = lane + 32 r); neighbors in order ----
+          if (!(a.debug & 4)) {
+            float4 fb[FPL];
+#pragma unroll
+            for (int r = 0; r < FPL; ++r)
+              fb[r] = (lane + 32 * r < F4) ? reinterpret_cast<const float4*>(s_fb)[lane + 32 * r] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float nrphi = -rphi;
+            if (ymask == 0) {  // no training link among the chunk's pairs (the usual case)
+#pragma unroll 8
+              for (uint32_t b = 0; b < cnt; ++b) {
+                const float inv = s_inv[b];
+#pragma unroll
+                for (int r = 0; r < FPL; ++r) {
+                  if (lane + 32 * r < F4) {
+                    const float4 x = reinterpret_cast<const float4*>(s_rows + (size_t)b * PSTR)[lane + 32 * r];
+                    g4[r].x += fmaf(fmaf(-x.x, fb[r].x, e_non), inv, nrphi);
+                    g4[r].y += fmaf(fmaf(-x.y, fb[r].y, e_non), inv, nrphi);
+                    g4[r].z += fmaf(fmaf(-x.z, fb[r].z, e_non), inv, nrphi);
+                    g4[r].w += fmaf(fmaf(-x.w, fb[r].w, e_non), inv, nrphi);
+                  }
+                }
+              }
+            } else {
+#pragma unroll 4
+              for (uint32_t b = 0; b < cnt; ++b) {
+                const float inv = s_inv[b];
+                const bool yb = (ymask >> b) & 1;
+                const float e = yb ? e_link : e_non, sg = yb ? 1.0f : -1.0f;
+#pragma unroll
+                for (int r = 0; r < FPL; ++r) {
+                  if (lane + 32 * r < F4) {
+                    const float4 x = reinterpret_cast<const float4*>(s_rows + (size_t)b * PSTR)[lane + 32 * r];
+                    g4[r].x += fmaf(fmaf(x.x * sg, fb[r].x, e), inv, nrphi);
+                    g4[r].y += fmaf(fmaf(x.y * sg, fb[r].y, e), inv, nrphi);
+                    g4[r].z += fmaf(fmaf(x.z * sg, fb[r].z, e), inv, nrphi);
+                    g4[r].w += fmaf(fmaf(x.w * sg, fb[r].w, e), inv, nrphi);
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();  // the rows may be overwritten by the next chunk / slot
+        }
+        // ---- Langevin step (phi.cc:266-274): lane = columns; the new piece replaces the own piece ----
+        if (!(a.debug & 16)) {
+          const float* nzrow = my_nz + (size_t)s * KG;
+#pragma unroll
+          for (int r = 0; r < FPL; ++r) {
+            const uint32_t f = lane + 32 * r;
+            if (f < F4) {
+              const float4 o = reinterpret_cast<const float4*>(s_own)[f];
+              float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (!a.disable_noise) z = __ldcg(reinterpret_cast<const float4*>(nzrow) + f);
+              float4 v;
+              v.x = phi_langevin(o.x, phi_sum, g4[r].x, z.x, half_eps, a.eps_t, a.alpha, a.Nn);
+              v.y = phi_langevin(o.y, phi_sum, g4[r].y, z.y, half_eps, a.eps_t, a.alpha, a.Nn);
+              v.z = phi_langevin(o.z, phi_sum, g4[r].z, z.z, half_eps, a.eps_t, a.alpha, a.Nn);
+              v.w = phi_langevin(o.w, phi_sum, g4[r].w, z.w, half_eps, a.eps_t, a.alpha, a.Nn);
+              reinterpret_cast<float4*>(my_vec + (size_t)slot * KG)[f] = v;
+              reinterpret_cast<float4*>(s_own)[f] = v;
+            }
+          }
+          __syncwarp();
+          // partial row sum: reference lane li adds its columns in order (i = 0 .. KPL-1), then the
+          // strides >= G of the tree; lanes li < LPG hold one reference lane each
+          float ls = 0.f;
+          if (lane < LPG) {
+            const float* v = reinterpret_cast<const float*>(s_own);
+#pragma unroll 8
+            for (int i = 0; i < KPL; ++i) ls += v[((i >> 2) * LPG + lane) * 4 + (i & 3)];
+          }
+#pragma unroll
+          for (int o = LPG / 2; o > 0; o >>= 1) ls += __shfl_xor_sync(FULL_MASK, ls, o);
+          ls = __shfl_sync(FULL_MASK, ls, 0);
+          if (lane < (uint32_t)G) {  // this rank's partial to every rank (its own mailbox included)
+            const uint32_t p = lane;
+            st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[a.loopback ? rank : p] + a.lay.R + half_R +
+                                                (size_t)(a.loopback ? p : rank) * a.lay.R_src) + ridx,
+                    partial_bits(ls));
+          }
+          __syncwarp();  // s_own is free for the next slot's own piece
+        }
+      }
+    }
+    if (!a.disable_noise && unit_n < active_units) rng_store(my_pool, (uint64_t)unit_n * 32 + l_ref, st);
   }
 }
 
@@ -1017,9 +1458,11 @@ extern "C" int ammsb_cols_create(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t 
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ppx, sizeof(float) * (max_pairs ? max_pairs : 1));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ws, sizeof(float) * 2 * s->KG * (size_t)s->ws_ctas);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ws_d, sizeof(double) * 4 * ((size_t)s->ws_ctas + 1));
+  s->nz_warps = (size_t)c->sm_count * 32;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_nz, sizeof(float) * s->nz_warps * K);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ppx, 0, sizeof(float) * (max_pairs ? max_pairs : 1), c->stream);
   if (e != cudaSuccess || vmm_alloc(c->device, s->lay.bytes, &s->local)) {
-    cudaFree(s->d_pi); cudaFree(s->d_phi); cudaFree(s->d_phi_vec); cudaFree(s->d_ppx); cudaFree(s->d_ws); cudaFree(s->d_ws_d);
+    cudaFree(s->d_pi); cudaFree(s->d_phi); cudaFree(s->d_phi_vec); cudaFree(s->d_ppx); cudaFree(s->d_ws); cudaFree(s->d_ws_d); cudaFree(s->d_nz);
     delete s;
     if (e != cudaSuccess) AMMSB_CHECK_CUDA(e);
     return 1;
@@ -1038,7 +1481,7 @@ extern "C" int ammsb_cols_destroy(ammsb_cols* s) {
   cudaSetDevice(s->ctx->device);
   for (int i = 0; i < AMMSB_MAX_SHARDS; ++i) vmm_free(&s->remote[i]);
   vmm_free(&s->local);
-  cudaFree(s->d_pi); cudaFree(s->d_phi); cudaFree(s->d_phi_vec); cudaFree(s->d_ppx); cudaFree(s->d_ws); cudaFree(s->d_ws_d);
+  cudaFree(s->d_pi); cudaFree(s->d_phi); cudaFree(s->d_phi_vec); cudaFree(s->d_ppx); cudaFree(s->d_ws); cudaFree(s->d_ws_d); cudaFree(s->d_nz);
   delete s;
   return 0;
 }
@@ -1195,7 +1638,7 @@ struct ColsTune {  // launch shape of k_cols_phi, overridable for A/B measuremen
 };
 static ColsTune cols_tune(uint32_t KPL, uint32_t G, uint32_t n) {
   ColsTune t;
-  t.warps = 6; t.R = 6; t.D = 3;
+  t.warps = 8; t.R = 4; t.D = 2;
   if (const char* e = getenv("AMMSB_COLS_WARPS")) t.warps = (uint32_t)atoi(e);
   if (const char* e = getenv("AMMSB_COLS_R")) t.R = (uint32_t)atoi(e);
   if (const char* e = getenv("AMMSB_COLS_D")) t.D = (uint32_t)atoi(e);
@@ -1208,10 +1651,73 @@ static ColsTune cols_tune(uint32_t KPL, uint32_t G, uint32_t n) {
   return t;
 }
 
+template <int KPL, int G, int NB>
+static int cols_phi_launch_nb(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv);
+
+// k_cols_phi2 (slot at a time): as many warps as the staged slot buffers allow, every CTA resident
+template <int KPL, int G>
+static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_nz, size_t nz_warps) {
+  constexpr uint32_t KG = KPL * (32 / G);
+  uint32_t warps = 12;
+  if (const char* e = getenv("AMMSB_COLS_WARPS")) warps = (uint32_t)atoi(e);
+  if (warps < 1) warps = 1;
+  if (warps > 12) warps = 12;
+  size_t smem;
+  for (;; --warps) {
+    smem = ColsPhi2Smem::per_cta(KG) + (size_t)warps * ColsPhi2Smem::per_warp(KG);
+    if (smem <= c->smem_optin || warps == 1) break;
+  }
+  AMMSB_REQUIRE(smem <= c->smem_optin, "column update_phi: shared memory request exceeds the device limit");
+  auto kern = k_cols_phi2<KPL, G>;
+  static bool attr_set[64] = {false};  // per device
+  if (!attr_set[c->device & 63]) {
+    AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    attr_set[c->device & 63] = true;
+  }
+  int occ = 0;
+  AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+  AMMSB_REQUIRE(occ > 0, "column update_phi: kernel does not fit on an SM");
+  const uint32_t resident = (uint32_t)occ * c->sm_count;
+  const uint32_t active = a.units < a.V ? a.units : a.V;
+  const uint32_t ngroups = (active + G - 1) / G;
+  uint32_t ctas = resident / nv;
+  if (ctas * warps > ngroups) ctas = (ngroups + warps - 1) / warps;
+  if (ctas > 0) {  // an even share of groups per warp (a static schedule: the slowest warp ends the kernel)
+    const uint32_t per = (ngroups + ctas * warps - 1) / (ctas * warps);
+    const uint32_t need = (ngroups + per - 1) / per;
+    ctas = (need + warps - 1) / warps;
+  }
+  AMMSB_REQUIRE(ctas > 0, "column update_phi: no resident CTA available per rank");
+  AMMSB_REQUIRE((size_t)ctas * nv * warps <= nz_warps, "column update_phi: noise scratch too small");
+  a.ctas_per_rank = ctas;
+  a.nv = nv;
+  void* params[] = {&a, &d_nz};
+  AMMSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(ctas * nv), dim3(warps * 32), params,
+                                               smem, c->stream));
+  AMMSB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int KPL, int G>
 static int cols_phi_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv) {
+  // stages per trip: 2 when the neighbor count allows it (AMMSB_COLS_NB=1 for A/B measurements)
+  uint32_t nb = (a.n % 2 == 0) ? 2 : 1;
+  if (const char* e = getenv("AMMSB_COLS_NB")) nb = (uint32_t)atoi(e);
+  if (nb == 4 && a.n % 4 == 0) return cols_phi_launch_nb<KPL, G, 4>(c, a, nv);
+  if (nb >= 2 && a.n % 2 == 0) return cols_phi_launch_nb<KPL, G, 2>(c, a, nv);
+  return cols_phi_launch_nb<KPL, G, 1>(c, a, nv);
+}
+
+template <int KPL, int G, int NB>
+static int cols_phi_launch_nb(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv) {
   using SM = ColsPhiSmem<KPL, G>;
-  const ColsTune t = cols_tune(KPL, G, a.n);
+  ColsTune t = cols_tune(KPL, G, a.n);
+  // whole trips: R and D multiples of NB, D >= NB, R > D
+  t.D = (t.D + NB - 1) / NB * NB;
+  if (t.D < (uint32_t)NB) t.D = NB;
+  t.R = (t.R + NB - 1) / NB * NB;
+  if (t.R <= t.D) t.R = t.D + NB;
+  AMMSB_REQUIRE(t.R <= a.n && t.R <= 32, "column update_phi: too few neighbors for the stage ring");
   a.R = t.R;
   a.D = t.D;
   const uint32_t min_seg = a.n % 32 ? a.n % 32 : 32;
@@ -1223,7 +1729,7 @@ static int cols_phi_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv) {
     if (smem <= c->smem_optin || warps == 1) break;
   }
   AMMSB_REQUIRE(smem <= c->smem_optin, "column update_phi: shared memory request exceeds the device limit");
-  auto kern = k_cols_phi<KPL, G>;
+  auto kern = k_cols_phi<KPL, G, NB>;
   static bool attr_set[64] = {false};  // per device
   if (!attr_set[c->device & 63]) {
     AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
@@ -1279,13 +1785,17 @@ extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uin
   a.parity = step_count & 1;
   a.disable_noise = o->disable_noise;
   a.loopback = getenv("AMMSB_COLS_LOOPBACK") != nullptr;
+  a.debug = getenv("AMMSB_COLS_DEBUG") ? (uint32_t)atoi(getenv("AMMSB_COLS_DEBUG")) : 0;
   a.eps_t = ammsb_eps_t(p, step_count);
   a.alpha = p->alpha;
   a.epsilon = p->epsilon;
   a.Nn = (1.0f * p->N) / p->num_neighbors;  // phi.cc:113
   const uint32_t kpl = p->K / 32, G = s0->G;
-#define COLS_PHI_CASE(KPL_, G_) \
-  if (kpl == KPL_ && G == G_) return cols_phi_launch<KPL_, G_>(c, a, nv);
+  const bool staged = getenv("AMMSB_COLS_STAGED") != nullptr;  // the per-neighbor stage-ring kernel (A/B measurements)
+#define COLS_PHI_CASE(KPL_, G_)                                                                              \
+  if (kpl == KPL_ && G == G_)                                                                                \
+    return staged ? cols_phi_launch<KPL_, G_>(c, a, nv)                                                      \
+                  : cols_phi2_launch<KPL_, G_>(c, a, nv, ranks[0]->d_nz, ranks[0]->nz_warps);
   COLS_PHI_CASE(4, 2) COLS_PHI_CASE(4, 4) COLS_PHI_CASE(4, 8)
   COLS_PHI_CASE(8, 2) COLS_PHI_CASE(8, 4) COLS_PHI_CASE(8, 8)
   COLS_PHI_CASE(16, 2) COLS_PHI_CASE(16, 4) COLS_PHI_CASE(16, 8)

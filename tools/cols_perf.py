@@ -64,10 +64,10 @@ def sweep(label, fn, nbytes, configs):
         os.environ.update(AMMSB_COLS_WARPS=str(w), AMMSB_COLS_R=str(R), AMMSB_COLS_D=str(D))
         try:
             t = timeit(fn)
-            print("%-28s warps=%d R=%2d D=%d  %8.4f ms  %8.1f GB/s  %5.1f%% of %d" %
+            print("%-40s warps=%d R=%2d D=%d  %8.4f ms  %8.1f GB/s  %5.1f%% of %d" %
                   (label, w, R, D, t, nbytes / t / 1e6, 100 * nbytes / t / 1e6 / PEAK, PEAK), flush=True)
         except A.AmmsbError as e:
-            print("%-28s warps=%d R=%2d D=%d  failed: %s" % (label, w, R, D, e), flush=True)
+            print("%-40s warps=%d R=%2d D=%d  failed: %s" % (label, w, R, D, e), flush=True)
 
 
 configs = [(6, 6, 3), (6, 6, 2), (5, 7, 3), (4, 10, 4), (4, 8, 3), (8, 4, 2), (8, 5, 2), (7, 5, 2)]
@@ -162,7 +162,13 @@ if "loop" in mode:
         step[0] += 1
         A.cols_update_beta(ctx, [r0], p, g.train, d_edges, G * m, 2.0 * E / m, step[0], bpools)
 
-    sweep("one rank of %d, V=%d (loopback)" % (G, Vg), loop, bytes_phi(Vg, K // G), configs)
+    for dbg in os.environ.get("COLS_PERF_DEBUGS", "0").split(","):
+        os.environ["AMMSB_COLS_DEBUG"] = dbg
+        for nb in os.environ.get("COLS_PERF_NBS", "2").split(","):
+            os.environ["AMMSB_COLS_NB"] = nb
+            sweep("1 of %d, V=%d loopback dbg=%s NB=%s" % (G, Vg, dbg, nb), loop, bytes_phi(Vg, K // G), configs)
+    os.environ["AMMSB_COLS_DEBUG"] = "0"
+    del os.environ["AMMSB_COLS_NB"]
     t0 = timeit(loop)
     t1 = timeit(loop_pi)
     print("loopback update_pi: %.4f ms (phi %.4f, phi+pi %.4f)" % (t1 - t0, t0, t1))
