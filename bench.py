@@ -56,8 +56,9 @@ def parse_args():
     ap.add_argument("--m", type=int, default=16384, help="mini-batch edges per GPU")
     ap.add_argument("--n", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--store", default="auto", choices=["auto", "partitioned", "replicated"],
-                    help="multi-GPU pi layout: node-partitioned (NVLink peer loads) or one copy per GPU")
+    ap.add_argument("--store", default="auto", choices=["auto", "partitioned", "replicated", "columns"],
+                    help="multi-GPU pi layout: node-partitioned (NVLink peer loads), one copy per GPU, or "
+                         "column-sharded (every GPU holds K/G columns of every row; partial sums cross NVLink)")
     ap.add_argument("--collectives", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU exchange steps: own kernels over NVLink peer memory, or NCCL")
     ap.add_argument("--graph", default="auto", choices=["auto", "host", "device"],
@@ -107,6 +108,11 @@ def config_of(args, w, world):
         mode, coll, gmode = sharded_plan(args, w, world)
         cfg["graph"] = "built in HBM (csrc/graph.cu)" if gmode == "device" else "built on the host"
         cfg["parallelism"] = (
+            "pi column-sharded over %d GPUs (GPU g holds the K/%d columns of the reference work-items l = g mod %d "
+            "of every row: all row reads are local HBM), partial sums of update_phi / update_pi / update_beta / "
+            "perplexity exchanged inside the kernels through mailboxes in NVLink peer memory and completed in the "
+            "WG_SUM tree order (bit-identical to one GPU); no barrier or all-reduce launches" % (world, world, world)
+        ) if mode == "columns" else (
             ("pi/phi node-partitioned over %d GPUs (NVLink peer loads), " % world if mode == "partitioned" else
              "pi/phi replicated on %d GPUs (fits: %.1f GB), mini-batch slots split over GPUs, updated rows written "
              "to every copy by NVLink peer stores, " % (world, 4.0 * N * K / 1e9)) +

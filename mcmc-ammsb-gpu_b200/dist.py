@@ -158,17 +158,23 @@ class ShardedLearner:
         #                shards are read over NVLink (the layout for graphs that need G GPUs)
         #   replicated:  a full copy per GPU (when N*K*4 fits), reads are local HBM and every
         #                updated row is written to all copies over NVLink
-        assert store_mode in ("partitioned", "replicated")
+        #   columns:     GPU g holds the columns of the reference work-items l = g (mod G) of EVERY row
+        #                (csrc/cols.cu): all row reads are local HBM, partial sums cross NVLink inside
+        #                the kernels, no barrier / all-reduce launches at all
+        assert store_mode in ("partitioned", "replicated", "columns")
         self.store_mode = store_mode if world > 1 else "partitioned"
+        self.cols = None
         # Shards are allocated with the CUDA virtual-memory API and shared as file descriptors:
         # a cudaIpc import maps peer memory with small pages and NVLink row gathers from a
         # multi-GB shard drop to 195 GB/s (735 GB/s with full-size pages, tools/peer_probe.py).
         shareable = world > 1
-        if self.store_mode == "replicated":
+        if self.store_mode == "columns":
+            self.store = None
+        elif self.store_mode == "replicated":
             self.store = A.Store(self.ctx, self.N, self.K, 1, 0, shareable=shareable)
         else:
             self.store = A.Store(self.ctx, self.N, self.K, world, rank, shareable=shareable)
-        if world > 1:
+        if world > 1 and self.store is not None:
             mine = self.store.export_fds()
             for peer, (fd_pi, fd_phi) in sorted(exchange_fds(rank, world, mine).items()):
                 if self.store_mode == "replicated":
@@ -185,14 +191,15 @@ class ShardedLearner:
         #   "nccl": torch.distributed all-reduces (baseline / fallback)
         assert collectives in ("peer", "nccl")
         self.peer = None
-        if world > 1 and collectives == "peer":
+        if world > 1 and collectives == "peer" and self.store_mode != "columns":
             self.peer = A.Peer(self.ctx, world, rank, max(8 * self.K, 64))
             fd = self.peer.export_fd()
             for peer_rank, (pfd,) in sorted(exchange_fds(rank, world, [fd]).items()):
                 self.peer.attach_fd(peer_rank, pfd)
                 os.close(pfd)
             os.close(fd)
-        self.store.init_pi(float(self.p.eta0), float(self.p.eta1))
+        if self.store is not None:
+            self.store.init_pi(float(self.p.eta0), float(self.p.eta1))
         # ---- replicated: edge sets, theta/beta, RNG pools ----
         if graph is not None:
             self.train, self.heldout = graph.train, graph.heldout
@@ -211,6 +218,17 @@ class ShardedLearner:
         else:
             self.Vmax, self.Emax = cfg.max_nodes(), cfg.max_edges()
         n = self.n
+        if self.store_mode == "columns":
+            H_all = graph.H if graph is not None else len(cfg.edges()[1])
+            self.cols = A.Cols(self.ctx, self.N, self.K, world, rank, n, self.Vmax, self.Emax, H_all)
+            fd = self.cols.export_fd()
+            for peer_rank, (pfd,) in sorted(exchange_fds(rank, world, [fd]).items()):
+                self.cols.attach_fd(peer_rank, pfd)
+                os.close(pfd)
+            os.close(fd)
+            self.cols.init_pi(float(self.p.eta0), float(self.p.eta1))
+            self.cols.write_theta(theta, beta)
+            dist.barrier()  # every mailbox is mapped and armed before the first kernel writes into one
         self.npools = [A.Rng(self.ctx, self.Vmax * 2 * n, 56, 57) for _ in range(self.STREAMS)]
         self.ppool = A.Rng(self.ctx, self.Vmax * 32, 42, 43)
         self.bpool = A.Rng(self.ctx, self.K, 44, 45)
@@ -234,15 +252,15 @@ class ShardedLearner:
         self.h_edges = torch.empty(self.Emax, dtype=torch.int64).pin_memory()
         self.h_beta = torch.empty(2 * self.K, dtype=torch.float32).pin_memory()
         self.opts = A.PhiOpts(A.MODE_WG, 32, 0, 0, rank, world)
-        # ---- held-out pairs: this rank's chunk ----
+        # ---- held-out pairs: this rank's chunk (columns: every rank walks all pairs) ----
         if graph is not None:
             self.H = graph.H
-            lo, hi = chunk(self.H, rank, world)
+            lo, hi = chunk(self.H, rank, world) if self.cols is None else (0, self.H)
             self.hedges = _Buf(graph.d_heldout_pairs.ptr.value + 8 * lo)
         else:
             he = cfg.edges()[1]
             self.H = len(he)
-            lo, hi = chunk(self.H, rank, world)
+            lo, hi = chunk(self.H, rank, world) if self.cols is None else (0, self.H)
             self.d_hedges = torch.from_numpy(he[lo:hi].astype(np.int64)).to(dev) if hi > lo else \
                 torch.zeros(1, dtype=torch.int64, device=dev)
             self.hedges = tbuf(self.d_hedges)
@@ -369,6 +387,21 @@ class ShardedLearner:
         self.enqueue_neighbors(d_nodes, V, pool_index, seq)  # no-op when it was enqueued ahead
         d_nb = self.d_nbs[seq & 1]
         self.stream.wait_event(self.ev_ns[seq & 1])
+        if self.cols is not None:
+            # column shards: the exchange of partial sums happens inside the kernels (mailboxes in
+            # peer memory), so the iteration is four launches and no barrier or all-reduce
+            A = self.A
+            if phi_events is not None:
+                phi_events[0].record(self.stream)
+            A.cols_update_phi(ctx, [self.cols], p, self.opts, self.train, d_nodes, tbuf(d_nb), V, self.step_count,
+                              [self.ppool])
+            if phi_events is not None:
+                phi_events[1].record(self.stream)
+            self.ev_phi[seq & 1].record(self.stream)
+            A.cols_update_pi(ctx, [self.cols], d_nodes, V, self.step_count)
+            A.cols_update_beta(ctx, [self.cols], p, self.train, d_edges, E_mb, weight, self.step_count, [self.bpool])
+            self.edges_processed += E_mb
+            return
         if phi_events is not None:
             phi_events[0].record(self.stream)
         ctx.update_phi(p, self.opts, tbuf(self.beta), self.store, self.train, d_nodes, tbuf(d_nb), V,
@@ -407,7 +440,7 @@ class ShardedLearner:
         self.device_step(d_nodes, _Buf(base + self.HDR), V, E_mb, weight, t % self.STREAMS, seq=t + 1)
         self.ev_free[b].record(self.stream)
         self._issue(t + 1)  # travels while the kernels of t run
-        self.h_beta.copy_(self.beta, non_blocking=True)
+        self._copy_beta_to_host()
         self.t = t + 1
         return E_mb
 
@@ -440,9 +473,18 @@ class ShardedLearner:
         self.mb_meta[1 - b] = self.draw_device_minibatch()  # blocks the host, not the compute stream
         self.enqueue_neighbors(tbuf(self.mb_nodes[1 - b]), self.mb_meta[1 - b][2], (t + 1) % self.STREAMS, t + 2,
                                after=self.ev_mb_ready[1 - b])
-        self.h_beta.copy_(self.beta, non_blocking=True)
+        self._copy_beta_to_host()
         self.t = t + 1
         return E_mb
+
+    def _copy_beta_to_host(self):
+        """the D2H read of the step's result (beta[2K]) into pinned host memory"""
+        if self.cols is not None:
+            _, d_beta = self.cols.beta_ptrs()
+            self.A._ck(self.A.lib().ammsb_d2h_async(self.ctx.h, C.c_void_p(self.h_beta.data_ptr()), C.c_void_p(d_beta),
+                                                    C.c_size_t(8 * self.K)))
+        else:
+            self.h_beta.copy_(self.beta, non_blocking=True)
 
     def run(self, iters):
         for _ in range(iters):
@@ -453,6 +495,11 @@ class ShardedLearner:
 
     def heldout_perplexity(self):
         self.ppx_calls += 1
+        if self.cols is not None:
+            avg, _ = self.A.cols_perplexity(self.ctx, [self.cols], self.p, self.heldout, self.hedges, self.H,
+                                            self.ppx_calls)
+            self.cols.check()
+            return float(np.exp(np.float32(avg[0])))
         if self.H_local > 0:
             self.ctx.perplexity_partial(self.p, self.store, tbuf(self.beta), self.heldout, self.hedges,
                                         self.H_local, tbuf(self.d_ppx), self.ppx_calls, tbuf(self.sums), tbuf(self.pws))
@@ -468,13 +515,22 @@ class ShardedLearner:
 
     # ------------------------------------------------------------- state ----
     def read_local_pi(self):
-        """rows this rank holds: its shard (partitioned) or the whole matrix (replicated)"""
+        """rows this rank holds: its shard (partitioned) or the whole matrix (replicated); columns:
+        all rows, with only the columns this rank owns filled in (the others are NaN)"""
+        if self.cols is not None:
+            out = np.full((self.N, self.K), np.nan, np.float32)
+            return self.cols.read_pi(out)
         return self.store.read_pi()
 
     def local_rows(self):
+        if self.cols is not None:
+            return 0, self.N
         return self.store.first_row, self.store.first_row + self.store.local_rows
 
     def read_beta(self):
+        if self.cols is not None:
+            self.torch.cuda.synchronize()
+            return self.cols.read_theta()[1]
         return self.beta.cpu().numpy()
 
 
@@ -599,7 +655,20 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     local_bytes = float(sum((V / world) * ((n + 2) * 4 * K + 68 * n + 8) for V in Vs))  # per GPU
-    if mode == "partitioned":
+    if mode == "columns":
+        # every GPU walks ALL slots on its K/G columns: local HBM bytes per GPU are those of the
+        # one-GPU kernel at the global mini-batch divided by G; NVLink carries 4 bytes per
+        # (slot, neighbor, peer)
+        col_bytes = float(sum(V * ((n + 2) * 4 * K / world + 68 * n + 8) for V in Vs))
+        ach = col_bytes / (phi_ms * 1e-3) / 1e9
+        out_bytes = float(sum(V * (n + 1) * 4 * (world - 1) for V in Vs))
+        roofline = {"bound": "hbm", "kernel": "k_cols_phi2 (per GPU, column-sharded pi)", "unit": "GB/s",
+                    "achieved": round(ach, 1), "peak": hbm_peak, "frac": round(ach / hbm_peak, 4),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)", "traffic": None,
+                    "share_of_step": round(phi_ms / dev_ms, 4),
+                    "nvlink_outbound_GB_per_gpu_per_step": round(out_bytes / args.steps / 1e9, 4),
+                    "nvlink_outbound_GBps": round(out_bytes / (phi_ms * 1e-3) / 1e9, 1)}
+    elif mode == "partitioned":
         # update_phi is bound by the neighbor rows that cross the switch into each GPU
         remote_bytes = float(sum((V / world) * n * 4 * K * (world - 1) / world for V in Vs))
         ach = remote_bytes / (phi_ms * 1e-3) / 1e9

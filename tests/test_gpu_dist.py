@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,coll", [("partitioned", "peer"), ("replicated", "peer"), ("partitioned", "nccl")])
+@pytest.mark.parametrize("mode,coll", [("partitioned", "peer"), ("replicated", "peer"), ("partitioned", "nccl"), ("columns", "peer")])
 def test_sharded_driver_matches_single_gpu(mode, coll):
     n = A.device_count()
     if n < 2:
