@@ -342,6 +342,12 @@ int ammsb_cols_check(ammsb_cols* cols, uint32_t* timed_out); /* 1: an exchange w
  * (perplexity.cc:251-274) on the column shards; pools[i] is rank i's RNG pool of the operator
  * (same sizes and seeds as on one GPU: a rank only touches the states of its own lanes/columns).
  * step_count / call_count also select the mailbox half and must agree on every rank. */
+/* NeighborSampler::operator() (sample.h:16-28) partitioned over the ranks: the reference work-item
+ * gid (state gid of the sampler pool) runs on rank gid % world and delivers its slots' lists to
+ * every rank's mailbox; ammsb_cols_update_phi with d_neighbors == NULL reads them there.  Same
+ * lists as ammsb_neighbor_sample. */
+int ammsb_cols_neighbor_sample(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv, const uint32_t* d_nodes,
+                               uint32_t V, uint32_t wg, uint32_t step_count, ammsb_rng* const* pools);
 int ammsb_cols_update_phi(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
                           const ammsb_phi_opts* opts, ammsb_set* train, const uint32_t* d_nodes,
                           const uint32_t* d_neighbors, uint32_t V, uint32_t step_count, ammsb_rng* const* pools);

@@ -64,6 +64,7 @@ struct ColsBoxLayout {
   size_t theta, beta;          // [2K] floats each (interleaved like the reference's buffers)
   size_t S, R, B, P;           // region bases
   size_t S_src, R_src, B_src, P_src;   // bytes per source
+  size_t NB, NB_third;         // sampled neighbor lists [3][Vcap * n] u32 (step % 3), written by the rank that owns the sampler state
   size_t bytes;
 };
 
@@ -75,7 +76,7 @@ struct ammsb_cols {
   uint64_t Hcap = 0;
   uint32_t KG = 0;
   float *d_pi = nullptr, *d_phi = nullptr, *d_phi_vec = nullptr, *d_ppx = nullptr, *d_ws = nullptr;
-  float* d_nz = nullptr;  // Langevin noise rows of the groups in flight: [resident warps][G][KG]
+  float* d_nz = nullptr;  // Langevin noise rows of the groups in flight: [resident warps][2][G][KG]
   size_t nz_warps = 0;
   double* d_ws_d = nullptr;
   ColsBoxLayout lay;
@@ -120,6 +121,8 @@ static ColsBoxLayout cols_layout(uint32_t K, uint32_t G, uint32_t n, uint32_t Vc
   l.R = off; off += 2 * (size_t)G * l.R_src;
   l.B = off; off += 2 * (size_t)G * l.B_src;
   l.P = off; off += 2 * (size_t)G * l.P_src;
+  l.NB_third = align_up((size_t)Vcap * n * 4, 256);
+  l.NB = off; off += 3 * l.NB_third;
   l.bytes = off;
   return l;
 }
@@ -212,6 +215,7 @@ struct ColsPhiArgs {
   uint32_t V, n, units;
   uint32_t R, D, MB;  // ring depth, A -> B distance (trips), metadata buffers
   uint32_t parity, disable_noise, loopback;
+  uint32_t nb_poll, nb_third;  // the neighbor lists are the mailbox region NB (third step % 3): words arrive from the rank that sampled them
   uint32_t debug;  // timing ablations (AMMSB_COLS_DEBUG): 1 no cuckoo, 2 no phase A math, 4 no phase B math, 8 no loads, 16 no Langevin step
   float eps_t, alpha, epsilon, Nn;
 };
@@ -767,28 +771,72 @@ __global__ void __launch_bounds__(384, 1) k_cols_phi2(const __grid_constant__ Co
   const uint32_t ngroups = (active_units + G - 1) / G;
   const uint32_t passes = (a.V + a.units - 1) / a.units;
   const uint32_t gwarp = cta * warps + wib, total_warps = a.ctas_per_rank * warps;
-  float* const my_nz = nz_scratch + ((size_t)vr * total_warps + gwarp) * G * KG;  // [G][KG]
+  float* const my_nz = nz_scratch + ((size_t)vr * total_warps + gwarp) * 2 * G * KG;  // [2][G][KG]
 
   // noise lanes: lane = (slot s_n of the group, reference lane li_n)
   const uint32_t s_n = lane / LPG, li_n = lane % LPG, l_ref = rank + G * li_n;
 
-  for (uint32_t group = gwarp; group < ngroups; group += total_warps) {
-    Rng st;
-    st.x = st.y = 0;
-    const uint32_t unit_n = group * G + s_n;
-    if (!a.disable_noise && unit_n < active_units) st = rng_load(my_pool, (uint64_t)unit_n * 32 + l_ref);
-    for (uint32_t pass = 0; pass < passes; ++pass) {
-      if ((size_t)group * G + (size_t)pass * a.units >= a.V) break;  // no live slot in this and later passes
-      // ---- the Langevin noise of the group-pass's G slots (phi.cc:266-274 draw order) ----
-      {
-        const uint32_t slot_n = unit_n + pass * a.units;
-        if (!a.disable_noise && unit_n < active_units && slot_n < a.V && !(a.debug & 16)) {
-          float* row = my_nz + (size_t)s_n * KG;
-#pragma unroll 4
-          for (int i = 0; i < KPL; ++i) row[((i >> 2) * LPG + li_n) * 4 + (i & 3)] = rng_randn_t(st, zig);
-        }
-        __syncwarp();
+  // The Langevin noise (phi.cc:266-274) of a group-pass is drawn one group-pass AHEAD of its use, a
+  // float4 of every lane's stream at a time, inside the waits for the peers' partial sums: the
+  // sequential draw chains fill time in which the warp would otherwise only poll.  `nz_*` is that
+  // cursor; the noise of a group-pass alternates between the two halves of the scratch rows.
+  constexpr int PIECES = KPL / 4;
+  auto gp_live = [&](uint32_t group, uint32_t pass) -> bool {
+    return group < ngroups && (size_t)group * G + (size_t)pass * a.units < a.V;
+  };
+  auto next_gp = [&](uint32_t& group, uint32_t& pass) {
+    do {
+      if (++pass == passes) {
+        pass = 0;
+        group += total_warps;
       }
+    } while (group < ngroups && !gp_live(group, pass));
+  };
+  uint32_t nz_group = gwarp, nz_pass = 0, nz_piece = 0, nz_half = 0;
+  Rng st;
+  st.x = st.y = 0;
+  const bool noisy = !a.disable_noise && !(a.debug & 16);
+  if (noisy && nz_group < ngroups && nz_group * G + s_n < active_units)
+    st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
+  // one float4 (4 consecutive draws of every lane's stream) of the cursor's group-pass
+  auto noise_piece = [&]() {
+    if (!noisy || nz_group >= ngroups || nz_piece >= (uint32_t)PIECES) return;
+    const uint32_t unit = nz_group * G + s_n, slot = unit + nz_pass * a.units;
+    if (unit < active_units && slot < a.V) {
+      float4 z;
+      z.x = rng_randn_t(st, zig);
+      z.y = rng_randn_t(st, zig);
+      z.z = rng_randn_t(st, zig);
+      z.w = rng_randn_t(st, zig);
+      reinterpret_cast<float4*>(my_nz + ((size_t)nz_half * G + s_n) * KG)[nz_piece * LPG + li_n] = z;
+    }
+    ++nz_piece;
+  };
+  // the cursor moves on to the next group-pass (its current one must be complete)
+  auto noise_advance = [&]() {
+    if (nz_group >= ngroups) return;
+    const uint32_t old = nz_group;
+    next_gp(nz_group, nz_pass);
+    nz_piece = 0;
+    nz_half ^= 1;
+    if (noisy && nz_group != old) {  // the old group's streams are finished: persist, load the new ones
+      if (old * G + s_n < active_units) rng_store(my_pool, (uint64_t)(old * G + s_n) * 32 + l_ref, st);
+      if (nz_group < ngroups && nz_group * G + s_n < active_units)
+        st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
+    }
+  };
+  // prologue: the whole noise of the warp's first group-pass
+  if (gwarp < ngroups) {
+    for (int k = 0; k < PIECES; ++k) noise_piece();
+    __syncwarp();
+    noise_advance();
+  }
+
+  uint32_t group = gwarp, pass = 0;
+  for (; group < ngroups; next_gp(group, pass)) {
+    {
+      const uint32_t use_half = nz_half ^ 1;  // the half the cursor filled before it moved on
+      {
       for (uint32_t s = 0; s < (uint32_t)G; ++s) {
         const uint32_t unit = group * G + s, slot = unit + pass * a.units;
         if (unit >= active_units || slot >= a.V) break;  // warp-uniform; later sub-slots are dead too
@@ -803,7 +851,14 @@ __global__ void __launch_bounds__(384, 1) k_cols_phi2(const __grid_constant__ Co
           const uint32_t cnt = min(32u, n - c0);
           // ---- stage the pieces: neighbor b of the chunk -> row b; the own piece -> row 32 ----
           uint32_t nb = node;
-          if (lane < cnt) nb = __ldg(&a.neighbors[(size_t)slot * n + c0 + lane]);
+          if (lane < cnt) {
+            if (a.nb_poll) {  // sampled on the rank that owns the slot's sampler state, delivered by peer stores
+              uint32_t* w = reinterpret_cast<uint32_t*>(mybox + a.lay.NB + (size_t)a.nb_third * a.lay.NB_third) + (size_t)slot * n + c0 + lane;
+              nb = __float_as_uint(finish_poll(w, peek_mbox(w), err));
+            } else {
+              nb = __ldg(&a.neighbors[(size_t)slot * n + c0 + lane]);
+            }
+          }
           if (!(a.debug & 8)) {
             if (F4 >= 32) {
 #pragma unroll 8
@@ -890,6 +945,9 @@ __global__ void __launch_bounds__(384, 1) k_cols_phi2(const __grid_constant__ Co
             for (int p = 0; p < G; ++p)
               if ((uint32_t)p != rank)
                 st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + sidx, bits);
+          }
+          if (c0 == 0) noise_piece();  // while the partials cross the switch: part of the next group-pass's noise
+          if (lane < cnt && !a.loopback) {
             uint32_t w[G];
 #pragma unroll
             for (int p = 0; p < G; ++p)
@@ -954,7 +1012,7 @@ __global__ void __launch_bounds__(384, 1) k_cols_phi2(const __grid_constant__ Co
         }
         // ---- Langevin step (phi.cc:266-274): lane = columns; the new piece replaces the own piece ----
         if (!(a.debug & 16)) {
-          const float* nzrow = my_nz + (size_t)s * KG;
+          const float* nzrow = my_nz + ((size_t)use_half * G + s) * KG;
 #pragma unroll
           for (int r = 0; r < FPL; ++r) {
             const uint32_t f = lane + 32 * r;
@@ -992,10 +1050,16 @@ __global__ void __launch_bounds__(384, 1) k_cols_phi2(const __grid_constant__ Co
           __syncwarp();  // s_own is free for the next slot's own piece
         }
       }
+      }
+      // what is left of the next group-pass's noise, then the cursor moves on
+      while (noisy && nz_group < ngroups && nz_piece < (uint32_t)PIECES) noise_piece();
+      __syncwarp();
+      noise_advance();
     }
-    if (!a.disable_noise && unit_n < active_units) rng_store(my_pool, (uint64_t)unit_n * 32 + l_ref, st);
   }
+  // the last group's streams (the cursor has run past the end: nothing left to persist otherwise)
 }
+
 
 // ---- update_pi on the column shards (phi.cc:154-197): pi[node][own columns] = phi_vec / sum ----
 struct ColsPiArgs {
@@ -1378,6 +1442,65 @@ __global__ void __launch_bounds__(128) k_cols_ppx_reduce(const __grid_constant__
   if (lane == 0) me.ws_d[(size_t)P * 4 + q] = s;
 }
 
+// ---- NeighborSampler (sample.cc:13-121) partitioned over the ranks ----
+// The reference work-item gid owns sampler state gid and serves the slots gid, gid + gsize, ...;
+// rank gid % G runs it (state ownership is static, so the lists do not depend on G) and delivers
+// every list to ALL ranks' mailboxes with peer stores.  A list word is self-validating like a
+// partial sum (ids are < N < 0xffffffff); the thirds of the region rotate with step % 3, so a word
+// is re-armed by its reader two kernel boundaries before it is written again.
+struct ColsNsArgs {
+  ColsRankView r[AMMSB_MAX_SHARDS];
+  ColsBoxLayout lay;
+  const uint32_t* nodes;
+  uint32_t nv, G, V, N, n, gsize, third, per_rank_blocks;
+};
+
+__global__ void __launch_bounds__(64) k_cols_neighbor_sample(const __grid_constant__ ColsNsArgs a) {
+  extern __shared__ uint32_t s_tab[];
+  const uint32_t vr = blockIdx.x / a.per_rank_blocks, blk = blockIdx.x % a.per_rank_blocks;
+  const ColsRankView& me = a.r[vr];
+  const uint32_t t = blk * blockDim.x + threadIdx.x;
+  const uint32_t gid = me.rank + a.G * t;  // the reference work-items of this rank
+  const uint32_t capacity = 2 * a.n, N = a.N, n = a.n;
+  if (gid >= a.gsize || gid >= a.V) return;
+  Rng seed = rng_load(me.pool, gid);
+  uint32_t* tab = s_tab + threadIdx.x;
+  const uint32_t stride = blockDim.x;
+  for (uint32_t i = gid; i < a.V; i += a.gsize) {
+    const uint32_t node = a.nodes[i];
+    for (uint32_t j = 0; j < capacity; ++j) tab[j * stride] = N;
+    for (uint32_t j = 0; j < n; ++j) {
+      uint32_t r, val;
+      do {
+        do {
+          r = (uint32_t)(rng_next(seed) % (uint64_t)N);  // randint(seed, 0, N - 1), random.cl.inc:37-39
+        } while (r == node);
+        const uint32_t l1 = (r ^ 553105253u) % capacity;
+        const uint32_t l2 = 1u + (capacity << 1);
+        for (uint32_t q = 0;; ++q) {
+          const uint32_t off = (l1 + q * l2) % capacity;
+          val = tab[off * stride];
+          if (val == r) break;
+          if (val == N) {
+            tab[off * stride] = r;
+            break;
+          }
+        }
+      } while (val == r);
+    }
+    uint32_t count = 0;
+    for (uint32_t j = 0; j < capacity && count < n; ++j) {
+      const uint32_t v = tab[j * stride];
+      if (v != N) {
+        for (uint32_t p = 0; p < a.G; ++p)
+          st_mbox(reinterpret_cast<uint32_t*>(me.box[p] + a.lay.NB + (size_t)a.third * a.lay.NB_third) + (size_t)i * n + count, v);
+        ++count;
+      }
+    }
+  }
+  rng_store(me.pool, gid, seed);
+}
+
 // ---- init / host access ----
 // RandomGammaAndNormalize (random.cc:131-167) on the column shards: every rank walks the whole
 // gamma stream of every row (group per row, state = group*32 + lane, pool seeded {11,113}) -- the
@@ -1459,7 +1582,7 @@ extern "C" int ammsb_cols_create(ammsb_ctx* c, uint64_t N, uint32_t K, uint32_t 
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ws, sizeof(float) * 2 * s->KG * (size_t)s->ws_ctas);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_ws_d, sizeof(double) * 4 * ((size_t)s->ws_ctas + 1));
   s->nz_warps = (size_t)c->sm_count * 32;
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_nz, sizeof(float) * s->nz_warps * K);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_nz, sizeof(float) * s->nz_warps * K * 2);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->d_ppx, 0, sizeof(float) * (max_pairs ? max_pairs : 1), c->stream);
   if (e != cudaSuccess || vmm_alloc(c->device, s->lay.bytes, &s->local)) {
     cudaFree(s->d_pi); cudaFree(s->d_phi); cudaFree(s->d_phi_vec); cudaFree(s->d_ppx); cudaFree(s->d_ws); cudaFree(s->d_ws_d); cudaFree(s->d_nz);
@@ -1780,6 +1903,8 @@ extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uin
   a.lay = s0->lay;
   a.nodes = d_nodes;
   a.neighbors = d_neighbors;
+  a.nb_poll = d_neighbors == nullptr;  // the lists of ammsb_cols_neighbor_sample (per rank: set below)
+  a.nb_third = step_count % 3;
   a.V = V;
   a.n = p->num_neighbors;
   a.parity = step_count & 1;
@@ -1792,6 +1917,7 @@ extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uin
   a.Nn = (1.0f * p->N) / p->num_neighbors;  // phi.cc:113
   const uint32_t kpl = p->K / 32, G = s0->G;
   const bool staged = getenv("AMMSB_COLS_STAGED") != nullptr;  // the per-neighbor stage-ring kernel (A/B measurements)
+  AMMSB_REQUIRE(!(staged && a.nb_poll), "the stage-ring kernel needs the neighbor lists as an argument");
 #define COLS_PHI_CASE(KPL_, G_)                                                                              \
   if (kpl == KPL_ && G == G_)                                                                                \
     return staged ? cols_phi_launch<KPL_, G_>(c, a, nv)                                                      \
@@ -1803,6 +1929,44 @@ extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uin
 #undef COLS_PHI_CASE
   AMMSB_REQUIRE(false, "unsupported (K, world) for the column layout");
   return 1;
+}
+
+extern "C" int ammsb_cols_neighbor_sample(ammsb_ctx* c, ammsb_cols* const* ranks, uint32_t nv, const uint32_t* d_nodes,
+                                          uint32_t V, uint32_t wg, uint32_t step_count, ammsb_rng* const* pools) {
+  if (cols_ready(ranks, nv)) return 1;
+  const ammsb_cols* s0 = ranks[0];
+  AMMSB_REQUIRE(V > 0 && V <= s0->Vcap, "bad mini-batch size");  // learner.cc:179
+  AMMSB_REQUIRE(wg > 0 && (uint64_t)s0->n < s0->N, "bad sampler geometry");
+  AMMSB_CHECK_CUDA(cudaSetDevice(c->device));
+  ColsNsArgs a;
+  memset(&a, 0, sizeof a);
+  // sample.cc:116-119: global = min(ceil(V/wg), 65535/wg) * wg
+  uint32_t groups = V / wg + (V % wg ? 1 : 0);
+  if (groups > 65535u / wg) groups = 65535u / wg;
+  a.gsize = groups * wg;
+  const uint32_t active = a.gsize < V ? a.gsize : V;
+  for (uint32_t i = 0; i < nv; ++i) {
+    AMMSB_REQUIRE(pools && pools[i] && pools[i]->n >= active, "Num seeds smaller than global threads");
+    a.r[i] = ranks[i]->view(pools[i]->d_state);
+  }
+  a.lay = s0->lay;
+  a.nodes = d_nodes;
+  a.nv = nv;
+  a.G = s0->G;
+  a.V = V;
+  a.N = (uint32_t)s0->N;
+  a.n = s0->n;
+  a.third = step_count % 3;
+  const uint32_t block = 64;
+  const uint32_t mine = (active + s0->G - 1) / s0->G;  // work-items of one rank
+  a.per_rank_blocks = (mine + block - 1) / block;
+  const size_t smem = sizeof(uint32_t) * 2 * s0->n * block;
+  AMMSB_REQUIRE(smem <= c->smem_optin, "num_node_sample too large for the shared-memory table");
+  if (smem > 48 * 1024)
+    AMMSB_CHECK_CUDA(cudaFuncSetAttribute(k_cols_neighbor_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cols_neighbor_sample<<<a.per_rank_blocks * nv, block, smem, c->stream>>>(a);
+  AMMSB_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int ammsb_cols_update_pi(ammsb_ctx* c, ammsb_cols* const* ranks, uint32_t nv, const uint32_t* d_nodes,

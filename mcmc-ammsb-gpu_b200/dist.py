@@ -375,7 +375,12 @@ class ShardedLearner:
         self.ns_stream.wait_event(self.ev_phi[b])  # update_phi of mini-batch seq-2 is done with the buffer
         if after is not None:
             self.ns_stream.wait_event(after)  # the nodes are on this GPU
-        self.ctx_ns.neighbor_sample(self.npools[pool_index], d_nodes, V, self.N, self.n, 32, tbuf(self.d_nbs[b]))
+        if self.cols is not None:
+            # each rank draws the lists of the sampler states it owns and delivers them to every
+            # rank's mailbox (third seq % 3); update_phi of step seq reads them there
+            self.A.cols_neighbor_sample(self.ctx_ns, [self.cols], d_nodes, V, 32, seq, [self.npools[pool_index]])
+        else:
+            self.ctx_ns.neighbor_sample(self.npools[pool_index], d_nodes, V, self.N, self.n, 32, tbuf(self.d_nbs[b]))
         self.ev_ns[b].record(self.ns_stream)
         self.ns_seq = seq
 
@@ -393,7 +398,8 @@ class ShardedLearner:
             A = self.A
             if phi_events is not None:
                 phi_events[0].record(self.stream)
-            A.cols_update_phi(ctx, [self.cols], p, self.opts, self.train, d_nodes, tbuf(d_nb), V, self.step_count,
+            assert seq == self.step_count  # the sampler delivered the lists under this step number
+            A.cols_update_phi(ctx, [self.cols], p, self.opts, self.train, d_nodes, None, V, self.step_count,
                               [self.ppool])
             if phi_events is not None:
                 phi_events[1].record(self.stream)

@@ -601,9 +601,15 @@ def _handles(objs):
     return (C.c_void_p * len(objs))(*[o.h if o is not None else None for o in objs])
 
 
+def cols_neighbor_sample(ctx, ranks, d_nodes, V, wg, step, pools):
+    _ck(lib().ammsb_cols_neighbor_sample(ctx.h, _handles(ranks), len(ranks), d_nodes.ptr, V, wg, step, _handles(pools)))
+
+
 def cols_update_phi(ctx, ranks, p, opts, train, d_nodes, d_neighbors, V, step, pools):
+    """d_neighbors None: the lists delivered by cols_neighbor_sample for the same step"""
     _ck(lib().ammsb_cols_update_phi(ctx.h, _handles(ranks), len(ranks), C.byref(p), C.byref(opts), train.h,
-                                    d_nodes.ptr, d_neighbors.ptr, V, step, _handles(pools)))
+                                    d_nodes.ptr, d_neighbors.ptr if d_neighbors is not None else None, V, step,
+                                    _handles(pools)))
 
 
 def cols_update_pi(ctx, ranks, d_nodes, V, step):

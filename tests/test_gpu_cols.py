@@ -287,3 +287,38 @@ def test_cols_init_pi_equals_one_gpu_init(ctx, orc, G, N, K):
     for a in rk.r:
         assert np.array_equal(a.read_phi(), want_phi)
     rk.free()
+
+
+@pytest.mark.parametrize("G,V,n", [(8, 300, 32), (4, 1000, 16), (2, 70001, 8)])
+def test_cols_neighbor_sampler_equals_one_gpu_sampler(ctx, orc, G, V, n):
+    """the sampler partitioned by state ownership (work-item gid on rank gid % G) delivers the lists
+    of ammsb_neighbor_sample to every rank's mailbox; update_phi reads them there"""
+    N, K = max(2 * V, 800), 128
+    prob = Problem(orc, N, K, 6 * N, n)
+    nodes = prob.minibatch_nodes(V, 5)
+    d_nodes = ctx.from_host(nodes)
+    pool1 = A.Rng(ctx, max(V, 64) * 2 * n, 56, 57)
+    d_nb = ctx.buf(np.uint32, V * n)
+    ctx.neighbor_sample(pool1, d_nodes, V, N, n, 32, d_nb)
+    want = d_nb.read().reshape(V, n)
+    rk = Ranks(ctx, prob, G, V)
+    npools = [A.Rng(ctx, max(V, 64) * 2 * n, 56, 57) for _ in range(G)]
+    step = 5
+    A.cols_neighbor_sample(ctx, rk.r, d_nodes, V, 32, step, npools)
+    # sampler state gid is advanced by rank gid % G only
+    st = np.stack([p.get_state() for p in npools])
+    gid = np.arange(st.shape[1])
+    assert np.array_equal(st[gid % G, gid], pool1.get_state())
+    # update_phi from the delivered lists == update_phi from the explicit ones (and == one GPU)
+    one = one_gpu_phi_pi(ctx, prob, nodes, want, step, True)
+    pools = [A.Rng(ctx, min(V, 65535) * 32, 42, 43) for _ in range(G)]
+    dset = dev_set(ctx, prob.train_set)
+    A.cols_update_phi(ctx, rk.r, dev_params(prob.p_orc), A.PhiOpts(A.MODE_WG, 32, 0, 0), dset, d_nodes, None, V, step, pools)
+    ctx.sync()
+    rk.check()
+    assert np.array_equal(rk.phi_vec(V), one["vec"])
+    for b in (d_nodes, d_nb):
+        b.free()
+    for p in pools + npools + [pool1]:
+        p.free()
+    dset.free(); rk.free()
