@@ -1736,6 +1736,16 @@ extern "C" int ammsb_cols_check(ammsb_cols* s, uint32_t* timed_out) {
   return ammsb_d2h(s->ctx, timed_out, s->box[s->rank], 4);
 }
 
+// The exchange kernels are persistent, fill the SMs they are given and wait for the other ranks.
+// A library kernel that ALSO waits for a peer (an NCCL broadcast on another stream) must always
+// find an SM, or the two waits can lock each other out across GPUs: the cooperative grids leave a
+// few SMs free (AMMSB_COLS_SPARE_SMS, default 4; pair with NCCL_MAX_NCHANNELS <= that).
+static uint32_t cols_usable_sms(const ammsb_ctx* c) {
+  uint32_t spare = 4;
+  if (const char* e = getenv("AMMSB_COLS_SPARE_SMS")) spare = (uint32_t)atoi(e);
+  return (uint32_t)c->sm_count > spare + 1 ? (uint32_t)c->sm_count - spare : 1u;
+}
+
 static int cols_ready(ammsb_cols* const* ranks, uint32_t nv) {
   AMMSB_REQUIRE(nv >= 1 && nv <= AMMSB_MAX_SHARDS, "bad number of ranks in one launch");
   for (uint32_t i = 0; i < nv; ++i) {
@@ -1800,7 +1810,7 @@ static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_
   int occ = 0;
   AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
   AMMSB_REQUIRE(occ > 0, "column update_phi: kernel does not fit on an SM");
-  const uint32_t resident = (uint32_t)occ * c->sm_count;
+  const uint32_t resident = (uint32_t)occ * cols_usable_sms(c);
   const uint32_t active = a.units < a.V ? a.units : a.V;
   const uint32_t ngroups = (active + G - 1) / G;
   uint32_t ctas = resident / nv;
@@ -2000,7 +2010,7 @@ static int cols_beta_launch(ammsb_ctx* c, ColsBetaArgs& a, uint32_t nv, uint32_t
   uint32_t ctas = (trips + 3) / 4;
   int occ = 0;  // every CTA must be resident: its warps wait for the same warps of the peers
   AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cols_beta<KPL, G>, 128, 0));
-  uint32_t cap = (uint32_t)c->sm_count * (uint32_t)occ / nv;
+  uint32_t cap = cols_usable_sms(c) * (uint32_t)occ / nv;
   if (cap > ws_ctas) cap = ws_ctas;
   if (ctas > cap) ctas = cap;
   if (ctas == 0) ctas = 1;
@@ -2066,7 +2076,7 @@ static int cols_ppx_launch(ammsb_ctx* c, ColsPpxArgs& a, uint32_t nv, uint32_t w
   uint32_t ctas = (trips + 3) / 4;
   int occ = 0;
   AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cols_ppx<KPL, G>, 128, 0));
-  uint32_t cap = (uint32_t)c->sm_count * (uint32_t)occ / nv;
+  uint32_t cap = cols_usable_sms(c) * (uint32_t)occ / nv;
   if (cap > ws_ctas) cap = ws_ctas;
   if (ctas > cap) ctas = cap;
   if (ctas == 0) ctas = 1;

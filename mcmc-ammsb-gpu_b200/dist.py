@@ -551,6 +551,11 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
 
     for k, v in (("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29541"), ("RANK", "0"), ("WORLD_SIZE", "1")):
         os.environ.setdefault(k, v)  # a plain `python bench.py --graph device` run on one GPU
+    if plan[0] == "columns":
+        # the column kernels are persistent and wait for the other ranks; an NCCL kernel (the
+        # mini-batch broadcast of the host path) that waits for a peer as well must always find an
+        # SM: the kernels leave 4 SMs free (csrc/cols.cu) and NCCL is held to 2 channels
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N, E, K, n = w["N"], w["E"], w["K"], w["n"]
     m = w["m"] * world
@@ -584,6 +589,61 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
         def make_learner(prefetch):
             return ShardedLearner(cfg, rank, world, local_rank, prefetch=prefetch, store_mode=mode, collectives=coll)
     log("graph + split + sets (%s): %.1fs" % (gmode, time.time() - t0))
+
+    # ---- parity of the sharded run against ONE GPU, in the run itself: one iteration on the same
+    #      (non-link) mini-batch from the same initial state, pi compared bit for bit on the rows /
+    #      columns this rank holds (results must not depend on the GPU count) ----
+    parity = "skipped: a full copy of pi (%.0f GB) beside the shard does not fit one GPU" % (4.0 * N * K / 1e9)
+    if world > 1 and 4.0 * N * K <= 60e9 and not os.environ.get("AMMSB_BENCH_NO_PARITY"):
+        os.environ["AMMSB_PHI_NOSPLIT"] = "1"  # one association of the gradient sum on both sides
+        try:
+            pl = make_learner(False)
+            if graph is not None:
+                single = ShardedLearner(None, 0, 1, local_rank, graph=graph, shape=(K, n, m))
+            else:
+                single = ShardedLearner(cfg, 0, 1, local_rank, prefetch=False)
+            mb = None
+            for _ in range(8):  # the first non-link mini-batch of the stream
+                if graph is not None:
+                    d_e = pl.ctx.buf(np.uint64, pl.Emax)
+                    d_n = pl.ctx.buf(np.uint32, pl.Vmax)
+                    wgt, E_mb, V = pl.draw_device_minibatch(d_e, d_n)
+                    torch.cuda.synchronize()
+                else:
+                    wgt, edges, nodes = pl.next_minibatch()
+                    E_mb, V = len(edges), len(nodes)
+                    d_e, d_n = pl.ctx.from_host(edges), pl.ctx.from_host(nodes)
+                if V > 1024:
+                    mb = (wgt, E_mb, V, d_e, d_n)
+                    break
+                d_e.free(); d_n.free()
+            if mb is None:
+                parity = "skipped: no non-link mini-batch among the first 8"
+            else:
+                wgt, E_mb, V, d_e, d_n = mb
+                for L in (pl, single):
+                    L.device_step(d_n, d_e, V, E_mb, wgt, 0)
+                torch.cuda.synchronize()
+                dist.barrier()
+                nodes_h = d_n.read()[:V].astype(np.int64)
+                a_pi, b_pi = pl.read_local_pi(), single.read_local_pi()
+                lo, hi = pl.local_rows()
+                b_pi = b_pi[lo:hi]
+                own = ~np.isnan(a_pi)
+                same = bool(np.array_equal(a_pi[own], b_pi[own]))
+                changed = int((b_pi[nodes_h[(nodes_h >= lo) & (nodes_h < hi)] - lo] != 0).any(axis=1).sum())
+                ok = torch.tensor([1.0 if same and changed > 0 else 0.0], device="cuda")
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                parity = ("ok: pi after one iteration (mini-batch of %d edges, %d nodes) bit-identical to the same "
+                          "iteration on one GPU, on every rank" % (E_mb, V)) if float(ok[0]) == 1.0 else "FAILED"
+                d_e.free(); d_n.free()
+            del pl, single
+            torch.cuda.empty_cache()
+        finally:
+            del os.environ["AMMSB_PHI_NOSPLIT"]
+        log("parity vs one GPU: %s" % parity)
+        if parity == "FAILED":
+            raise SystemExit("bench.py: the sharded run differs from the one-GPU run")
     lrn = make_learner(False)
     stream = lrn.stream
     ctx = lrn.ctx
@@ -737,6 +797,7 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
             "config": config,
             "iterations_per_s": args.steps / (dev_ms * 1e-3), "perplexity_eval_s": ppx_s, "heldout_perplexity": ppx,
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
+            "parity_vs_n1": parity,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
