@@ -176,6 +176,23 @@ int ammsb_minibatch_nonlink(ammsb_sampler* sampler, ammsb_ctx* ctx, uint32_t u, 
 int ammsb_minibatch_link(ammsb_ctx* ctx, uint32_t u, uint32_t degree, const uint64_t* d_offsets,
                          const uint32_t* d_adj, uint64_t* d_edges, uint32_t* d_nodes);
 
+/* ---- the reference's emission ORDER on the device.  The reference emits a mini-batch in the
+ *      iteration order of libstdc++'s std::unordered_set (edges: sample.cc:267,290; nodes:
+ *      ExtractNodesFromMiniBatch, learner.cc:162-173).  ammsb_orderset_apply turns keys in insertion
+ *      order (no duplicates; std::hash of an integer is the identity) into that iteration order;
+ *      ammsb_minibatch_finish is the tail of a device strategy: d_edges (E edges in insertion
+ *      order -- what ammsb_minibatch_nonlink / _link produce) are reordered in place, d_nodes
+ *      receives the endpoints' unordered_set<Vertex> order, *num_nodes their count (waits for the
+ *      stream).  With the adjacency in the host Graph's order (data.cc:12-25) the Node strategy on
+ *      the device is then bit-identical to sampleNode + ExtractNodesFromMiniBatch.
+ *      max_keys >= 2 * the largest mini-batch (the endpoint sequence has 2 E entries). ---- */
+typedef struct ammsb_orderset ammsb_orderset;
+int ammsb_orderset_create(ammsb_ctx* ctx, uint32_t max_keys, ammsb_orderset** out);
+int ammsb_orderset_destroy(ammsb_orderset* os);
+int ammsb_orderset_apply(ammsb_orderset* os, ammsb_ctx* ctx, const uint64_t* d_keys, uint32_t n, uint64_t* d_out);
+int ammsb_minibatch_finish(ammsb_orderset* os, ammsb_ctx* ctx, uint64_t* d_edges, uint32_t E, uint32_t* d_nodes,
+                           uint32_t* num_nodes);
+
 /* ---- pi/phi store: RowPartitionedMatrixFactory<Float>::CreateMatrix(rows, cols)
  *      (partitioned-alloc.h:152-157) + the phi[N] buffer (learner.cc:83).
  *      Node-partitioned over `num_shards` GPUs: shard s owns rows

@@ -726,7 +726,7 @@ struct ColsPhi2Smem {
 };
 
 template <int KPL, int G>
-__global__ void __launch_bounds__(384, 1) k_cols_phi2(const __grid_constant__ ColsPhiArgs a, float* __restrict__ nz_scratch) {
+__global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ ColsPhiArgs a, float* __restrict__ nz_scratch) {
   constexpr int LPG = 32 / G, KG = KPL * LPG, F4 = KG / 4;
   constexpr int PSTR = KG * 4 + 16;
   constexpr int FPL = (F4 + 31) / 32;  // float4 per lane in the column phases
@@ -1791,10 +1791,10 @@ static int cols_phi_launch_nb(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv);
 template <int KPL, int G>
 static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_nz, size_t nz_warps) {
   constexpr uint32_t KG = KPL * (32 / G);
-  uint32_t warps = 12;
+  uint32_t warps = 16;  // 128 registers per thread: up to 16 warps; the staged slot buffers decide (12 at K/G = 128)
   if (const char* e = getenv("AMMSB_COLS_WARPS")) warps = (uint32_t)atoi(e);
   if (warps < 1) warps = 1;
-  if (warps > 12) warps = 12;
+  if (warps > 16) warps = 16;
   size_t smem;
   for (;; --warps) {
     smem = ColsPhi2Smem::per_cta(KG) + (size_t)warps * ColsPhi2Smem::per_warp(KG);

@@ -350,11 +350,24 @@ class DeviceSampler:
     candidate stream.  Same edges and nodes as the host strategy for the same seed (in draw
     order), same seed afterwards."""
 
-    def __init__(self, ctx, N, E, m, train, heldout, d_offsets, d_adj, degree):
+    def __init__(self, ctx, N, E, m, train, heldout, d_offsets, d_adj, degree, exact_order=False):
+        """exact_order: emit edges and nodes in the reference's std::unordered_set order
+        (csrc/orderset.cu); with d_adj in the host Graph's order the mini-batch is then bit-identical
+        to the host strategy's"""
         h = C.c_void_p()
         _ck(lib().ammsb_sampler_create(ctx.h, C.c_uint64(N), m, C.byref(h)))
         self.h, self.ctx, self.N, self.E, self.m = h, ctx, N, E, m
         self.train, self.heldout, self.d_offsets, self.d_adj, self.degree = train, heldout, d_offsets, d_adj, degree
+        self.os = None
+        if exact_order:
+            o = C.c_void_p()
+            _ck(lib().ammsb_orderset_create(ctx.h, 2 * max(m, int(np.max(degree)) if len(degree) else 1) + 2, C.byref(o)))
+            self.os = o
+
+    def _finish(self, ctx, d_edges, d_nodes, E_mb):
+        nn = C.c_uint32(0)
+        _ck(lib().ammsb_minibatch_finish(self.os, ctx.h, d_edges.ptr, E_mb, d_nodes.ptr, C.byref(nn)))
+        return nn.value
 
     def sample(self, seed, d_edges, d_nodes, ctx=None):
         """one mini-batch into d_edges / d_nodes; returns (weight, E_mb, V)"""
@@ -366,18 +379,25 @@ class DeviceSampler:
                 if d > 0:
                     break
             _ck(lib().ammsb_minibatch_link(ctx.h, u, d, self.d_offsets.ptr, self.d_adj.ptr, d_edges.ptr, d_nodes.ptr))
+            if self.os is not None:
+                return float(np.float32(self.N)), d, self._finish(ctx, d_edges, d_nodes, d)
             return float(np.float32(self.N)), d, d + 1
         u = rand_r(seed) % self.N
         ne, nn = C.c_uint32(0), C.c_uint32(0)
         _ck(lib().ammsb_minibatch_nonlink(self.h, ctx.h, u, C.byref(seed), self.train.h,
                                           self.heldout.h if self.heldout is not None else None, d_edges.ptr,
                                           d_nodes.ptr, C.byref(ne), C.byref(nn)))
+        if self.os is not None:
+            nn = C.c_uint32(self._finish(ctx, d_edges, d_nodes, ne.value))
         return float(np.float32(2 * self.E) / np.float32(self.m)), ne.value, nn.value
 
     def free(self):
         if self.h is not None:
             lib().ammsb_sampler_destroy(self.h)
             self.h = None
+        if self.os is not None:
+            lib().ammsb_orderset_destroy(self.os)
+            self.os = None
 
 
 class Peer:

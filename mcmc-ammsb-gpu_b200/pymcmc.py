@@ -99,6 +99,11 @@ def set_order(keys, width):
     return a[:n], b[:n]
 
 
+def unordered_set_order(keys):
+    """iteration order of std::unordered_set<uint64_t> fed `keys` in order (the real container)"""
+    return set_order(keys, 8)[0]
+
+
 def init_theta_host(K, eta0=1.0, eta1=1.0):
     out = np.zeros(2 * K, dtype=np.float32)
     lib().mcmc_init_theta_host(K, eta0, eta1, _p(out))

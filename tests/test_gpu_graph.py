@@ -173,3 +173,79 @@ def test_device_sampler_draws_the_host_strategys_minibatches(ctx, N, E, m, built
     smp.free(); train.free(); heldout.free(); cfg.close()
     if ref is not None:
         ref.close()
+
+
+def host_order_csr(N, tr):
+    """mcmc::Graph (data.cc:12-25): for every training edge (u, v) in list order, v joins u's
+    neighbors and u joins v's -- the order sampleNodeLink walks"""
+    u, v = (tr >> np.uint64(32)).astype(np.int64), (tr & np.uint64(0xffffffff)).astype(np.int64)
+    ends = np.stack([u, v], axis=1).ravel()       # u0, v0, u1, v1, ...
+    other = np.stack([v, u], axis=1).ravel()
+    order = np.argsort(ends, kind="stable")        # per vertex, in order of appearance
+    deg = np.bincount(ends, minlength=N)
+    off = np.zeros(N + 1, np.uint64)
+    off[1:] = np.cumsum(deg)
+    return off, other[order].astype(np.uint32), deg.astype(np.uint32)
+
+
+@pytest.mark.parametrize("n", [1, 5, 13, 14, 100, 1109, 1110, 2357, 2358, 5000, 40000])
+def test_orderset_is_libstdcxx_iteration_order(ctx, n):
+    """keys in insertion order -> std::unordered_set iteration order, against the host container
+    (host/mcmc/std_order_set.h, itself tested against std::unordered_set) at sizes around the
+    growth steps of _Prime_rehash_policy and across the one-CTA / radix-sort switch"""
+    rng = np.random.default_rng(n)
+    for wide in (False, True):
+        keys = rng.choice(1 << 22, size=n, replace=False).astype(np.uint64)
+        if wide:
+            keys = (keys << np.uint64(32)) | rng.integers(0, 1 << 22, n).astype(np.uint64)
+        want = pymcmc.unordered_set_order(keys)
+        os_ = C.c_void_p()
+        A._ck(A.lib().ammsb_orderset_create(ctx.h, max(n, 4), C.byref(os_)))
+        d_in, d_out = ctx.from_host(keys), ctx.buf(np.uint64, n)
+        A._ck(A.lib().ammsb_orderset_apply(os_, ctx.h, d_in.ptr, n, d_out.ptr))
+        ctx.sync()
+        assert np.array_equal(d_out.read(), want)
+        A.lib().ammsb_orderset_destroy(os_)
+        d_in.free(); d_out.free()
+
+
+@pytest.mark.parametrize("N,E,m", [(3000, 60000, 500), (20000, 100000, 4096), (317080, 1049866, 16384)])
+def test_device_node_strategy_is_bit_identical_to_the_host_strategy(ctx, N, E, m):
+    """with the reference's emission order computed on the device (csrc/orderset.cu) and the
+    adjacency in the host Graph's order, the device Node strategy + node extraction equals
+    sampleNode (sample.cc:253-302) + ExtractNodesFromMiniBatch (learner.cc:162-173) element by
+    element, mini-batch after mini-batch, with the same rand_r state afterwards"""
+    keys = make_edges(N, E, 9)
+    cfg = pymcmc.Config(K=8, mini_batch_size=m, heldout_ratio=0.1, strategy="Node")
+    cfg.set_graph(N, keys, srand_seed=5)
+    tr, he = cfg.edges()
+    ref = RefSampler(N, keys, 0.1, 5, m) if RefSampler.available() and N <= 20000 else None
+    train = A.DevSet(ctx, *cfg.set_table(0))
+    heldout = A.DevSet(ctx, *cfg.set_table(1))
+    off, adj, deg = host_order_csr(N, tr)
+    assert deg.max() == cfg.max_fan_out()
+    d_off, d_adj = ctx.from_host(off), ctx.from_host(adj)
+    smp = A.DeviceSampler(ctx, N, E, m, train, heldout, d_off, d_adj, deg, exact_order=True)
+    cap = max(m, int(deg.max()))
+    d_edges, d_nodes = ctx.buf(np.uint64, cap), ctx.buf(np.uint32, 2 * cap + 2)
+    seed_h, seed_d, seed_r = C.c_uint(77), C.c_uint(77), C.c_uint(77)
+    kinds = set()
+    for _ in range(12):
+        w_h, e_h, n_h = cfg.sample("Node", seed_h)
+        if ref is not None:
+            w_r, e_r, n_r = ref.sample("Node", seed_r)
+            assert np.array_equal(e_r, e_h) and np.array_equal(n_r, n_h)
+        w_d, ne, nn = smp.sample(seed_d, d_edges, d_nodes)
+        ctx.sync()
+        assert (ne, nn) == (len(e_h), len(n_h))
+        assert np.array_equal(d_edges.read(ne), e_h), "edges are not in the reference's order"
+        assert np.array_equal(d_nodes.read(nn), n_h), "nodes are not in the reference's order"
+        assert np.float32(w_d) == np.float32(w_h) and seed_d.value == seed_h.value
+        kinds.add(ne == m)
+    assert kinds == {True, False}
+    for b in (d_off, d_adj, d_edges, d_nodes):
+        b.free()
+    smp.free(); train.free(); heldout.free()
+    if ref is not None:
+        ref.close()
+    cfg.close()

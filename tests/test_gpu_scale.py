@@ -1,0 +1,172 @@
+"""-m gpu parity tests at the sizes the benchmark runs at:
+
+  (a) the headline configuration itself -- com-DBLP shape, K = 1024, mini-batch 16384, n = 32:
+      iterations of mcmc::Learner::Run (at least one non-link mini-batch: 16385 slots on a
+      persistent grid, the real 9 MB cuckoo table, 1.3 GB of pi) against the reference's own
+      kernels restated (the OpenMP build of the oracle port, which tests/test_oracle.py pins bit for
+      bit to oracle/_ref) from identical state;
+  (b) a pi matrix with more than 2^32 elements (N = 4.3 M, K = 1024): update_phi / update_pi /
+      update_beta on rows whose element offset does not fit 32 bits, against the oracle on the
+      same rows gathered into a small matrix -- pins 64-bit row addressing end to end.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import pyammsb as A
+import pymcmc
+import pyoracle
+from test_gpu_learner import OracleLearner, close_enough, RTOL
+from test_gpu_parity import dev_params, dev_set
+from util import make_edges, random_theta, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def report(tag, got, want):
+    e = rel_err(got, want)
+    print("%-22s max rel %.3e  median %.1e  elements beyond %g: %d of %d" %
+          (tag, e.max(), np.median(e), RTOL, int((e > RTOL).sum()), e.size))
+
+
+def test_dblp_shape_iterations_match_reference_kernels(ctx):
+    # the OpenMP build of the oracle port: the same source that tests/test_oracle.py pins bit for bit
+    # to the reference's own kernel text (oracle/_ref), run on every host core (an iteration at this
+    # size is seconds of CPU work)
+    orc = pyoracle.Oracle(omp=True)
+    orc.L.orc_set_num_threads.argtypes = [__import__("ctypes").c_int]
+    orc.L.orc_set_num_threads(os.cpu_count() or 1)
+    N, E, K, m, n = 317080, 1049866, 1024, 16384, 32
+    cfg = pymcmc.Config(K=K, mini_batch_size=m, num_node_sample=n, heldout_ratio=0.1, strategy="Node")
+    cfg.set_graph(N, make_edges(N, E, 1))
+    lrn = pymcmc.Learner(cfg, 0)
+    ol = OracleLearner(orc, cfg, lrn, N, K, n)
+    nonlink = 0
+    for it in range(6):
+        edges, nodes, nbrs, weight = lrn.peek(n)
+        want_nbrs = ol.iterate(edges, nodes, weight)
+        assert np.array_equal(nbrs, want_nbrs), "iteration %d: neighbor ids differ" % it
+        lrn.run(1)
+        pi, phi, beta, theta = lrn.read(N, K)
+        print("iteration %d: %d edges, %d nodes" % (it, len(edges), len(nodes)))
+        report("  pi (mini-batch rows)", pi[nodes], ol.pi[nodes])
+        report("  phi", phi[nodes], ol.phi[nodes])
+        report("  theta", theta, ol.theta)
+        report("  beta", beta, ol.beta)
+        # K = 1024: pi elements are ~1e-3 and alpha = 1/K, so more elements of the Langevin update are
+        # ill-conditioned than at K = 64 (a link mini-batch has only a handful of rows to average
+        # over); the conditioning-aware bound of close_enough -- error <= 2e-6 of the row maximum,
+        # median <= 1e-6 -- is what holds everywhere, the share beyond 1e-5 is printed above
+        close_enough(pi[nodes], ol.pi[nodes], "pi it %d" % it, frac=4e-2)
+        close_enough(phi[nodes], ol.phi[nodes], "phi it %d" % it)
+        # theta' = |theta + eps/2 (eta - theta + scale g) + sqrt(eps theta) xi| with scale = N or 2E/m
+        # and g a sum over the mini-batch in another (fixed) association than the reference's serial
+        # sum_grads: relative 1e-5 on all but 2 % of the elements, every element within 1e-4
+        for name, got, want in (("theta", theta, ol.theta), ("beta", beta, ol.beta)):
+            e = rel_err(got, want)
+            assert np.median(e) < 1e-6 and float((e > RTOL).mean()) < 2e-2 and e.max() < 1e-4, (name, it, e.max())
+        untouched = np.ones(N, bool)
+        untouched[nodes] = False
+        assert np.array_equal(pi[untouched], ol.pi[untouched]), "rows outside the mini-batch changed"
+        ol.pi, ol.phi, ol.beta, ol.theta = pi, phi, beta, theta  # every iteration judged on its own
+        nonlink += len(nodes) > 1000
+        if nonlink >= 2 and it >= 2:
+            break
+    assert nonlink >= 1, "no non-link mini-batch among the iterations"
+    got, want = lrn.heldout_perplexity(), ol.perplexity()
+    print("held-out perplexity: device %.6f reference kernels %.6f" % (got, want))
+    assert abs(got - want) <= 1e-3 * want
+    lrn.close()
+    cfg.close()
+
+
+def test_rows_beyond_2_pow_32_elements(ctx, orc):
+    N, K, n, V = 4_300_000, 1024, 16, 64
+    assert N * K > 2 ** 32
+    rng = np.random.default_rng(7)
+    # mini-batch nodes and neighbors: half of them beyond row 2^32 / K, the last row included
+    hi_lo = 2 ** 32 // K
+    nodes = np.unique(np.concatenate([rng.integers(hi_lo, N, V // 2), rng.integers(0, hi_lo, V // 2 - 1), [N - 1]]))
+    nodes = rng.permutation(nodes).astype(np.uint32)
+    V = len(nodes)
+    nb = np.where(rng.random((V, n)) < 0.5, rng.integers(hi_lo, N, (V, n)), rng.integers(0, hi_lo, (V, n))).astype(np.uint32)
+    clash = nb == nodes[:, None]
+    nb[clash] = (nb[clash] + 1) % N
+    touched = np.unique(np.concatenate([nodes, nb.ravel()]))
+    T = len(touched)
+    compact = {int(v): i for i, v in enumerate(touched)}
+    cmap = np.vectorize(compact.get)
+    g = rng.gamma(1.0, 1.0, size=(T, K)).astype(np.float32)
+    phi_c = g.sum(axis=1, dtype=np.float32)
+    pi_c = np.ascontiguousarray((g / phi_c[:, None]).astype(np.float32))
+    theta = random_theta(K, 3)
+    beta = orc.theta_to_beta(theta)
+    # training links: every fourth sampled pair, under the real ids (device) and the compact ids (oracle)
+    pick = rng.random((V, n)) < 0.25
+    a_big, b_big = np.broadcast_to(nodes[:, None], nb.shape)[pick].astype(np.uint64), nb[pick].astype(np.uint64)
+    keys_big = (np.minimum(a_big, b_big) << np.uint64(32)) | np.maximum(a_big, b_big)
+    a_c, b_c = cmap(a_big).astype(np.uint64), cmap(b_big).astype(np.uint64)
+    keys_c = (np.minimum(a_c, b_c) << np.uint64(32)) | np.maximum(a_c, b_c)
+    keys_big, idx = np.unique(keys_big, return_index=True)
+    keys_c = keys_c[idx]
+    set_big, set_c = orc.set_build(keys_big), orc.set_build(keys_c)
+    p = orc.make_params(N, 10 * N, K, n)
+
+    # ---- device: the full-size store, only the touched rows written ----
+    st = A.Store(ctx, N, K)
+    for r, row in zip(touched, pi_c):
+        st.write_pi(row, row0=int(r))
+        st.write_phi(phi_c[compact[int(r)]:compact[int(r)] + 1], row0=int(r))
+    dset = dev_set(ctx, set_big)
+    d_nodes, d_nb, d_beta = ctx.from_host(nodes), ctx.from_host(nb), ctx.from_host(beta)
+    d_vec, d_sum = ctx.buf(np.float32, V * K), ctx.buf(np.float32, V)
+    pool = A.Rng(ctx, V * 32, 42, 43)
+    os.environ["AMMSB_PHI_NOSPLIT"] = "1"  # the one-warp-per-slot (production) kernel also for 64 slots
+    try:
+        ctx.update_phi(dev_params(p), A.PhiOpts(A.MODE_WG, 32, 0, 0), d_beta, st, dset, d_nodes, d_nb, V, 2, pool, d_vec, d_sum)
+    finally:
+        del os.environ["AMMSB_PHI_NOSPLIT"]
+    ctx.update_pi(K, st, d_vec, d_sum, d_nodes, V)
+    got_pi = np.stack([st.read_pi(row0=int(r), nrows=1)[0] for r in nodes])
+    got_phi = np.array([st.read_phi(row0=int(r), nrows=1)[0] for r in nodes])
+
+    # ---- oracle: the same rows in a compact matrix ----
+    opool = orc.rng_pool(V * 32, 42, 43)
+    nodes_c, nb_c = cmap(nodes).astype(np.uint32), cmap(nb).astype(np.uint32)
+    want_vec = orc.update_phi(A.MODE_WG, 32, p, beta, pi_c, phi_c, set_c, nodes_c, nb_c, 2, opool)
+    assert np.array_equal(pool.get_state(), opool)
+    e = rel_err(d_vec.read().reshape(V, K), want_vec)
+    print("update_phi on rows beyond 2^32 elements: max rel %.3e, beyond %g: %d of %d" % (e.max(), RTOL, (e > RTOL).sum(), e.size))
+    assert np.median(e) < 1e-6 and (e > RTOL).mean() < 2e-3
+    pi_o, phi_o = pi_c.copy(), phi_c.copy()
+    orc.update_pi(A.MODE_WG, 32, K, pi_o, phi_o, want_vec, nodes_c)
+    e = rel_err(got_pi, pi_o[nodes_c])
+    assert np.median(e) < 1e-6 and (e > RTOL).mean() < 2e-3
+    assert rel_err(got_phi, phi_o[nodes_c]).max() < RTOL
+    # a neighbor row that is not a mini-batch node is untouched (no write landed on a wrapped address)
+    other = [int(r) for r in touched if r not in set(nodes.tolist())][:8]
+    for r in other:
+        assert np.array_equal(st.read_pi(row0=r, nrows=1)[0], pi_c[compact[r]])
+
+    # ---- update_beta with both endpoints beyond 2^32 elements ----
+    m = 96
+    eu, ev = rng.choice(touched[touched >= hi_lo], m), rng.choice(touched, m)
+    ev[ev == eu] = touched[0]
+    edges_big = (np.minimum(eu, ev).astype(np.uint64) << np.uint64(32)) | np.maximum(eu, ev).astype(np.uint64)
+    cu, cv = cmap(eu).astype(np.uint64), cmap(ev).astype(np.uint64)
+    edges_c = (np.minimum(cu, cv) << np.uint64(32)) | np.maximum(cu, cv)
+    pi_now = np.stack([st.read_pi(row0=int(r), nrows=1)[0] for r in touched])
+    theta_o, beta_o = theta.copy(), beta.copy()
+    orc.update_beta(A.MODE_WG, 32, p, theta_o, beta_o, pi_now, set_c, edges_c, 7.5, 3, orc.rng_pool(K, 44, 45))
+    d_theta, d_beta2, d_edges = ctx.from_host(theta), ctx.from_host(beta), ctx.from_host(edges_big)
+    d_ts, d_g = ctx.buf(np.float32, K), ctx.buf(np.float32, 2 * K)
+    ws = ctx.buf(np.uint8, ctx.beta_workspace_bytes(K))
+    bpool = A.Rng(ctx, K, 44, 45)
+    ctx.update_beta(dev_params(p), d_theta, d_beta2, st, dset, d_edges, m, 7.5, 3, bpool, d_ts, d_g, ws)
+    et = rel_err(d_theta.read(), theta_o)
+    print("update_beta on rows beyond 2^32 elements: theta max rel %.3e" % et.max())
+    assert np.median(et) < 1e-6 and (et > RTOL).mean() < 5e-3
+    for b in (d_nodes, d_nb, d_beta, d_vec, d_sum, d_theta, d_beta2, d_edges, d_ts, d_g, ws):
+        b.free()
+    pool.free(); bpool.free(); dset.free(); st.free()
