@@ -214,8 +214,9 @@ struct ColsPhiArgs {
   uint32_t nv, ctas_per_rank;
   uint32_t V, n, units;
   uint32_t R, D, MB;  // ring depth, A -> B distance (trips), metadata buffers
-  uint32_t parity, disable_noise, loopback;
+  uint32_t parity, disable_noise, loopback, split;
   uint32_t nb_poll, nb_third;  // the neighbor lists are the mailbox region NB (third step % 3): words arrive from the rank that sampled them
+  uint32_t fake_lat;  // loopback only: cycles a warp waits after its sends, as if the peers' partials took that long (AMMSB_COLS_FAKE_LAT, ns)
   uint32_t debug;  // timing ablations (AMMSB_COLS_DEBUG): 1 no cuckoo, 2 no phase A math, 4 no phase B math, 8 no loads, 16 no Langevin step
   float eps_t, alpha, epsilon, Nn;
 };
@@ -772,9 +773,14 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
   const uint32_t passes = (a.V + a.units - 1) / a.units;
   const uint32_t gwarp = cta * warps + wib, total_warps = a.ctas_per_rank * warps;
   float* const my_nz = nz_scratch + ((size_t)vr * total_warps + gwarp) * 2 * G * KG;  // [2][G][KG]
+  // a.split (few slots: the link mini-batches): the G slots of a group go to G different warps --
+  // warp w takes sub-slot w % G of group w / G -- instead of one warp taking them one after the other
+  const uint32_t g_first = a.split ? gwarp / G : gwarp, g_stride = a.split ? total_warps / G : total_warps;
+  const uint32_t sub_lo = a.split ? gwarp % G : 0, sub_hi = a.split ? sub_lo + 1 : G;
 
   // noise lanes: lane = (slot s_n of the group, reference lane li_n)
   const uint32_t s_n = lane / LPG, li_n = lane % LPG, l_ref = rank + G * li_n;
+  const bool nz_mine = !a.split || s_n == sub_lo;  // this lane's slot of the group is this warp's
 
   // The Langevin noise (phi.cc:266-274) of a group-pass is drawn one group-pass AHEAD of its use, a
   // float4 of every lane's stream at a time, inside the waits for the peers' partial sums: the
@@ -788,21 +794,21 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
     do {
       if (++pass == passes) {
         pass = 0;
-        group += total_warps;
+        group += g_stride;
       }
     } while (group < ngroups && !gp_live(group, pass));
   };
-  uint32_t nz_group = gwarp, nz_pass = 0, nz_piece = 0, nz_half = 0;
+  uint32_t nz_group = g_first, nz_pass = 0, nz_piece = 0, nz_half = 0;
   Rng st;
   st.x = st.y = 0;
   const bool noisy = !a.disable_noise && !(a.debug & 16);
-  if (noisy && nz_group < ngroups && nz_group * G + s_n < active_units)
+  if (noisy && nz_mine && nz_group < ngroups && nz_group * G + s_n < active_units)
     st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
   // one float4 (4 consecutive draws of every lane's stream) of the cursor's group-pass
   auto noise_piece = [&]() {
     if (!noisy || nz_group >= ngroups || nz_piece >= (uint32_t)PIECES) return;
     const uint32_t unit = nz_group * G + s_n, slot = unit + nz_pass * a.units;
-    if (unit < active_units && slot < a.V) {
+    if (nz_mine && unit < active_units && slot < a.V) {
       float4 z;
       z.x = rng_randn_t(st, zig);
       z.y = rng_randn_t(st, zig);
@@ -820,24 +826,24 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
     nz_piece = 0;
     nz_half ^= 1;
     if (noisy && nz_group != old) {  // the old group's streams are finished: persist, load the new ones
-      if (old * G + s_n < active_units) rng_store(my_pool, (uint64_t)(old * G + s_n) * 32 + l_ref, st);
-      if (nz_group < ngroups && nz_group * G + s_n < active_units)
+      if (nz_mine && old * G + s_n < active_units) rng_store(my_pool, (uint64_t)(old * G + s_n) * 32 + l_ref, st);
+      if (nz_mine && nz_group < ngroups && nz_group * G + s_n < active_units)
         st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
     }
   };
   // prologue: the whole noise of the warp's first group-pass
-  if (gwarp < ngroups) {
+  if (g_first < ngroups) {
     for (int k = 0; k < PIECES; ++k) noise_piece();
     __syncwarp();
     noise_advance();
   }
 
-  uint32_t group = gwarp, pass = 0;
+  uint32_t group = g_first, pass = 0;
   for (; group < ngroups; next_gp(group, pass)) {
     {
       const uint32_t use_half = nz_half ^ 1;  // the half the cursor filled before it moved on
       {
-      for (uint32_t s = 0; s < (uint32_t)G; ++s) {
+      for (uint32_t s = sub_lo; s < sub_hi; ++s) {
         const uint32_t unit = group * G + s, slot = unit + pass * a.units;
         if (unit >= active_units || slot >= a.V) break;  // warp-uniform; later sub-slots are dead too
         const uint32_t node = __ldg(&a.nodes[slot]);
@@ -946,7 +952,11 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
               if ((uint32_t)p != rank)
                 st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + sidx, bits);
           }
+          const long long t_sent = a.fake_lat ? clock64() : 0;
           if (c0 == 0) noise_piece();  // while the partials cross the switch: part of the next group-pass's noise
+          if (a.fake_lat) {
+            while (clock64() - t_sent < (long long)a.fake_lat) {}
+          }
           if (lane < cnt && !a.loopback) {
             uint32_t w[G];
 #pragma unroll
@@ -1061,6 +1071,390 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
 }
 
 
+// ----------------------------------------------------------------------------------------------
+// k_cols_phi3 -- k_cols_phi2's slot-at-a-time mapping with the exchange and the loads taken off a
+// warp's critical path (pieces of <= 512 bytes, n <= 32).
+//
+// What bounds k_cols_phi2 on real NVLink is how long a slot occupies its staging buffer: the SM
+// holds 12-13 slot buffers, and a buffer is busy from the first copy until phase B has read it --
+// load (~3 us) + phase A + the partial sums' round trip (~4 us on 8 GPUs) + phase B.  Here the rows
+// of a slot move from shared memory into REGISTERS (lane = columns: one float4 per neighbor, 32
+// neighbors = 128 registers) as soon as phase A has run: the buffer is free for the next slot's
+// copies at once, and the slot's phase B runs one slot LATER, from registers, when its peers'
+// partials have long arrived.  Per iteration a warp
+//     1. collects the partials of slot s-1 (sent an iteration ago) and runs its phase B (registers)
+//     2. waits for the copies of slot s (issued an iteration ago), runs phase A, sends the partials
+//     3. moves the rows of slot s to registers and issues the copies of slot s+1
+//     4. does the Langevin step of slot s-1, one piece of noise, the cuckoo lookups of slot s+1
+// so that neither a copy nor a round trip is ever waited for with nothing else to do.  The
+// arithmetic is k_cols_phi2's expression for expression (bit-identical results).
+struct ColsPhi3Smem {
+  __host__ __device__ static size_t pstr(uint32_t KG) { return (size_t)KG * 4 + 16; }
+  __host__ __device__ static size_t per_warp(uint32_t KG) { return (33 * pstr(KG) + (size_t)KG * 4 + 128 + 127) / 128 * 128; }
+  __host__ __device__ static size_t per_cta(uint32_t KG) { return 1536 + (((size_t)KG * 4 + 127) / 128 * 128); }
+};
+
+// Registers are allocated to a CTA in units of four warps: 9-12 warps leave 168 registers per thread
+// (the 128 row registers then push ~50 values into local memory, which misses the small L1 left
+// beside 219 KB of shared memory: measured 2x slower), 8 warps get 255 and nothing spills.
+#ifndef COLS_PHI3_WARPS
+#define COLS_PHI3_WARPS 8
+#endif
+template <int KPL, int G>
+__global__ void __launch_bounds__(COLS_PHI3_WARPS * 32, 1) k_cols_phi3(const __grid_constant__ ColsPhiArgs a, float* __restrict__ nz_scratch) {
+  constexpr int LPG = 32 / G, KG = KPL * LPG, F4 = KG / 4;
+  static_assert(F4 <= 32, "one float4 of a piece per lane");
+  constexpr int PSTR = KG * 4 + 16;
+  constexpr int PPI = 32 / F4;  // pieces per copy instruction
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
+  const uint32_t rank = a.r[vr].rank;
+  const uint32_t n = a.n;
+  float* const my_pi = a.r[vr].pi;
+  const float* const my_phi = a.r[vr].phi;
+  float* const my_vec = a.r[vr].phi_vec;
+  ulonglong2* const my_pool = a.r[vr].pool;
+
+  uint32_t* s_zig = reinterpret_cast<uint32_t*>(s_raw);
+  const ZigShared zig{s_zig};
+  zig_stage(s_zig);
+  float* s_fb = reinterpret_cast<float*>(s_raw + 1536);  // beta_k - epsilon, local column order
+  unsigned char* mybox = a.r[vr].box[rank];
+  uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
+  {
+    const float* beta = reinterpret_cast<const float*>(mybox + a.lay.beta);
+    for (uint32_t c = threadIdx.x; c < KG; c += blockDim.x) {
+      const uint32_t f = c >> 2, e = c & 3, q = f / LPG, li = f % LPG;
+      const uint32_t k = (rank + G * li) + 32 * (4 * q + e);
+      s_fb[c] = beta[2 * k + 1] - a.epsilon;  // phi.cc:237-239
+    }
+  }
+  __syncthreads();
+  unsigned char* wbase = s_raw + ColsPhi3Smem::per_cta(KG) + (size_t)wib * ColsPhi3Smem::per_warp(KG);
+  unsigned char* s_rows = wbase;                                        // [32] neighbor pieces
+  unsigned char* s_own = wbase + 32 * PSTR;                             // own piece
+  float* s_new = reinterpret_cast<float*>(wbase + 33 * PSTR);           // the new phi piece (row-sum scratch)
+  float* s_inv = reinterpret_cast<float*>(wbase + 33 * PSTR + KG * 4);  // [32] 1 / (probs_sum * phi_sum)
+  const uint32_t rows_u32 = smem_u32(s_rows);
+
+  const size_t half_S = (size_t)a.parity * G * a.lay.S_src, half_R = (size_t)a.parity * G * a.lay.R_src;
+  const float e_link = a.epsilon, e_non = 1.0f - a.epsilon;
+  const float half_eps = a.eps_t / 2;
+
+  const uint32_t active_units = a.units < a.V ? a.units : a.V;
+  const uint32_t ngroups = (active_units + G - 1) / G;
+  const uint32_t passes = (a.V + a.units - 1) / a.units;
+  const uint32_t gwarp = cta * warps + wib, total_warps = a.ctas_per_rank * warps;
+  if (gwarp >= ngroups) return;  // no CTA-wide barrier below
+  float* const my_nz = nz_scratch + ((size_t)vr * total_warps + gwarp) * 2 * G * KG;  // [2][G][KG]
+
+  // ---- the Langevin noise: one group-pass ahead of its use, a float4 per lane at a time (k_cols_phi2) ----
+  const uint32_t s_n = lane / LPG, li_n = lane % LPG, l_ref = rank + G * li_n;
+  constexpr int PIECES = KPL / 4;
+  auto gp_live = [&](uint32_t group, uint32_t pass) -> bool {
+    return group < ngroups && (size_t)group * G + (size_t)pass * a.units < a.V;
+  };
+  auto next_gp = [&](uint32_t& group, uint32_t& pass) {
+    do {
+      if (++pass == passes) {
+        pass = 0;
+        group += total_warps;
+      }
+    } while (group < ngroups && !gp_live(group, pass));
+  };
+  uint32_t nz_group = gwarp, nz_pass = 0, nz_piece = 0, nz_half = 0;
+  Rng st;
+  st.x = st.y = 0;
+  const bool noisy = !a.disable_noise;
+  if (noisy && nz_group * G + s_n < active_units) st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
+  auto noise_piece = [&]() {
+    if (!noisy || nz_group >= ngroups || nz_piece >= (uint32_t)PIECES) return;
+    const uint32_t unit = nz_group * G + s_n, slot = unit + nz_pass * a.units;
+    if (unit < active_units && slot < a.V) {
+      float4 z;
+      z.x = rng_randn_t(st, zig);
+      z.y = rng_randn_t(st, zig);
+      z.z = rng_randn_t(st, zig);
+      z.w = rng_randn_t(st, zig);
+      reinterpret_cast<float4*>(my_nz + ((size_t)nz_half * G + s_n) * KG)[nz_piece * LPG + li_n] = z;
+    }
+    ++nz_piece;
+  };
+  auto noise_advance = [&]() {
+    if (nz_group >= ngroups) return;
+    const uint32_t old = nz_group;
+    next_gp(nz_group, nz_pass);
+    nz_piece = 0;
+    nz_half ^= 1;
+    if (noisy && nz_group != old) {
+      if (old * G + s_n < active_units) rng_store(my_pool, (uint64_t)(old * G + s_n) * 32 + l_ref, st);
+      if (nz_group < ngroups && nz_group * G + s_n < active_units)
+        st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
+    }
+  };
+  for (int k = 0; k < PIECES; ++k) noise_piece();  // the whole noise of the first group-pass
+  __syncwarp();
+  noise_advance();
+
+  // ---- the warp's slots in order: (group, pass), live sub-slots 0 .. ----
+  struct Slot {  // warp-uniform
+    uint32_t slot, node, half, last, valid;
+    float phi_sum;
+    size_t ridx;
+  };
+  uint32_t it_group = gwarp, it_pass = 0, it_sub = 0, it_half = 0;
+  auto sub_live = [&](uint32_t group, uint32_t pass, uint32_t sub) -> bool {
+    const uint32_t unit = group * G + sub;
+    return sub < (uint32_t)G && unit < active_units && (size_t)unit + (size_t)pass * a.units < a.V;
+  };
+  // the slot under the iterator (meta loads issued here), then the iterator moves on
+  auto take = [&](Slot& s, uint32_t& nb) {
+    s.valid = it_group < ngroups;
+    nb = 0;
+    if (!s.valid) return;
+    s.slot = it_group * G + it_sub + it_pass * a.units;
+    s.ridx = ((size_t)it_group * passes + it_pass) * G + it_sub;
+    s.half = it_half;
+    s.node = __ldg(&a.nodes[s.slot]);
+    s.phi_sum = my_phi[s.node];
+    nb = s.node;  // lanes >= n; a polled word is only PEEKED here and resolved by nb_resolve()
+    if (lane < n) {
+      if (a.nb_poll) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(mybox + a.lay.NB + (size_t)a.nb_third * a.lay.NB_third) + (size_t)s.slot * n + lane;
+        nb = peek_mbox(w);
+      } else {
+        nb = __ldg(&a.neighbors[(size_t)s.slot * n + lane]);
+      }
+    }
+    s.last = !sub_live(it_group, it_pass, it_sub + 1);
+    if (s.last) {
+      it_sub = 0;
+      it_half ^= 1;
+      next_gp(it_group, it_pass);
+    } else {
+      ++it_sub;
+    }
+  };
+  // a neighbor id that came through the mailbox: wait for it if the peek was too early, re-arm the word
+  auto nb_resolve = [&](const Slot& s, uint32_t& nb) {
+    if (a.nb_poll && s.valid && lane < n) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(mybox + a.lay.NB + (size_t)a.nb_third * a.lay.NB_third) + (size_t)s.slot * n + lane;
+      nb = __float_as_uint(finish_poll(w, nb, err));
+    }
+  };
+  auto issue_copies = [&](const Slot& s, uint32_t nb) {
+    if (F4 == 32) {
+#pragma unroll 8
+      for (uint32_t r = 0; r < 32; ++r) {
+        const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
+        if (r < n) cp_async16_u32(rows_u32 + r * PSTR + lane * 16, my_pi + (size_t)id * KG + lane * 4);
+      }
+      cp_async16_u32(rows_u32 + 32 * PSTR + lane * 16, my_pi + (size_t)s.node * KG + lane * 4);
+    } else {
+      const uint32_t sub = lane / F4, w = lane % F4;
+#pragma unroll 8
+      for (uint32_t r0 = 0; r0 < 32; r0 += PPI) {
+        const uint32_t r = r0 + sub;
+        const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
+        if (r < n) cp_async16_u32(rows_u32 + r * PSTR + w * 16, my_pi + (size_t)id * KG + w * 4);
+      }
+      if (lane < F4) cp_async16_u32(rows_u32 + 32 * PSTR + lane * 16, my_pi + (size_t)s.node * KG + lane * 4);
+    }
+    cp_async_commit();
+  };
+
+  Slot cur, nxt, prev;
+  prev.valid = 0;
+  uint32_t nb_cur, nb_nxt;
+  take(cur, nb_cur);
+  nb_resolve(cur, nb_cur);
+  issue_copies(cur, nb_cur);
+  bool y_cur = false;
+  if (lane < n) y_cur = set_has(a.set, make_edge(min(cur.node, nb_cur), max(cur.node, nb_cur)));
+
+  float4 xr[32];        // rows of the slot whose exchange is in flight, lane = float4 of the piece
+  float4 o_prev = make_float4(0.f, 0.f, 0.f, 0.f);  // its own piece
+  float S_prev = 0.f;   // its partial sum (lane = neighbor)
+  uint32_t ymask_prev = 0;
+  long long t_sent = 0;
+  const bool col_lane = lane < (uint32_t)F4;
+
+  while (cur.valid || prev.valid) {
+    take(nxt, nb_nxt);  // meta loads of the slot after `cur`: consumed in step 3
+    // ---- 1. slot prev: collect the peers' partials, phase B from registers ----
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (prev.valid) {
+      const size_t sidx = prev.ridx * n + lane;
+      float P[G];
+#pragma unroll
+      for (int p = 0; p < G; ++p) P[p] = S_prev;
+      if (a.fake_lat) {
+        while (clock64() - t_sent < (long long)a.fake_lat) {}
+      }
+      if (lane < n && !a.loopback) {
+        uint32_t w[G];
+#pragma unroll
+        for (int p = 0; p < G; ++p)
+          if ((uint32_t)p != rank)
+            w[p] = peek_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p * a.lay.S_src) + sidx);
+#pragma unroll
+        for (int p = 0; p < G; ++p)
+          if ((uint32_t)p != rank)
+            P[p] = finish_poll(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p * a.lay.S_src) + sidx, w[p], err);
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {  // strides G/2 .. 1 of WG_SUM
+#pragma unroll
+        for (int p = 0; p < o; ++p) P[p] += P[p + o];
+      }
+      s_inv[lane] = 1.0f / (P[0] * prev.phi_sum);
+      __syncwarp();
+      const float nrphi = -(1.0f / prev.phi_sum);
+      const float4 fb = col_lane ? reinterpret_cast<const float4*>(s_fb)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ymask_prev == 0) {  // no training link among the slot's pairs (the usual case)
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          if ((uint32_t)b < n) {
+            const float inv = s_inv[b];
+            g4.x += fmaf(fmaf(-xr[b].x, fb.x, e_non), inv, nrphi);
+            g4.y += fmaf(fmaf(-xr[b].y, fb.y, e_non), inv, nrphi);
+            g4.z += fmaf(fmaf(-xr[b].z, fb.z, e_non), inv, nrphi);
+            g4.w += fmaf(fmaf(-xr[b].w, fb.w, e_non), inv, nrphi);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          if ((uint32_t)b < n) {
+            const float inv = s_inv[b];
+            const bool yb = (ymask_prev >> b) & 1;
+            const float e = yb ? e_link : e_non, sg = yb ? 1.0f : -1.0f;
+            g4.x += fmaf(fmaf(xr[b].x * sg, fb.x, e), inv, nrphi);
+            g4.y += fmaf(fmaf(xr[b].y * sg, fb.y, e), inv, nrphi);
+            g4.z += fmaf(fmaf(xr[b].z * sg, fb.z, e), inv, nrphi);
+            g4.w += fmaf(fmaf(xr[b].w * sg, fb.w, e), inv, nrphi);
+          }
+        }
+      }
+      __syncwarp();  // s_inv is rewritten by the next slot
+    }
+    // ---- 2. slot cur: phase A from shared memory (lane = neighbor), partials to every peer ----
+    float S = 0.f;
+    uint32_t ymask = 0;
+    float4 o_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cur.valid) {
+      ymask = __ballot_sync(FULL_MASK, y_cur);
+      cp_async_wait_pending(0);
+      __syncwarp();
+      {
+        float ch[LPG];
+#pragma unroll
+        for (int t = 0; t < LPG; ++t) ch[t] = 0.f;
+        const float4* own4 = reinterpret_cast<const float4*>(s_own);
+        const float4* fb4 = reinterpret_cast<const float4*>(s_fb);
+        const float4* row4 = reinterpret_cast<const float4*>(s_rows + (size_t)(lane < n ? lane : 0) * PSTR);
+        if (ymask == 0) {
+#pragma unroll
+          for (int f = 0; f < F4; ++f) {
+            const float4 o = own4[f], fb = fb4[f], r = row4[f];
+            float& acc = ch[f % LPG];
+            acc = fmaf(o.x, fmaf(-r.x, fb.x, e_non), acc);  // fma(r, -f, e) == fma(-r, f, e) bit for bit
+            acc = fmaf(o.y, fmaf(-r.y, fb.y, e_non), acc);
+            acc = fmaf(o.z, fmaf(-r.z, fb.z, e_non), acc);
+            acc = fmaf(o.w, fmaf(-r.w, fb.w, e_non), acc);
+          }
+        } else {
+          const float e = y_cur ? e_link : e_non;
+          const float sg = y_cur ? 1.0f : -1.0f;
+#pragma unroll
+          for (int f = 0; f < F4; ++f) {
+            const float4 o = own4[f], fb = fb4[f], r = row4[f];
+            float& acc = ch[f % LPG];
+            acc = fmaf(o.x, fmaf(r.x * sg, fb.x, e), acc);
+            acc = fmaf(o.y, fmaf(r.y * sg, fb.y, e), acc);
+            acc = fmaf(o.z, fmaf(r.z * sg, fb.z, e), acc);
+            acc = fmaf(o.w, fmaf(r.w * sg, fb.w, e), acc);
+          }
+        }
+#pragma unroll
+        for (int o = LPG / 2; o > 0; o >>= 1) {
+#pragma unroll
+          for (int t = 0; t < o; ++t) ch[t] += ch[t + o];
+        }
+        S = ch[0];
+      }
+      if (lane < n && !a.loopback) {
+        const size_t sidx = cur.ridx * n + lane;
+        const uint32_t bits = partial_bits(S);
+#pragma unroll
+        for (int p = 0; p < G; ++p)
+          if ((uint32_t)p != rank)
+            st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + sidx, bits);
+      }
+      if (a.fake_lat) t_sent = clock64();
+      // ---- 3. rows of cur -> registers, the buffer is free: copies of the next slot ----
+      if (col_lane) {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) xr[b] = reinterpret_cast<const float4*>(s_rows + (size_t)b * PSTR)[lane];
+        o_cur = reinterpret_cast<const float4*>(s_own)[lane];
+      }
+      __syncwarp();
+    }
+    nb_resolve(nxt, nb_nxt);
+    if (nxt.valid) issue_copies(nxt, nb_nxt);
+    // ---- 4. slot prev: Langevin step (phi.cc:266-274), partial row sum to every rank ----
+    if (prev.valid) {
+      const float* nzrow = my_nz + ((size_t)prev.half * G + (prev.ridx % G)) * KG;
+      if (col_lane) {
+        float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (!a.disable_noise) z = __ldcg(reinterpret_cast<const float4*>(nzrow) + lane);
+        float4 v;
+        v.x = phi_langevin(o_prev.x, prev.phi_sum, g4.x, z.x, half_eps, a.eps_t, a.alpha, a.Nn);
+        v.y = phi_langevin(o_prev.y, prev.phi_sum, g4.y, z.y, half_eps, a.eps_t, a.alpha, a.Nn);
+        v.z = phi_langevin(o_prev.z, prev.phi_sum, g4.z, z.z, half_eps, a.eps_t, a.alpha, a.Nn);
+        v.w = phi_langevin(o_prev.w, prev.phi_sum, g4.w, z.w, half_eps, a.eps_t, a.alpha, a.Nn);
+        reinterpret_cast<float4*>(my_vec + (size_t)prev.slot * KG)[lane] = v;
+        reinterpret_cast<float4*>(s_new)[lane] = v;
+      }
+      __syncwarp();
+      float ls = 0.f;
+      if (lane < LPG) {
+#pragma unroll 8
+        for (int i = 0; i < KPL; ++i) ls += s_new[((i >> 2) * LPG + lane) * 4 + (i & 3)];
+      }
+#pragma unroll
+      for (int o = LPG / 2; o > 0; o >>= 1) ls += __shfl_xor_sync(FULL_MASK, ls, o);
+      ls = __shfl_sync(FULL_MASK, ls, 0);
+      if (lane < (uint32_t)G) {  // this rank's partial to every rank (its own mailbox included)
+        const uint32_t p = lane;
+        st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[a.loopback ? rank : p] + a.lay.R + half_R +
+                                            (size_t)(a.loopback ? p : rank) * a.lay.R_src) + prev.ridx,
+                partial_bits(ls));
+      }
+      __syncwarp();  // s_new is free
+    }
+    // one piece of the noise the cursor is filling; when prev closed its group-pass, the rest of it
+    noise_piece();
+    if (prev.valid && prev.last) {
+      while (noisy && nz_group < ngroups && nz_piece < (uint32_t)PIECES) noise_piece();
+      __syncwarp();
+      noise_advance();
+    }
+    // the cuckoo answers of the next slot (phi.cc:230-234)
+    bool y_nxt = false;
+    if (nxt.valid && lane < n) y_nxt = set_has(a.set, make_edge(min(nxt.node, nb_nxt), max(nxt.node, nb_nxt)));
+    // ---- rotate ----
+    prev = cur;
+    o_prev = o_cur;
+    S_prev = S;
+    ymask_prev = ymask;
+    cur = nxt;
+    nb_cur = nb_nxt;
+    y_cur = y_nxt;
+  }
+}
+
 // ---- update_pi on the column shards (phi.cc:154-197): pi[node][own columns] = phi_vec / sum ----
 struct ColsPiArgs {
   ColsRankView r[AMMSB_MAX_SHARDS];
@@ -1116,6 +1510,34 @@ struct ColsBetaArgs {
   float epsilon;
 };
 
+// two mailbox words at once (a partial pair is 8-byte aligned); every word still validates itself
+__device__ __forceinline__ uint2 ld_mbox2(const uint32_t* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_mbox2(uint32_t* p, uint32_t x, uint32_t y) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 finish_poll2(uint32_t* p, uint2 v, uint32_t* err) {
+  uint32_t spins = 0;
+  while (v.x == COLS_SENTINEL || v.y == COLS_SENTINEL) {
+    if (++spins > COLS_SPIN_LIMIT) {
+      atomicExch(err, 1u);
+      break;
+    }
+    v = ld_mbox2(p);
+  }
+  st_mbox2(p, COLS_SENTINEL, COLS_SENTINEL);
+  return v;
+}
+
+// The exchange is taken off the critical path: a trip's partial pair is SENT when its rows are
+// first read, and the trip is FINISHED (peers' pairs collected, tree, accumulation) BETA_D trips
+// later, from the same rows read again -- they are in L2 -- so a warp never sits through an NVLink
+// round trip, and the ranks need not run in lockstep trip by trip.  (Measured on 8 GPUs with the
+// finish right behind the send: 0.37 ms for 131072 edges against 0.06 ms without the waits.)
+#define BETA_D 3
 template <int KPL, int G>
 __global__ void __launch_bounds__(128) k_cols_beta(const __grid_constant__ ColsBetaArgs a) {
   constexpr int LPG = 32 / G, KG = KPL * LPG, Q = KPL / 4, WARPS = 4;
@@ -1137,12 +1559,14 @@ __global__ void __launch_bounds__(128) k_cols_beta(const __grid_constant__ ColsB
     accA[i] = accB[i] = 0.f;
   }
   const uint32_t trips = (a.E_mb + G - 1) / G;
-  for (uint32_t tr = cta * WARPS + wib; tr < trips; tr += a.ctas_per_rank * WARPS) {
-    const uint32_t e = tr * G + sub;
-    const bool live = e < a.E_mb;
-    float q[KPL];
-    bool y = false;
-    float pi_sum = 0.f, probs_sum = 0.f;
+  const uint32_t first = cta * WARPS + wib, stride = a.ctas_per_rank * WARPS;
+  const uint32_t my_trips = first < trips ? (trips - first + stride - 1) / stride : 0;
+  uint32_t ybits = 0;  // y of the trips in flight, bit = trip number mod 32
+
+  // rows of edge e -> q[i] = probs_k of the own columns, the two partial sums (sub-group reduced)
+  auto partials = [&](uint32_t e, bool live, bool have_y, bool& y, float* q, float& pi_sum, float& probs_sum) {
+    pi_sum = 0.f;
+    probs_sum = 0.f;
     if (live) {
       const uint64_t edge = __ldg(&a.edges[e]);
       const uint32_t u = (uint32_t)(edge >> 32), v = (uint32_t)(edge & 0xffffffffu);
@@ -1154,7 +1578,7 @@ __global__ void __launch_bounds__(128) k_cols_beta(const __grid_constant__ ColsB
         const float4 z = ldg_stream4(reinterpret_cast<const float*>(pb + qq * LPG + li));
         q[4 * qq] = x.x * z.x; q[4 * qq + 1] = x.y * z.y; q[4 * qq + 2] = x.z * z.z; q[4 * qq + 3] = x.w * z.w;
       }
-      y = set_has(a.set, make_edge(min(u, v), max(u, v)));
+      if (!have_y) y = set_has(a.set, make_edge(min(u, v), max(u, v)));
 #pragma unroll
       for (int i = 0; i < KPL; ++i) {
         pi_sum += q[i];
@@ -1170,45 +1594,72 @@ __global__ void __launch_bounds__(128) k_cols_beta(const __grid_constant__ ColsB
       pi_sum += __shfl_xor_sync(FULL_MASK, pi_sum, o);
       probs_sum += __shfl_xor_sync(FULL_MASK, probs_sum, o);
     }
-    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-    if (live) {
-      const size_t idx = (size_t)e * 2;
-      if (!a.loopback) {
+  };
+
+  for (uint32_t it = 0; it < my_trips + BETA_D; ++it) {
+    if (it < my_trips) {  // ---- send: partial pair of trip `it` to every peer ----
+      const uint32_t e = (first + it * stride) * G + sub;
+      const bool live = e < a.E_mb;
+      float q[KPL];
+      bool y = false;
+      float pi_sum, probs_sum;
+      partials(e, live, false, y, q, pi_sum, probs_sum);
+      ybits = (ybits & ~(1u << (it & 31))) | ((uint32_t)y << (it & 31));
+      if (live && !a.loopback) {
         const uint32_t pb_ = partial_bits(pi_sum), qb_ = partial_bits(probs_sum);
         for (uint32_t p = li; p < G; p += LPG)
-          if (p != rank) {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(me.box[p] + a.lay.B + half_B + (size_t)rank * a.lay.B_src) + idx;
-            st_mbox(dst, pb_);
-            st_mbox(dst + 1, qb_);
-          }
-      }
-      if (li < G) {
-        if (li == rank || a.loopback) {
-          a0 = pi_sum; b0 = probs_sum;
-        } else {
-          uint32_t* src = reinterpret_cast<uint32_t*>(mybox + a.lay.B + half_B + (size_t)li * a.lay.B_src) + idx;
-          a0 = poll_mbox(src, err); b0 = poll_mbox(src + 1, err);
-        }
-      }
-      if (G > LPG) {
-        const uint32_t p1 = li + LPG;
-        if (p1 == rank || a.loopback) {
-          a1 = pi_sum; b1 = probs_sum;
-        } else {
-          uint32_t* src = reinterpret_cast<uint32_t*>(mybox + a.lay.B + half_B + (size_t)p1 * a.lay.B_src) + idx;
-          a1 = poll_mbox(src, err); b1 = poll_mbox(src + 1, err);
-        }
+          if (p != rank)
+            st_mbox2(reinterpret_cast<uint32_t*>(me.box[p] + a.lay.B + half_B + (size_t)rank * a.lay.B_src) + (size_t)e * 2,
+                     pb_, qb_);
       }
     }
-    pi_sum = cols_rank_tree<G>(a0, a1, lane);
-    probs_sum = cols_rank_tree<G>(b0, b1, lane);
-    // prob_0 = (y ? EPSILON : 1 - EPSILON) * (1 - pi_sum)   (beta.cc:124-125)
-    probs_sum += (y ? a.epsilon : 1.0f - a.epsilon) * (1.0f - pi_sum);
-    const float rS = live ? 1.0f / probs_sum : 0.f;
+    if (it >= BETA_D) {  // ---- finish trip it - BETA_D ----
+      const uint32_t jt = it - BETA_D;
+      const uint32_t e = (first + jt * stride) * G + sub;
+      const bool live = e < a.E_mb;
+      const size_t idx = (size_t)e * 2;
+      // the peers' pairs first (they have had BETA_D trips to arrive), then the rows again
+      const uint32_t p0 = li, p1 = li + LPG;
+      const bool poll0 = live && !a.loopback && p0 < (uint32_t)G && p0 != rank;
+      const bool poll1 = live && !a.loopback && G > LPG && p1 != rank;
+      uint32_t* src0 = reinterpret_cast<uint32_t*>(mybox + a.lay.B + half_B + (size_t)p0 * a.lay.B_src) + idx;
+      uint32_t* src1 = reinterpret_cast<uint32_t*>(mybox + a.lay.B + half_B + (size_t)(G > LPG ? p1 : 0) * a.lay.B_src) + idx;
+      uint2 w0 = make_uint2(0u, 0u), w1 = make_uint2(0u, 0u);
+      if (poll0) w0 = ld_mbox2(src0);
+      if (poll1) w1 = ld_mbox2(src1);
+      float q[KPL];
+      bool y = (ybits >> (jt & 31)) & 1u;
+      float pi_sum, probs_sum;
+      partials(e, live, true, y, q, pi_sum, probs_sum);
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+      if (live) {
+        if (li < (uint32_t)G) {
+          if (poll0) {
+            w0 = finish_poll2(src0, w0, err);
+            a0 = __uint_as_float(w0.x); b0 = __uint_as_float(w0.y);
+          } else {
+            a0 = pi_sum; b0 = probs_sum;
+          }
+        }
+        if (G > LPG) {
+          if (poll1) {
+            w1 = finish_poll2(src1, w1, err);
+            a1 = __uint_as_float(w1.x); b1 = __uint_as_float(w1.y);
+          } else {
+            a1 = pi_sum; b1 = probs_sum;
+          }
+        }
+      }
+      pi_sum = cols_rank_tree<G>(a0, a1, lane);
+      probs_sum = cols_rank_tree<G>(b0, b1, lane);
+      // prob_0 = (y ? EPSILON : 1 - EPSILON) * (1 - pi_sum)   (beta.cc:124-125)
+      probs_sum += (y ? a.epsilon : 1.0f - a.epsilon) * (1.0f - pi_sum);
+      const float rS = live ? 1.0f / probs_sum : 0.f;
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      if (y) accB[i] = fmaf(q[i], rS, accB[i]);
-      else accA[i] = fmaf(q[i], rS, accA[i]);
+      for (int i = 0; i < KPL; ++i) {
+        if (y) accB[i] = fmaf(q[i], rS, accB[i]);
+        else accA[i] = fmaf(q[i], rS, accA[i]);
+      }
     }
   }
   // combine: sub-groups of a warp (shuffle tree over the sub-group index), then the CTA's warps in
@@ -1451,54 +1902,54 @@ __global__ void __launch_bounds__(128) k_cols_ppx_reduce(const __grid_constant__
 struct ColsNsArgs {
   ColsRankView r[AMMSB_MAX_SHARDS];
   ColsBoxLayout lay;
+  NsGeom g;
   const uint32_t* nodes;
-  uint32_t nv, G, V, N, n, gsize, third, per_rank_blocks;
+  uint32_t nv, G, V, gsize, third, per_rank_blocks;
 };
 
-__global__ void __launch_bounds__(64) k_cols_neighbor_sample(const __grid_constant__ ColsNsArgs a) {
-  extern __shared__ uint32_t s_tab[];
+// A warp per 32 of the rank's work-items: every lane draws its slot's ids into its own column of a
+// shared-memory table (ns_draw_slot, common.cuh), then the warp packs the tables one by one (table
+// order, first n entries: sample.cc:64-74) and delivers each list to every rank with ONE coalesced
+// store per peer -- n scattered 4-byte peer stores per slot would be bound by the NVLink message
+// rate and compete with the partial-sum exchange of update_phi.
+__global__ void __launch_bounds__(32) k_cols_neighbor_sample(const __grid_constant__ ColsNsArgs a) {
+  extern __shared__ uint32_t s_tab[];  // [capacity][33]
+  constexpr uint32_t STRIDE = 33;
   const uint32_t vr = blockIdx.x / a.per_rank_blocks, blk = blockIdx.x % a.per_rank_blocks;
   const ColsRankView& me = a.r[vr];
-  const uint32_t t = blk * blockDim.x + threadIdx.x;
-  const uint32_t gid = me.rank + a.G * t;  // the reference work-items of this rank
-  const uint32_t capacity = 2 * a.n, N = a.N, n = a.n;
-  if (gid >= a.gsize || gid >= a.V) return;
-  Rng seed = rng_load(me.pool, gid);
-  uint32_t* tab = s_tab + threadIdx.x;
-  const uint32_t stride = blockDim.x;
-  for (uint32_t i = gid; i < a.V; i += a.gsize) {
-    const uint32_t node = a.nodes[i];
-    for (uint32_t j = 0; j < capacity; ++j) tab[j * stride] = N;
-    for (uint32_t j = 0; j < n; ++j) {
-      uint32_t r, val;
-      do {
-        do {
-          r = (uint32_t)(rng_next(seed) % (uint64_t)N);  // randint(seed, 0, N - 1), random.cl.inc:37-39
-        } while (r == node);
-        const uint32_t l1 = (r ^ 553105253u) % capacity;
-        const uint32_t l2 = 1u + (capacity << 1);
-        for (uint32_t q = 0;; ++q) {
-          const uint32_t off = (l1 + q * l2) % capacity;
-          val = tab[off * stride];
-          if (val == r) break;
-          if (val == N) {
-            tab[off * stride] = r;
-            break;
-          }
+  const uint32_t lane = threadIdx.x;
+  const uint32_t gid0 = me.rank + a.G * (blk * 32);  // the reference work-items of this rank: rank, rank + G, ...
+  const uint32_t gid = gid0 + a.G * lane;
+  const uint32_t n = a.g.n, N = a.g.N, cap = a.g.capacity;
+  const bool owner = gid < a.gsize && gid < a.V;
+  Rng seed;
+  seed.x = seed.y = 0;
+  if (owner) seed = rng_load(me.pool, gid);
+  const uint32_t lanes_lt = (1u << lane) - 1;
+  const size_t region = a.lay.NB + (size_t)a.third * a.lay.NB_third;
+  for (uint32_t pass = 0; gid0 + pass < a.V; pass += a.gsize) {  // warp-uniform: the passes of the warp's first work-item
+    const uint32_t i = gid + pass;
+    if (owner && i < a.V) ns_draw_slot(seed, __ldg(&a.nodes[i]), a.g, s_tab + lane, STRIDE);
+    __syncwarp();
+    for (uint32_t t = 0; t < 32; ++t) {
+      const uint32_t gt = gid0 + a.G * t;
+      if (gt >= a.gsize || gt + pass >= a.V) break;
+      const size_t out = (size_t)(gt + pass) * n;
+      uint32_t count = 0;
+      for (uint32_t c = 0; c < cap && count < n; c += 32) {
+        const uint32_t j = c + lane;
+        const uint32_t v = j < cap ? s_tab[j * STRIDE + t] : N;
+        const uint32_t m = __ballot_sync(FULL_MASK, v != N);
+        const uint32_t pos = count + __popc(m & lanes_lt);
+        if (v != N && pos < n) {
+          for (uint32_t p = 0; p < a.G; ++p) st_mbox(reinterpret_cast<uint32_t*>(me.box[p] + region) + out + pos, v);
         }
-      } while (val == r);
-    }
-    uint32_t count = 0;
-    for (uint32_t j = 0; j < capacity && count < n; ++j) {
-      const uint32_t v = tab[j * stride];
-      if (v != N) {
-        for (uint32_t p = 0; p < a.G; ++p)
-          st_mbox(reinterpret_cast<uint32_t*>(me.box[p] + a.lay.NB + (size_t)a.third * a.lay.NB_third) + (size_t)i * n + count, v);
-        ++count;
+        count += __popc(m);
       }
     }
+    __syncwarp();
   }
-  rng_store(me.pool, gid, seed);
+  if (owner) rng_store(me.pool, gid, seed);
 }
 
 // ---- init / host access ----
@@ -1801,6 +2252,16 @@ static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_
     if (smem <= c->smem_optin || warps == 1) break;
   }
   AMMSB_REQUIRE(smem <= c->smem_optin, "column update_phi: shared memory request exceeds the device limit");
+  const uint32_t active = a.units < a.V ? a.units : a.V;
+  const uint32_t ngroups = (active + G - 1) / G;
+  // few slots (a link mini-batch): a warp per SLOT instead of a warp per group of G slots, so that
+  // the slots' load / exchange / Langevin chains run side by side (CTAs of a multiple of G warps)
+  const uint32_t wsplit = warps / G * G;
+  a.split = wsplit > 0 && (size_t)ngroups * G <= (size_t)cols_usable_sms(c) / nv * wsplit && !getenv("AMMSB_COLS_NOSPLIT");
+  if (a.split) {
+    warps = wsplit;
+    smem = ColsPhi2Smem::per_cta(KG) + (size_t)warps * ColsPhi2Smem::per_warp(KG);
+  }
   auto kern = k_cols_phi2<KPL, G>;
   static bool attr_set[64] = {false};  // per device
   if (!attr_set[c->device & 63]) {
@@ -1811,11 +2272,10 @@ static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_
   AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
   AMMSB_REQUIRE(occ > 0, "column update_phi: kernel does not fit on an SM");
   const uint32_t resident = (uint32_t)occ * cols_usable_sms(c);
-  const uint32_t active = a.units < a.V ? a.units : a.V;
-  const uint32_t ngroups = (active + G - 1) / G;
   uint32_t ctas = resident / nv;
-  if (ctas * warps > ngroups) ctas = (ngroups + warps - 1) / warps;
-  if (ctas > 0) {  // an even share of groups per warp (a static schedule: the slowest warp ends the kernel)
+  const uint32_t tasks = a.split ? ngroups * G : ngroups;
+  if (ctas * warps > tasks) ctas = (tasks + warps - 1) / warps;
+  if (ctas > 0 && !a.split) {  // an even share of groups per warp (a static schedule: the slowest warp ends the kernel)
     const uint32_t per = (ngroups + ctas * warps - 1) / (ctas * warps);
     const uint32_t need = (ngroups + per - 1) / per;
     ctas = (need + warps - 1) / warps;
@@ -1829,6 +2289,61 @@ static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_
                                                smem, c->stream));
   AMMSB_LAUNCH_CHECK();
   return 0;
+}
+
+// which update_phi kernel takes the large mini-batches of pieces <= 512 bytes: AMMSB_COLS_PHI3=1 / =0
+static bool cols_phi3_default() {
+  if (const char* e = getenv("AMMSB_COLS_PHI3")) return atoi(e) != 0;
+  return false;
+}
+
+// k_cols_phi3 (pieces <= 512 bytes, n <= 32): COLS_PHI3_WARPS warps per SM, every CTA resident
+template <int KPL, int G>
+static int cols_phi3_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_nz, size_t nz_warps) {
+  constexpr uint32_t KG = KPL * (32 / G);
+  if constexpr (KG > 128) {
+    AMMSB_REQUIRE(false, "k_cols_phi3 handles pieces of at most 512 bytes");
+    return 1;
+  } else {
+    uint32_t warps = COLS_PHI3_WARPS;
+    if (const char* e = getenv("AMMSB_COLS_WARPS")) warps = (uint32_t)atoi(e);
+    if (warps < 1) warps = 1;
+    if (warps > COLS_PHI3_WARPS) warps = COLS_PHI3_WARPS;
+    size_t smem;
+    for (;; --warps) {
+      smem = ColsPhi3Smem::per_cta(KG) + (size_t)warps * ColsPhi3Smem::per_warp(KG);
+      if (smem <= c->smem_optin || warps == 1) break;
+    }
+    AMMSB_REQUIRE(smem <= c->smem_optin, "column update_phi: shared memory request exceeds the device limit");
+    auto kern = k_cols_phi3<KPL, G>;
+    static bool attr_set[64] = {false};  // per device
+    if (!attr_set[c->device & 63]) {
+      AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+      attr_set[c->device & 63] = true;
+    }
+    int occ = 0;
+    AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+    AMMSB_REQUIRE(occ > 0, "column update_phi: kernel does not fit on an SM");
+    const uint32_t resident = (uint32_t)occ * cols_usable_sms(c);
+    const uint32_t active = a.units < a.V ? a.units : a.V;
+    const uint32_t ngroups = (active + G - 1) / G;
+    uint32_t ctas = resident / nv;
+    if (ctas * warps > ngroups) ctas = (ngroups + warps - 1) / warps;
+    if (ctas > 0) {  // an even share of groups per warp (a static schedule: the slowest warp ends the kernel)
+      const uint32_t per = (ngroups + ctas * warps - 1) / (ctas * warps);
+      const uint32_t need = (ngroups + per - 1) / per;
+      ctas = (need + warps - 1) / warps;
+    }
+    AMMSB_REQUIRE(ctas > 0, "column update_phi: no resident CTA available per rank");
+    AMMSB_REQUIRE((size_t)ctas * nv * warps <= nz_warps, "column update_phi: noise scratch too small");
+    a.ctas_per_rank = ctas;
+    a.nv = nv;
+    void* params[] = {&a, &d_nz};
+    AMMSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(ctas * nv), dim3(warps * 32), params,
+                                                 smem, c->stream));
+    AMMSB_LAUNCH_CHECK();
+    return 0;
+  }
 }
 
 template <int KPL, int G>
@@ -1921,6 +2436,7 @@ extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uin
   a.disable_noise = o->disable_noise;
   a.loopback = getenv("AMMSB_COLS_LOOPBACK") != nullptr;
   a.debug = getenv("AMMSB_COLS_DEBUG") ? (uint32_t)atoi(getenv("AMMSB_COLS_DEBUG")) : 0;
+  a.fake_lat = (a.loopback && getenv("AMMSB_COLS_FAKE_LAT")) ? (uint32_t)(atof(getenv("AMMSB_COLS_FAKE_LAT")) * 1.965) : 0;
   a.eps_t = ammsb_eps_t(p, step_count);
   a.alpha = p->alpha;
   a.epsilon = p->epsilon;
@@ -1928,10 +2444,14 @@ extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uin
   const uint32_t kpl = p->K / 32, G = s0->G;
   const bool staged = getenv("AMMSB_COLS_STAGED") != nullptr;  // the per-neighbor stage-ring kernel (A/B measurements)
   AMMSB_REQUIRE(!(staged && a.nb_poll), "the stage-ring kernel needs the neighbor lists as an argument");
+  // pieces of at most 512 bytes and n <= 32: the register-buffered kernel (AMMSB_COLS_PHI2 keeps k_cols_phi2)
+  const bool phi3 = !staged && (p->K / G) <= 128 && a.n <= 32 && V > 2048 && !a.debug && cols_phi3_default();
 #define COLS_PHI_CASE(KPL_, G_)                                                                              \
-  if (kpl == KPL_ && G == G_)                                                                                \
+  if (kpl == KPL_ && G == G_) {                                                                              \
+    if (phi3) return cols_phi3_launch<KPL_, G_>(c, a, nv, ranks[0]->d_nz, ranks[0]->nz_warps);               \
     return staged ? cols_phi_launch<KPL_, G_>(c, a, nv)                                                      \
-                  : cols_phi2_launch<KPL_, G_>(c, a, nv, ranks[0]->d_nz, ranks[0]->nz_warps);
+                  : cols_phi2_launch<KPL_, G_>(c, a, nv, ranks[0]->d_nz, ranks[0]->nz_warps);                \
+  }
   COLS_PHI_CASE(4, 2) COLS_PHI_CASE(4, 4) COLS_PHI_CASE(4, 8)
   COLS_PHI_CASE(8, 2) COLS_PHI_CASE(8, 4) COLS_PHI_CASE(8, 8)
   COLS_PHI_CASE(16, 2) COLS_PHI_CASE(16, 4) COLS_PHI_CASE(16, 8)
@@ -1960,17 +2480,16 @@ extern "C" int ammsb_cols_neighbor_sample(ammsb_ctx* c, ammsb_cols* const* ranks
     a.r[i] = ranks[i]->view(pools[i]->d_state);
   }
   a.lay = s0->lay;
+  a.g = ns_geom((uint32_t)s0->N, s0->n);
   a.nodes = d_nodes;
   a.nv = nv;
   a.G = s0->G;
   a.V = V;
-  a.N = (uint32_t)s0->N;
-  a.n = s0->n;
   a.third = step_count % 3;
-  const uint32_t block = 64;
+  const uint32_t block = 32;
   const uint32_t mine = (active + s0->G - 1) / s0->G;  // work-items of one rank
   a.per_rank_blocks = (mine + block - 1) / block;
-  const size_t smem = sizeof(uint32_t) * 2 * s0->n * block;
+  const size_t smem = sizeof(uint32_t) * 2 * s0->n * 33;
   AMMSB_REQUIRE(smem <= c->smem_optin, "num_node_sample too large for the shared-memory table");
   if (smem > 48 * 1024)
     AMMSB_CHECK_CUDA(cudaFuncSetAttribute(k_cols_neighbor_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

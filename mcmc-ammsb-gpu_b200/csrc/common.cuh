@@ -194,6 +194,68 @@ __device__ __forceinline__ float rng_uniform(Rng& s) {
   return __ull2float_rn(rng_next(s)) * 5.42101086242752217e-20f;  // 2^-64
 }
 
+// ---- NeighborSampler building blocks (sample.cc:13-77), shared by small_kernels.cu / cols.cu ----
+// generate_random_int draws `rand % N` from a 64-bit xorshift value and probes an open-addressing
+// table with `(l1 + q * (1 + 2 * capacity)) % capacity`.  The same values, without a divide: the
+// 64-bit remainder by N is Lemire's multiply form (as set_mod), `x % capacity` a mask or the 32-bit
+// multiply form, and the probe sequence is l1, l1 + 1, ... (mod capacity) because
+// 1 + 2 * capacity = 1 (mod capacity).
+struct NsGeom {
+  uint64_t n_m_hi, n_m_lo;  // ceil(2^128 / N)
+  uint64_t cap_m;           // ceil(2^64 / capacity)
+  uint32_t N, n, capacity, cap_pow2;
+};
+static inline NsGeom ns_geom(uint32_t N, uint32_t n) {
+  NsGeom g;
+  const unsigned __int128 m = ~static_cast<unsigned __int128>(0) / N + 1;
+  g.n_m_hi = static_cast<uint64_t>(m >> 64);
+  g.n_m_lo = static_cast<uint64_t>(m);
+  g.N = N;
+  g.n = n;
+  g.capacity = 2 * n;
+  g.cap_m = ~0ull / g.capacity + 1;
+  g.cap_pow2 = (g.capacity & (g.capacity - 1)) == 0;
+  return g;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t ns_mod_N(const NsGeom& g, uint64_t a) {
+  const uint64_t low_lo = g.n_m_lo * a;
+  const uint64_t low_hi = __umul64hi(g.n_m_lo, a) + g.n_m_hi * a;
+  const uint64_t bottom_hi = __umul64hi(low_lo, (uint64_t)g.N);
+  const uint64_t top_lo = low_hi * g.N, top_hi = __umul64hi(low_hi, (uint64_t)g.N);
+  return (uint32_t)(top_hi + ((top_lo + bottom_hi) < top_lo ? 1 : 0));
+}
+// one slot: n distinct ids != node into the table tab[j * stride], j < capacity (empty = N)
+__device__ __forceinline__ void ns_draw_slot(Rng& seed, uint32_t node, const NsGeom& g, uint32_t* tab, uint32_t stride) {
+  const uint32_t cap = g.capacity, N = g.N;
+  for (uint32_t j = 0; j < cap; ++j) tab[j * stride] = N;
+  for (uint32_t j = 0; j < g.n; ++j) {
+    for (;;) {
+      uint32_t r;
+      do {
+        r = ns_mod_N(g, rng_next(seed));  // randint(seed, 0, N - 1), random.cl.inc:37-39
+      } while (r == node);
+      const uint32_t h = r ^ 553105253u;
+      uint32_t off = g.cap_pow2 ? (h & (cap - 1)) : (uint32_t)__umul64hi(g.cap_m * h, (uint64_t)cap);
+      bool dup = false;
+      for (;;) {
+        const uint32_t val = tab[off * stride];
+        if (val == r) {
+          dup = true;
+          break;
+        }
+        if (val == N) {
+          tab[off * stride] = r;
+          break;
+        }
+        off = off + 1 == cap ? 0 : off + 1;
+      }
+      if (!dup) break;
+    }
+  }
+}
+#endif
+
 __device__ const uint32_t d_zig_ytab[128] = AMMSB_ZIG_YTAB_BITS_INIT;
 __device__ const uint32_t d_zig_ktab[128] = AMMSB_ZIG_KTAB_INIT;
 __device__ const uint32_t d_zig_wtab[128] = AMMSB_ZIG_WTAB_BITS_INIT;

@@ -1,5 +1,7 @@
 // small_kernels.cu -- RNG pools, cuckoo membership, neighbor sampler, pi init and
 // the work-group sum/normalise helpers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------- RNG ----
@@ -181,6 +183,45 @@ __global__ void k_neighbor_sample(ulonglong2* pool, const uint32_t* __restrict__
   rng_store(pool, gid, seed);
 }
 
+// The production launch: a warp per 32 work-items.  Each lane draws its slot's ids into its own
+// column of a shared-memory table (stride 33 words: conflict-free for the per-lane probes AND for
+// the row-wise read-out), then the warp packs the 32 tables one after the other -- table order,
+// first n entries, as sample.cc:64-74 -- with ballots, so that a slot's list leaves the SM as one
+// coalesced 4n-byte store instead of n scattered words.  Same draws, same lists, same pool state as
+// k_neighbor_sample; no divide in the loop (NsGeom).
+#define NS_WARP_STRIDE 33
+__global__ void __launch_bounds__(32)
+    k_neighbor_sample_warp(ulonglong2* pool, const uint32_t* __restrict__ nodes, uint32_t V, uint32_t gsize,
+                           const NsGeom g, uint32_t* __restrict__ packed_all) {
+  extern __shared__ uint32_t s_tab[];  // [capacity][33]
+  const uint32_t lane = threadIdx.x, first = blockIdx.x * 32, gid = first + lane;
+  const bool owner = gid < gsize && gid < V;
+  Rng seed;
+  seed.x = seed.y = 0;
+  if (owner) seed = rng_load(pool, gid);
+  const uint32_t lanes_lt = (1u << lane) - 1;
+  for (uint32_t base = first; base < V; base += gsize) {  // warp-uniform: the passes of work-item `first`
+    const uint32_t i = base + lane;
+    if (owner && i < V) ns_draw_slot(seed, __ldg(&nodes[i]), g, s_tab + lane, NS_WARP_STRIDE);
+    __syncwarp();
+    for (uint32_t t = 0; t < 32; ++t) {
+      if (first + t >= gsize || base + t >= V) break;
+      uint32_t* packed = packed_all + (size_t)(base + t) * g.n;
+      uint32_t count = 0;
+      for (uint32_t c = 0; c < g.capacity && count < g.n; c += 32) {
+        const uint32_t j = c + lane;
+        const uint32_t v = j < g.capacity ? s_tab[j * NS_WARP_STRIDE + t] : g.N;
+        const uint32_t m = __ballot_sync(FULL_MASK, v != g.N);
+        const uint32_t pos = count + __popc(m & lanes_lt);
+        if (v != g.N && pos < g.n) packed[pos] = v;
+        count += __popc(m);
+      }
+    }
+    __syncwarp();
+  }
+  if (owner) rng_store(pool, gid, seed);
+}
+
 extern "C" int ammsb_neighbor_sample(ammsb_ctx* c, ammsb_rng* pool, const uint32_t* d_nodes,
                                      uint32_t V, uint32_t N, uint32_t n, uint32_t wg,
                                      uint32_t* d_neighbors, uint32_t* d_hash_out) {
@@ -193,6 +234,13 @@ extern "C" int ammsb_neighbor_sample(ammsb_ctx* c, ammsb_rng* pool, const uint32
   if (groups > 65535u / wg) groups = 65535u / wg;
   const uint32_t gsize = groups * wg;
   AMMSB_REQUIRE(pool->n >= (uint64_t)(gsize < V ? gsize : V), "Num seeds smaller than global threads");
+  if (d_hash_out == nullptr && sizeof(uint32_t) * 2 * n * NS_WARP_STRIDE <= 48 * 1024 && !getenv("AMMSB_NS_THREAD")) {
+    const uint32_t active = gsize < V ? gsize : V;
+    k_neighbor_sample_warp<<<(active + 31) / 32, 32, sizeof(uint32_t) * 2 * n * NS_WARP_STRIDE, c->stream>>>(
+        pool->d_state, d_nodes, V, gsize, ns_geom(N, n), d_neighbors);
+    AMMSB_LAUNCH_CHECK();
+    return 0;
+  }
   const uint32_t block = 64;
   size_t smem = d_hash_out ? 0 : sizeof(uint32_t) * 2 * n * block;
   if (smem > c->smem_optin) {

@@ -372,16 +372,29 @@ class ShardedLearner:
         if self.ns_seq >= seq:
             return
         b = seq & 1
-        self.ns_stream.wait_event(self.ev_phi[b])  # update_phi of mini-batch seq-2 is done with the buffer
+        # column shards: the sampler runs on the COMPUTE stream, between the kernels of the previous
+        # mini-batch -- the column kernels are persistent cooperative grids that wait for their peers,
+        # and a concurrent kernel on a side stream either starves on the SMs they leave free or holds
+        # up their launch (measured on 8 GPUs: 0.5 ms on the side stream for 40 us of work)
+        ns_stream = self.stream if self.cols is not None else self.ns_stream
+        ns_stream.wait_event(self.ev_phi[b])  # update_phi of mini-batch seq-2 is done with the buffer
         if after is not None:
-            self.ns_stream.wait_event(after)  # the nodes are on this GPU
+            ns_stream.wait_event(after)  # the nodes are on this GPU
+        ns_ev = getattr(self, "ns_timing", None)
+        if ns_ev is not None:
+            e0 = self.torch.cuda.Event(enable_timing=True)
+            e0.record(ns_stream)
         if self.cols is not None:
             # each rank draws the lists of the sampler states it owns and delivers them to every
             # rank's mailbox (third seq % 3); update_phi of step seq reads them there
-            self.A.cols_neighbor_sample(self.ctx_ns, [self.cols], d_nodes, V, 32, seq, [self.npools[pool_index]])
+            self.A.cols_neighbor_sample(self.ctx, [self.cols], d_nodes, V, 32, seq, [self.npools[pool_index]])
         else:
             self.ctx_ns.neighbor_sample(self.npools[pool_index], d_nodes, V, self.N, self.n, 32, tbuf(self.d_nbs[b]))
-        self.ev_ns[b].record(self.ns_stream)
+        if ns_ev is not None:
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e1.record(ns_stream)
+            ns_ev.append((V, e0, e1))
+        self.ev_ns[b].record(ns_stream)
         self.ns_seq = seq
 
     def device_step(self, d_nodes, d_edges, V, E_mb, weight, pool_index, phi_events=None, seq=None):
@@ -405,7 +418,11 @@ class ShardedLearner:
                 phi_events[1].record(self.stream)
             self.ev_phi[seq & 1].record(self.stream)
             A.cols_update_pi(ctx, [self.cols], d_nodes, V, self.step_count)
+            if phi_events is not None and len(phi_events) > 2:
+                phi_events[2].record(self.stream)
             A.cols_update_beta(ctx, [self.cols], p, self.train, d_edges, E_mb, weight, self.step_count, [self.bpool])
+            if phi_events is not None and len(phi_events) > 2:
+                phi_events[3].record(self.stream)
             self.edges_processed += E_mb
             return
         if phi_events is not None:
@@ -418,6 +435,8 @@ class ShardedLearner:
         self.barrier()  # every read of the old pi is done before any rank writes
         ctx.update_pi_part(K, self.store, tbuf(self.d_vec), tbuf(self.d_sum), d_nodes, V, self.opts)
         self.barrier()  # every write is visible before beta reads pi
+        if phi_events is not None and len(phi_events) > 2:
+            phi_events[2].record(self.stream)
         lo, hi = chunk(E_mb, self.rank, self.world)
         ctx.beta_grads(p, tbuf(self.theta), tbuf(self.beta), self.store, self.train,
                        _Buf(d_edges.ptr.value + 8 * lo), hi - lo, tbuf(self.d_tsum), tbuf(self.grads), tbuf(self.ws))
@@ -426,6 +445,8 @@ class ShardedLearner:
         elif self.world > 1:
             self.dist.all_reduce(self.grads)
         ctx.update_theta(p, tbuf(self.theta), tbuf(self.beta), tbuf(self.grads), weight, self.step_count, self.bpool)
+        if phi_events is not None and len(phi_events) > 2:
+            phi_events[3].record(self.stream)
         self.edges_processed += E_mb
 
     def host_step(self):
@@ -690,11 +711,15 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
         clocks.start()  # sampled from before the warm-up to the end of the timed region
     for i in range(args.warmup):
         step(i)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # AMMSB_STAGE_EVENTS=1: events after update_pi and update_beta as well (per-stage times of the run itself)
+    nev = 4 if os.environ.get("AMMSB_STAGE_EVENTS") else 2
+    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(nev)) for _ in range(args.steps)]
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
     launches0 = A.launch_count()
+    if nev == 4:
+        lrn.ns_timing = []
     e_start.record(stream)
     for k in range(args.steps):
         step(args.warmup + k, evs[k])
@@ -703,7 +728,7 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
     dist.barrier()
     torch.cuda.synchronize()
     launches = A.launch_count() - launches0
-    t = torch.tensor([e_start.elapsed_time(e_stop), sum(a.elapsed_time(b) for a, b in evs)],
+    t = torch.tensor([e_start.elapsed_time(e_stop), sum(e[0].elapsed_time(e[1]) for e in evs)],
                      dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
     dev_ms, phi_ms = float(t[0]), float(t[1])
@@ -754,6 +779,24 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
                     "share_of_step": round(phi_ms / dev_ms, 4),
                     "nvlink_outbound_GB_per_gpu_per_step": round(out_bytes / args.steps / 1e9, 4)}
     roofline["store"] = mode
+    stages_in_run = None
+    if nev == 4:
+        # mean ms per stage over the timed steps of this rank, non-link and link mini-batches apart;
+        # "gap" = from the end of update_beta to the start of the next update_phi on the stream
+        stages_in_run = {}
+        for kind, sel in (("non_link", lambda V: V > 1024), ("link", lambda V: V <= 1024)):
+            ks = [k for k in range(args.steps) if sel(Vs[k])]
+            if not ks:
+                continue
+            d = {"steps": len(ks),
+                 "update_phi": float(np.mean([evs[k][0].elapsed_time(evs[k][1]) for k in ks])),
+                 "update_pi": float(np.mean([evs[k][1].elapsed_time(evs[k][2]) for k in ks])),
+                 "update_beta": float(np.mean([evs[k][2].elapsed_time(evs[k][3]) for k in ks]))}
+            ns = [a.elapsed_time(b) for V, a, b in lrn.ns_timing if sel(V)]
+            d["neighbor_sample"] = float(np.mean(ns)) if ns else 0.0
+            gaps = [evs[k][3].elapsed_time(evs[k + 1][0]) for k in ks if k + 1 < args.steps]
+            d["gap_to_next"] = float(np.mean(gaps)) if gaps else 0.0
+            stages_in_run[kind] = {a: round(b, 4) if isinstance(b, float) else b for a, b in d.items()}
 
     # ---- perplexity (sharded) ----
     torch.cuda.synchronize()
@@ -799,6 +842,8 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
             "parity_vs_n1": parity,
         }
+        if stages_in_run is not None:
+            line["stages_in_run_ms"] = stages_in_run
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

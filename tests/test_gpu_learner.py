@@ -49,16 +49,26 @@ class OracleLearner:
         self.ppx_calls = 0
 
     def iterate(self, edges, nodes, weight):
+        nbrs = self.iterate_phi_pi(nodes)
+        self.iterate_beta(edges, weight)
+        return nbrs
+
+    def iterate_phi_pi(self, nodes):
+        """neighbor sampling, update_phi, update_pi of the next iteration"""
         o = self.orc
         nbrs, _ = o.neighbor_sample(self.nb_pools[self.phase], nodes, self.N, self.n, 32)
         self.step += 1
         vec = o.update_phi(A.MODE_WG, 32, self.p, self.beta, self.pi, self.phi, self.train_set, nodes, nbrs,
                            self.step, self.phi_pool)
         o.update_pi(A.MODE_WG, 32, self.K, self.pi, self.phi, vec, nodes)
-        o.update_beta(A.MODE_WG, 32, self.p, self.theta, self.beta, self.pi, self.train_set, edges, weight,
-                      self.step, self.beta_pool)
-        self.phase = 1 - self.phase
         return nbrs
+
+    def iterate_beta(self, edges, weight):
+        """update_beta of the iteration iterate_phi_pi began (reads self.pi: a test may put the
+        device's rows there first, so that the stage is judged from identical input)"""
+        self.orc.update_beta(A.MODE_WG, 32, self.p, self.theta, self.beta, self.pi, self.train_set, edges, weight,
+                             self.step, self.beta_pool)
+        self.phase = 1 - self.phase
 
     def perplexity(self):
         self.ppx_calls += 1

