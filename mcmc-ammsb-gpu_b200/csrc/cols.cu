@@ -722,12 +722,19 @@ __global__ void __launch_bounds__(256, 1) k_cols_phi(const __grid_constant__ Col
 // control flow.
 struct ColsPhi2Smem {
   __host__ __device__ static size_t pstr(uint32_t KG) { return (size_t)KG * 4 + 16; }  // piece stride: conflict-free float4 rows
-  __host__ __device__ static size_t per_warp(uint32_t KG) { return (33 * pstr(KG) + 128 + 127) / 128 * 128; }
+  __host__ __device__ static size_t per_warp(uint32_t KG) { return (33 * pstr(KG) + 128 + (size_t)KG * 4 + 127) / 128 * 128; }
   __host__ __device__ static size_t per_cta(uint32_t KG) { return 1536 + (((size_t)KG * 4 + 127) / 128 * 128); }
+  // warps of a CTA (one CTA per SM): what 227 KB of shared memory hold, at most 16; registers come in
+  // units of four warps, so 13-15 warps would cost the 128-register budget of 16 for little: 12 (168)
+  __host__ __device__ static constexpr uint32_t max_warps(uint32_t KG) {
+    const size_t pw = (33 * ((size_t)KG * 4 + 16) + 128 + (size_t)KG * 4 + 127) / 128 * 128, pc = 1536 + (((size_t)KG * 4 + 127) / 128 * 128);
+    const size_t fit = (232448 - pc) / pw;
+    return fit >= 16 ? 16u : (fit > 12 ? 12u : (fit < 1 ? 1u : (uint32_t)fit));
+  }
 };
 
 template <int KPL, int G>
-__global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ ColsPhiArgs a, float* __restrict__ nz_scratch) {
+__global__ void __launch_bounds__(ColsPhi2Smem::max_warps(KPL * (32 / G)) * 32, 1) k_cols_phi2(const __grid_constant__ ColsPhiArgs a, float* __restrict__ nz_scratch) {
   constexpr int LPG = 32 / G, KG = KPL * LPG, F4 = KG / 4;
   constexpr int PSTR = KG * 4 + 16;
   constexpr int FPL = (F4 + 31) / 32;  // float4 per lane in the column phases
@@ -762,6 +769,7 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
   unsigned char* s_rows = wbase;                                   // [32] neighbor pieces
   unsigned char* s_own = wbase + 32 * PSTR;                        // own piece, later the new phi piece
   float* s_inv = reinterpret_cast<float*>(wbase + 33 * PSTR);      // [32] 1 / (probs_sum * phi_sum)
+  float* s_new = reinterpret_cast<float*>(wbase + 33 * PSTR + 128);  // the new phi piece (row-sum scratch)
   const uint32_t rows_u32 = smem_u32(s_rows);
 
   const size_t half_S = (size_t)a.parity * G * a.lay.S_src, half_R = (size_t)a.parity * G * a.lay.R_src;
@@ -838,17 +846,54 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
     noise_advance();
   }
 
+  // the pieces of a chunk: neighbor b -> row b, (first chunk) the own piece -> row 32; one commit group
+  auto issue_copies = [&](uint32_t node, uint32_t nb, uint32_t cnt, bool own) {
+    if (F4 >= 32) {
+#pragma unroll 8
+      for (uint32_t r = 0; r < 32; ++r) {
+        const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
+        if (r < cnt) {
+#pragma unroll
+          for (int h = 0; h < IPP; ++h)
+            cp_async16_u32(rows_u32 + r * PSTR + (h * 32 + lane) * 16, my_pi + (size_t)id * KG + (h * 32 + lane) * 4);
+        }
+      }
+      if (own) {
+#pragma unroll
+        for (int h = 0; h < IPP; ++h)
+          cp_async16_u32(rows_u32 + 32 * PSTR + (h * 32 + lane) * 16, my_pi + (size_t)node * KG + (h * 32 + lane) * 4);
+      }
+    } else {
+      const uint32_t sub = lane / F4, w = lane % F4;
+#pragma unroll 8
+      for (uint32_t r0 = 0; r0 < 32; r0 += PPI) {
+        const uint32_t r = r0 + sub;
+        const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
+        if (r < cnt) cp_async16_u32(rows_u32 + r * PSTR + w * 16, my_pi + (size_t)id * KG + w * 4);
+      }
+      if (own && lane < F4) cp_async16_u32(rows_u32 + 32 * PSTR + lane * 16, my_pi + (size_t)node * KG + lane * 4);
+    }
+    cp_async_commit();
+  };
+
   uint32_t group = g_first, pass = 0;
   for (; group < ngroups; next_gp(group, pass)) {
     {
       const uint32_t use_half = nz_half ^ 1;  // the half the cursor filled before it moved on
       {
+      // the next slot's node, row sum, neighbor id and cuckoo answer are fetched while the current
+      // slot waits for its partials and runs phase B (n <= 32: one chunk per slot)
+      bool pf_valid = false, pf_y = false, copies_ahead = false;
+      uint32_t pf_node = 0, pf_nb = 0;
+      float pf_phi = 0.f;
       for (uint32_t s = sub_lo; s < sub_hi; ++s) {
         const uint32_t unit = group * G + s, slot = unit + pass * a.units;
         if (unit >= active_units || slot >= a.V) break;  // warp-uniform; later sub-slots are dead too
-        const uint32_t node = __ldg(&a.nodes[slot]);
-        const float phi_sum = my_phi[node];
+        const uint32_t node = pf_valid ? pf_node : __ldg(&a.nodes[slot]);
+        const float phi_sum = pf_valid ? pf_phi : my_phi[node];
         const float rphi = 1.0f / phi_sum;
+        const bool have_pf = pf_valid;
+        const bool pf_next = n <= 32 && s + 1 < sub_hi && unit + 1 < active_units && slot + 1 < a.V && !a.debug;
         const size_t ridx = ((size_t)group * passes + pass) * G + s;
         float4 g4[FPL];
 #pragma unroll
@@ -857,7 +902,9 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
           const uint32_t cnt = min(32u, n - c0);
           // ---- stage the pieces: neighbor b of the chunk -> row b; the own piece -> row 32 ----
           uint32_t nb = node;
-          if (lane < cnt) {
+          if (have_pf) {
+            nb = pf_nb;
+          } else if (lane < cnt) {
             if (a.nb_poll) {  // sampled on the rank that owns the slot's sampler state, delivered by peer stores
               uint32_t* w = reinterpret_cast<uint32_t*>(mybox + a.lay.NB + (size_t)a.nb_third * a.lay.NB_third) + (size_t)slot * n + c0 + lane;
               nb = __float_as_uint(finish_poll(w, peek_mbox(w), err));
@@ -865,37 +912,11 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
               nb = __ldg(&a.neighbors[(size_t)slot * n + c0 + lane]);
             }
           }
-          if (!(a.debug & 8)) {
-            if (F4 >= 32) {
-#pragma unroll 8
-              for (uint32_t r = 0; r < 32; ++r) {
-                const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
-                if (r < cnt) {
-#pragma unroll
-                  for (int h = 0; h < IPP; ++h)
-                    cp_async16_u32(rows_u32 + r * PSTR + (h * 32 + lane) * 16, my_pi + (size_t)id * KG + (h * 32 + lane) * 4);
-                }
-              }
-              if (c0 == 0) {
-#pragma unroll
-                for (int h = 0; h < IPP; ++h)
-                  cp_async16_u32(rows_u32 + 32 * PSTR + (h * 32 + lane) * 16, my_pi + (size_t)node * KG + (h * 32 + lane) * 4);
-              }
-            } else {
-              const uint32_t sub = lane / F4, w = lane % F4;
-#pragma unroll 8
-              for (uint32_t r0 = 0; r0 < 32; r0 += PPI) {
-                const uint32_t r = r0 + sub;
-                const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
-                if (r < cnt) cp_async16_u32(rows_u32 + r * PSTR + w * 16, my_pi + (size_t)id * KG + w * 4);
-              }
-              if (c0 == 0 && lane < F4) cp_async16_u32(rows_u32 + 32 * PSTR + lane * 16, my_pi + (size_t)node * KG + lane * 4);
-            }
-          }
-          cp_async_commit();
+          if (!(a.debug & 8) && !(have_pf && copies_ahead)) issue_copies(node, nb, cnt, c0 == 0);
           // the cuckoo answer for this lane's neighbor while the pieces travel (phi.cc:230-234)
           bool y = false;
-          if (lane < cnt && !(a.debug & 1)) y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
+          if (have_pf) y = pf_y;
+          else if (lane < cnt && !(a.debug & 1)) y = set_has(a.set, make_edge(min(node, nb), max(node, nb)));
           const uint32_t ymask = __ballot_sync(FULL_MASK, y);
           cp_async_wait_pending(0);
           __syncwarp();
@@ -953,6 +974,19 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
                 st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + sidx, bits);
           }
           const long long t_sent = a.fake_lat ? clock64() : 0;
+          uint32_t* pf_w = nullptr;
+          if (pf_next) {  // first-level loads of the next slot, in flight across the noise piece and the wait
+            pf_node = __ldg(&a.nodes[slot + 1]);
+            pf_nb = pf_node;
+            if (lane < n) {
+              if (a.nb_poll) {
+                pf_w = reinterpret_cast<uint32_t*>(mybox + a.lay.NB + (size_t)a.nb_third * a.lay.NB_third) + (size_t)(slot + 1) * n + lane;
+                pf_nb = peek_mbox(pf_w);
+              } else {
+                pf_nb = __ldg(&a.neighbors[(size_t)(slot + 1) * n + lane]);
+              }
+            }
+          }
           if (c0 == 0) noise_piece();  // while the partials cross the switch: part of the next group-pass's noise
           if (a.fake_lat) {
             while (clock64() - t_sent < (long long)a.fake_lat) {}
@@ -976,6 +1010,12 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
           // (probs_k / probs_sum) / (pi_k * phi_sum) - 1 / phi_sum with probs_k / pi_k = t_k
           s_inv[lane] = 1.0f / (P[0] * phi_sum);
           __syncwarp();
+          if (pf_next) {  // second level: the row sum and the cuckoo bins, in flight across phase B
+            pf_phi = my_phi[pf_node];
+            if (pf_w != nullptr) pf_nb = __float_as_uint(finish_poll(pf_w, pf_nb, err));
+            pf_y = lane < n ? set_has(a.set, make_edge(min(pf_node, pf_nb), max(pf_node, pf_nb))) : false;
+          }
+          pf_valid = pf_next;
 
           // ---- phase B: lane = columns (float4 f = lane + 32 r); neighbors in order ----
           if (!(a.debug & 4)) {
@@ -1020,14 +1060,23 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
           }
           __syncwarp();  // the rows may be overwritten by the next chunk / slot
         }
-        // ---- Langevin step (phi.cc:266-274): lane = columns; the new piece replaces the own piece ----
+        // ---- Langevin step (phi.cc:266-274): lane = columns.  The own piece moves to registers and the
+        //      staging buffer is handed to the NEXT slot's copies first (its node and neighbor ids were
+        //      prefetched): they travel while this slot finishes ----
         if (!(a.debug & 16)) {
           const float* nzrow = my_nz + ((size_t)use_half * G + s) * KG;
+          float4 o4[FPL];
+#pragma unroll
+          for (int r = 0; r < FPL; ++r)
+            o4[r] = (lane + 32 * r < F4) ? reinterpret_cast<const float4*>(s_own)[lane + 32 * r] : make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();
+          copies_ahead = pf_valid && !(a.debug & 8);
+          if (copies_ahead) issue_copies(pf_node, pf_nb, n, true);
 #pragma unroll
           for (int r = 0; r < FPL; ++r) {
             const uint32_t f = lane + 32 * r;
             if (f < F4) {
-              const float4 o = reinterpret_cast<const float4*>(s_own)[f];
+              const float4 o = o4[r];
               float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
               if (!a.disable_noise) z = __ldcg(reinterpret_cast<const float4*>(nzrow) + f);
               float4 v;
@@ -1036,7 +1085,7 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
               v.z = phi_langevin(o.z, phi_sum, g4[r].z, z.z, half_eps, a.eps_t, a.alpha, a.Nn);
               v.w = phi_langevin(o.w, phi_sum, g4[r].w, z.w, half_eps, a.eps_t, a.alpha, a.Nn);
               reinterpret_cast<float4*>(my_vec + (size_t)slot * KG)[f] = v;
-              reinterpret_cast<float4*>(s_own)[f] = v;
+              reinterpret_cast<float4*>(s_new)[f] = v;
             }
           }
           __syncwarp();
@@ -1044,7 +1093,7 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
           // strides >= G of the tree; lanes li < LPG hold one reference lane each
           float ls = 0.f;
           if (lane < LPG) {
-            const float* v = reinterpret_cast<const float*>(s_own);
+            const float* v = s_new;
 #pragma unroll 8
             for (int i = 0; i < KPL; ++i) ls += v[((i >> 2) * LPG + lane) * 4 + (i & 3)];
           }
@@ -1057,7 +1106,9 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
                                                 (size_t)(a.loopback ? p : rank) * a.lay.R_src) + ridx,
                     partial_bits(ls));
           }
-          __syncwarp();  // s_own is free for the next slot's own piece
+          __syncwarp();  // s_new is free for the next slot
+        } else {
+          copies_ahead = false;
         }
       }
       }
@@ -1070,390 +1121,6 @@ __global__ void __launch_bounds__(512, 1) k_cols_phi2(const __grid_constant__ Co
   // the last group's streams (the cursor has run past the end: nothing left to persist otherwise)
 }
 
-
-// ----------------------------------------------------------------------------------------------
-// k_cols_phi3 -- k_cols_phi2's slot-at-a-time mapping with the exchange and the loads taken off a
-// warp's critical path (pieces of <= 512 bytes, n <= 32).
-//
-// What bounds k_cols_phi2 on real NVLink is how long a slot occupies its staging buffer: the SM
-// holds 12-13 slot buffers, and a buffer is busy from the first copy until phase B has read it --
-// load (~3 us) + phase A + the partial sums' round trip (~4 us on 8 GPUs) + phase B.  Here the rows
-// of a slot move from shared memory into REGISTERS (lane = columns: one float4 per neighbor, 32
-// neighbors = 128 registers) as soon as phase A has run: the buffer is free for the next slot's
-// copies at once, and the slot's phase B runs one slot LATER, from registers, when its peers'
-// partials have long arrived.  Per iteration a warp
-//     1. collects the partials of slot s-1 (sent an iteration ago) and runs its phase B (registers)
-//     2. waits for the copies of slot s (issued an iteration ago), runs phase A, sends the partials
-//     3. moves the rows of slot s to registers and issues the copies of slot s+1
-//     4. does the Langevin step of slot s-1, one piece of noise, the cuckoo lookups of slot s+1
-// so that neither a copy nor a round trip is ever waited for with nothing else to do.  The
-// arithmetic is k_cols_phi2's expression for expression (bit-identical results).
-struct ColsPhi3Smem {
-  __host__ __device__ static size_t pstr(uint32_t KG) { return (size_t)KG * 4 + 16; }
-  __host__ __device__ static size_t per_warp(uint32_t KG) { return (33 * pstr(KG) + (size_t)KG * 4 + 128 + 127) / 128 * 128; }
-  __host__ __device__ static size_t per_cta(uint32_t KG) { return 1536 + (((size_t)KG * 4 + 127) / 128 * 128); }
-};
-
-// Registers are allocated to a CTA in units of four warps: 9-12 warps leave 168 registers per thread
-// (the 128 row registers then push ~50 values into local memory, which misses the small L1 left
-// beside 219 KB of shared memory: measured 2x slower), 8 warps get 255 and nothing spills.
-#ifndef COLS_PHI3_WARPS
-#define COLS_PHI3_WARPS 8
-#endif
-template <int KPL, int G>
-__global__ void __launch_bounds__(COLS_PHI3_WARPS * 32, 1) k_cols_phi3(const __grid_constant__ ColsPhiArgs a, float* __restrict__ nz_scratch) {
-  constexpr int LPG = 32 / G, KG = KPL * LPG, F4 = KG / 4;
-  static_assert(F4 <= 32, "one float4 of a piece per lane");
-  constexpr int PSTR = KG * 4 + 16;
-  constexpr int PPI = 32 / F4;  // pieces per copy instruction
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  const uint32_t vr = blockIdx.x / a.ctas_per_rank, cta = blockIdx.x % a.ctas_per_rank;
-  const uint32_t rank = a.r[vr].rank;
-  const uint32_t n = a.n;
-  float* const my_pi = a.r[vr].pi;
-  const float* const my_phi = a.r[vr].phi;
-  float* const my_vec = a.r[vr].phi_vec;
-  ulonglong2* const my_pool = a.r[vr].pool;
-
-  uint32_t* s_zig = reinterpret_cast<uint32_t*>(s_raw);
-  const ZigShared zig{s_zig};
-  zig_stage(s_zig);
-  float* s_fb = reinterpret_cast<float*>(s_raw + 1536);  // beta_k - epsilon, local column order
-  unsigned char* mybox = a.r[vr].box[rank];
-  uint32_t* err = reinterpret_cast<uint32_t*>(mybox);
-  {
-    const float* beta = reinterpret_cast<const float*>(mybox + a.lay.beta);
-    for (uint32_t c = threadIdx.x; c < KG; c += blockDim.x) {
-      const uint32_t f = c >> 2, e = c & 3, q = f / LPG, li = f % LPG;
-      const uint32_t k = (rank + G * li) + 32 * (4 * q + e);
-      s_fb[c] = beta[2 * k + 1] - a.epsilon;  // phi.cc:237-239
-    }
-  }
-  __syncthreads();
-  unsigned char* wbase = s_raw + ColsPhi3Smem::per_cta(KG) + (size_t)wib * ColsPhi3Smem::per_warp(KG);
-  unsigned char* s_rows = wbase;                                        // [32] neighbor pieces
-  unsigned char* s_own = wbase + 32 * PSTR;                             // own piece
-  float* s_new = reinterpret_cast<float*>(wbase + 33 * PSTR);           // the new phi piece (row-sum scratch)
-  float* s_inv = reinterpret_cast<float*>(wbase + 33 * PSTR + KG * 4);  // [32] 1 / (probs_sum * phi_sum)
-  const uint32_t rows_u32 = smem_u32(s_rows);
-
-  const size_t half_S = (size_t)a.parity * G * a.lay.S_src, half_R = (size_t)a.parity * G * a.lay.R_src;
-  const float e_link = a.epsilon, e_non = 1.0f - a.epsilon;
-  const float half_eps = a.eps_t / 2;
-
-  const uint32_t active_units = a.units < a.V ? a.units : a.V;
-  const uint32_t ngroups = (active_units + G - 1) / G;
-  const uint32_t passes = (a.V + a.units - 1) / a.units;
-  const uint32_t gwarp = cta * warps + wib, total_warps = a.ctas_per_rank * warps;
-  if (gwarp >= ngroups) return;  // no CTA-wide barrier below
-  float* const my_nz = nz_scratch + ((size_t)vr * total_warps + gwarp) * 2 * G * KG;  // [2][G][KG]
-
-  // ---- the Langevin noise: one group-pass ahead of its use, a float4 per lane at a time (k_cols_phi2) ----
-  const uint32_t s_n = lane / LPG, li_n = lane % LPG, l_ref = rank + G * li_n;
-  constexpr int PIECES = KPL / 4;
-  auto gp_live = [&](uint32_t group, uint32_t pass) -> bool {
-    return group < ngroups && (size_t)group * G + (size_t)pass * a.units < a.V;
-  };
-  auto next_gp = [&](uint32_t& group, uint32_t& pass) {
-    do {
-      if (++pass == passes) {
-        pass = 0;
-        group += total_warps;
-      }
-    } while (group < ngroups && !gp_live(group, pass));
-  };
-  uint32_t nz_group = gwarp, nz_pass = 0, nz_piece = 0, nz_half = 0;
-  Rng st;
-  st.x = st.y = 0;
-  const bool noisy = !a.disable_noise;
-  if (noisy && nz_group * G + s_n < active_units) st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
-  auto noise_piece = [&]() {
-    if (!noisy || nz_group >= ngroups || nz_piece >= (uint32_t)PIECES) return;
-    const uint32_t unit = nz_group * G + s_n, slot = unit + nz_pass * a.units;
-    if (unit < active_units && slot < a.V) {
-      float4 z;
-      z.x = rng_randn_t(st, zig);
-      z.y = rng_randn_t(st, zig);
-      z.z = rng_randn_t(st, zig);
-      z.w = rng_randn_t(st, zig);
-      reinterpret_cast<float4*>(my_nz + ((size_t)nz_half * G + s_n) * KG)[nz_piece * LPG + li_n] = z;
-    }
-    ++nz_piece;
-  };
-  auto noise_advance = [&]() {
-    if (nz_group >= ngroups) return;
-    const uint32_t old = nz_group;
-    next_gp(nz_group, nz_pass);
-    nz_piece = 0;
-    nz_half ^= 1;
-    if (noisy && nz_group != old) {
-      if (old * G + s_n < active_units) rng_store(my_pool, (uint64_t)(old * G + s_n) * 32 + l_ref, st);
-      if (nz_group < ngroups && nz_group * G + s_n < active_units)
-        st = rng_load(my_pool, (uint64_t)(nz_group * G + s_n) * 32 + l_ref);
-    }
-  };
-  for (int k = 0; k < PIECES; ++k) noise_piece();  // the whole noise of the first group-pass
-  __syncwarp();
-  noise_advance();
-
-  // ---- the warp's slots in order: (group, pass), live sub-slots 0 .. ----
-  struct Slot {  // warp-uniform
-    uint32_t slot, node, half, last, valid;
-    float phi_sum;
-    size_t ridx;
-  };
-  uint32_t it_group = gwarp, it_pass = 0, it_sub = 0, it_half = 0;
-  auto sub_live = [&](uint32_t group, uint32_t pass, uint32_t sub) -> bool {
-    const uint32_t unit = group * G + sub;
-    return sub < (uint32_t)G && unit < active_units && (size_t)unit + (size_t)pass * a.units < a.V;
-  };
-  // the slot under the iterator (meta loads issued here), then the iterator moves on
-  auto take = [&](Slot& s, uint32_t& nb) {
-    s.valid = it_group < ngroups;
-    nb = 0;
-    if (!s.valid) return;
-    s.slot = it_group * G + it_sub + it_pass * a.units;
-    s.ridx = ((size_t)it_group * passes + it_pass) * G + it_sub;
-    s.half = it_half;
-    s.node = __ldg(&a.nodes[s.slot]);
-    s.phi_sum = my_phi[s.node];
-    nb = s.node;  // lanes >= n; a polled word is only PEEKED here and resolved by nb_resolve()
-    if (lane < n) {
-      if (a.nb_poll) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(mybox + a.lay.NB + (size_t)a.nb_third * a.lay.NB_third) + (size_t)s.slot * n + lane;
-        nb = peek_mbox(w);
-      } else {
-        nb = __ldg(&a.neighbors[(size_t)s.slot * n + lane]);
-      }
-    }
-    s.last = !sub_live(it_group, it_pass, it_sub + 1);
-    if (s.last) {
-      it_sub = 0;
-      it_half ^= 1;
-      next_gp(it_group, it_pass);
-    } else {
-      ++it_sub;
-    }
-  };
-  // a neighbor id that came through the mailbox: wait for it if the peek was too early, re-arm the word
-  auto nb_resolve = [&](const Slot& s, uint32_t& nb) {
-    if (a.nb_poll && s.valid && lane < n) {
-      uint32_t* w = reinterpret_cast<uint32_t*>(mybox + a.lay.NB + (size_t)a.nb_third * a.lay.NB_third) + (size_t)s.slot * n + lane;
-      nb = __float_as_uint(finish_poll(w, nb, err));
-    }
-  };
-  auto issue_copies = [&](const Slot& s, uint32_t nb) {
-    if (F4 == 32) {
-#pragma unroll 8
-      for (uint32_t r = 0; r < 32; ++r) {
-        const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
-        if (r < n) cp_async16_u32(rows_u32 + r * PSTR + lane * 16, my_pi + (size_t)id * KG + lane * 4);
-      }
-      cp_async16_u32(rows_u32 + 32 * PSTR + lane * 16, my_pi + (size_t)s.node * KG + lane * 4);
-    } else {
-      const uint32_t sub = lane / F4, w = lane % F4;
-#pragma unroll 8
-      for (uint32_t r0 = 0; r0 < 32; r0 += PPI) {
-        const uint32_t r = r0 + sub;
-        const uint32_t id = __shfl_sync(FULL_MASK, nb, r);
-        if (r < n) cp_async16_u32(rows_u32 + r * PSTR + w * 16, my_pi + (size_t)id * KG + w * 4);
-      }
-      if (lane < F4) cp_async16_u32(rows_u32 + 32 * PSTR + lane * 16, my_pi + (size_t)s.node * KG + lane * 4);
-    }
-    cp_async_commit();
-  };
-
-  Slot cur, nxt, prev;
-  prev.valid = 0;
-  uint32_t nb_cur, nb_nxt;
-  take(cur, nb_cur);
-  nb_resolve(cur, nb_cur);
-  issue_copies(cur, nb_cur);
-  bool y_cur = false;
-  if (lane < n) y_cur = set_has(a.set, make_edge(min(cur.node, nb_cur), max(cur.node, nb_cur)));
-
-  float4 xr[32];        // rows of the slot whose exchange is in flight, lane = float4 of the piece
-  float4 o_prev = make_float4(0.f, 0.f, 0.f, 0.f);  // its own piece
-  float S_prev = 0.f;   // its partial sum (lane = neighbor)
-  uint32_t ymask_prev = 0;
-  long long t_sent = 0;
-  const bool col_lane = lane < (uint32_t)F4;
-
-  while (cur.valid || prev.valid) {
-    take(nxt, nb_nxt);  // meta loads of the slot after `cur`: consumed in step 3
-    // ---- 1. slot prev: collect the peers' partials, phase B from registers ----
-    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (prev.valid) {
-      const size_t sidx = prev.ridx * n + lane;
-      float P[G];
-#pragma unroll
-      for (int p = 0; p < G; ++p) P[p] = S_prev;
-      if (a.fake_lat) {
-        while (clock64() - t_sent < (long long)a.fake_lat) {}
-      }
-      if (lane < n && !a.loopback) {
-        uint32_t w[G];
-#pragma unroll
-        for (int p = 0; p < G; ++p)
-          if ((uint32_t)p != rank)
-            w[p] = peek_mbox(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p * a.lay.S_src) + sidx);
-#pragma unroll
-        for (int p = 0; p < G; ++p)
-          if ((uint32_t)p != rank)
-            P[p] = finish_poll(reinterpret_cast<uint32_t*>(mybox + a.lay.S + half_S + (size_t)p * a.lay.S_src) + sidx, w[p], err);
-      }
-#pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {  // strides G/2 .. 1 of WG_SUM
-#pragma unroll
-        for (int p = 0; p < o; ++p) P[p] += P[p + o];
-      }
-      s_inv[lane] = 1.0f / (P[0] * prev.phi_sum);
-      __syncwarp();
-      const float nrphi = -(1.0f / prev.phi_sum);
-      const float4 fb = col_lane ? reinterpret_cast<const float4*>(s_fb)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ymask_prev == 0) {  // no training link among the slot's pairs (the usual case)
-#pragma unroll
-        for (int b = 0; b < 32; ++b) {
-          if ((uint32_t)b < n) {
-            const float inv = s_inv[b];
-            g4.x += fmaf(fmaf(-xr[b].x, fb.x, e_non), inv, nrphi);
-            g4.y += fmaf(fmaf(-xr[b].y, fb.y, e_non), inv, nrphi);
-            g4.z += fmaf(fmaf(-xr[b].z, fb.z, e_non), inv, nrphi);
-            g4.w += fmaf(fmaf(-xr[b].w, fb.w, e_non), inv, nrphi);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int b = 0; b < 32; ++b) {
-          if ((uint32_t)b < n) {
-            const float inv = s_inv[b];
-            const bool yb = (ymask_prev >> b) & 1;
-            const float e = yb ? e_link : e_non, sg = yb ? 1.0f : -1.0f;
-            g4.x += fmaf(fmaf(xr[b].x * sg, fb.x, e), inv, nrphi);
-            g4.y += fmaf(fmaf(xr[b].y * sg, fb.y, e), inv, nrphi);
-            g4.z += fmaf(fmaf(xr[b].z * sg, fb.z, e), inv, nrphi);
-            g4.w += fmaf(fmaf(xr[b].w * sg, fb.w, e), inv, nrphi);
-          }
-        }
-      }
-      __syncwarp();  // s_inv is rewritten by the next slot
-    }
-    // ---- 2. slot cur: phase A from shared memory (lane = neighbor), partials to every peer ----
-    float S = 0.f;
-    uint32_t ymask = 0;
-    float4 o_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cur.valid) {
-      ymask = __ballot_sync(FULL_MASK, y_cur);
-      cp_async_wait_pending(0);
-      __syncwarp();
-      {
-        float ch[LPG];
-#pragma unroll
-        for (int t = 0; t < LPG; ++t) ch[t] = 0.f;
-        const float4* own4 = reinterpret_cast<const float4*>(s_own);
-        const float4* fb4 = reinterpret_cast<const float4*>(s_fb);
-        const float4* row4 = reinterpret_cast<const float4*>(s_rows + (size_t)(lane < n ? lane : 0) * PSTR);
-        if (ymask == 0) {
-#pragma unroll
-          for (int f = 0; f < F4; ++f) {
-            const float4 o = own4[f], fb = fb4[f], r = row4[f];
-            float& acc = ch[f % LPG];
-            acc = fmaf(o.x, fmaf(-r.x, fb.x, e_non), acc);  // fma(r, -f, e) == fma(-r, f, e) bit for bit
-            acc = fmaf(o.y, fmaf(-r.y, fb.y, e_non), acc);
-            acc = fmaf(o.z, fmaf(-r.z, fb.z, e_non), acc);
-            acc = fmaf(o.w, fmaf(-r.w, fb.w, e_non), acc);
-          }
-        } else {
-          const float e = y_cur ? e_link : e_non;
-          const float sg = y_cur ? 1.0f : -1.0f;
-#pragma unroll
-          for (int f = 0; f < F4; ++f) {
-            const float4 o = own4[f], fb = fb4[f], r = row4[f];
-            float& acc = ch[f % LPG];
-            acc = fmaf(o.x, fmaf(r.x * sg, fb.x, e), acc);
-            acc = fmaf(o.y, fmaf(r.y * sg, fb.y, e), acc);
-            acc = fmaf(o.z, fmaf(r.z * sg, fb.z, e), acc);
-            acc = fmaf(o.w, fmaf(r.w * sg, fb.w, e), acc);
-          }
-        }
-#pragma unroll
-        for (int o = LPG / 2; o > 0; o >>= 1) {
-#pragma unroll
-          for (int t = 0; t < o; ++t) ch[t] += ch[t + o];
-        }
-        S = ch[0];
-      }
-      if (lane < n && !a.loopback) {
-        const size_t sidx = cur.ridx * n + lane;
-        const uint32_t bits = partial_bits(S);
-#pragma unroll
-        for (int p = 0; p < G; ++p)
-          if ((uint32_t)p != rank)
-            st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[p] + a.lay.S + half_S + (size_t)rank * a.lay.S_src) + sidx, bits);
-      }
-      if (a.fake_lat) t_sent = clock64();
-      // ---- 3. rows of cur -> registers, the buffer is free: copies of the next slot ----
-      if (col_lane) {
-#pragma unroll
-        for (int b = 0; b < 32; ++b) xr[b] = reinterpret_cast<const float4*>(s_rows + (size_t)b * PSTR)[lane];
-        o_cur = reinterpret_cast<const float4*>(s_own)[lane];
-      }
-      __syncwarp();
-    }
-    nb_resolve(nxt, nb_nxt);
-    if (nxt.valid) issue_copies(nxt, nb_nxt);
-    // ---- 4. slot prev: Langevin step (phi.cc:266-274), partial row sum to every rank ----
-    if (prev.valid) {
-      const float* nzrow = my_nz + ((size_t)prev.half * G + (prev.ridx % G)) * KG;
-      if (col_lane) {
-        float4 z = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (!a.disable_noise) z = __ldcg(reinterpret_cast<const float4*>(nzrow) + lane);
-        float4 v;
-        v.x = phi_langevin(o_prev.x, prev.phi_sum, g4.x, z.x, half_eps, a.eps_t, a.alpha, a.Nn);
-        v.y = phi_langevin(o_prev.y, prev.phi_sum, g4.y, z.y, half_eps, a.eps_t, a.alpha, a.Nn);
-        v.z = phi_langevin(o_prev.z, prev.phi_sum, g4.z, z.z, half_eps, a.eps_t, a.alpha, a.Nn);
-        v.w = phi_langevin(o_prev.w, prev.phi_sum, g4.w, z.w, half_eps, a.eps_t, a.alpha, a.Nn);
-        reinterpret_cast<float4*>(my_vec + (size_t)prev.slot * KG)[lane] = v;
-        reinterpret_cast<float4*>(s_new)[lane] = v;
-      }
-      __syncwarp();
-      float ls = 0.f;
-      if (lane < LPG) {
-#pragma unroll 8
-        for (int i = 0; i < KPL; ++i) ls += s_new[((i >> 2) * LPG + lane) * 4 + (i & 3)];
-      }
-#pragma unroll
-      for (int o = LPG / 2; o > 0; o >>= 1) ls += __shfl_xor_sync(FULL_MASK, ls, o);
-      ls = __shfl_sync(FULL_MASK, ls, 0);
-      if (lane < (uint32_t)G) {  // this rank's partial to every rank (its own mailbox included)
-        const uint32_t p = lane;
-        st_mbox(reinterpret_cast<uint32_t*>(a.r[vr].box[a.loopback ? rank : p] + a.lay.R + half_R +
-                                            (size_t)(a.loopback ? p : rank) * a.lay.R_src) + prev.ridx,
-                partial_bits(ls));
-      }
-      __syncwarp();  // s_new is free
-    }
-    // one piece of the noise the cursor is filling; when prev closed its group-pass, the rest of it
-    noise_piece();
-    if (prev.valid && prev.last) {
-      while (noisy && nz_group < ngroups && nz_piece < (uint32_t)PIECES) noise_piece();
-      __syncwarp();
-      noise_advance();
-    }
-    // the cuckoo answers of the next slot (phi.cc:230-234)
-    bool y_nxt = false;
-    if (nxt.valid && lane < n) y_nxt = set_has(a.set, make_edge(min(nxt.node, nb_nxt), max(nxt.node, nb_nxt)));
-    // ---- rotate ----
-    prev = cur;
-    o_prev = o_cur;
-    S_prev = S;
-    ymask_prev = ymask;
-    cur = nxt;
-    nb_cur = nb_nxt;
-    y_cur = y_nxt;
-  }
-}
 
 // ---- update_pi on the column shards (phi.cc:154-197): pi[node][own columns] = phi_vec / sum ----
 struct ColsPiArgs {
@@ -2242,10 +1909,10 @@ static int cols_phi_launch_nb(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv);
 template <int KPL, int G>
 static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_nz, size_t nz_warps) {
   constexpr uint32_t KG = KPL * (32 / G);
-  uint32_t warps = 16;  // 128 registers per thread: up to 16 warps; the staged slot buffers decide (12 at K/G = 128)
+  uint32_t warps = ColsPhi2Smem::max_warps(KG);  // the staged slot buffers decide (12 at K/G = 128)
   if (const char* e = getenv("AMMSB_COLS_WARPS")) warps = (uint32_t)atoi(e);
   if (warps < 1) warps = 1;
-  if (warps > 16) warps = 16;
+  if (warps > ColsPhi2Smem::max_warps(KG)) warps = ColsPhi2Smem::max_warps(KG);
   size_t smem;
   for (;; --warps) {
     smem = ColsPhi2Smem::per_cta(KG) + (size_t)warps * ColsPhi2Smem::per_warp(KG);
@@ -2289,61 +1956,6 @@ static int cols_phi2_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_
                                                smem, c->stream));
   AMMSB_LAUNCH_CHECK();
   return 0;
-}
-
-// which update_phi kernel takes the large mini-batches of pieces <= 512 bytes: AMMSB_COLS_PHI3=1 / =0
-static bool cols_phi3_default() {
-  if (const char* e = getenv("AMMSB_COLS_PHI3")) return atoi(e) != 0;
-  return false;
-}
-
-// k_cols_phi3 (pieces <= 512 bytes, n <= 32): COLS_PHI3_WARPS warps per SM, every CTA resident
-template <int KPL, int G>
-static int cols_phi3_launch(ammsb_ctx* c, ColsPhiArgs& a, uint32_t nv, float* d_nz, size_t nz_warps) {
-  constexpr uint32_t KG = KPL * (32 / G);
-  if constexpr (KG > 128) {
-    AMMSB_REQUIRE(false, "k_cols_phi3 handles pieces of at most 512 bytes");
-    return 1;
-  } else {
-    uint32_t warps = COLS_PHI3_WARPS;
-    if (const char* e = getenv("AMMSB_COLS_WARPS")) warps = (uint32_t)atoi(e);
-    if (warps < 1) warps = 1;
-    if (warps > COLS_PHI3_WARPS) warps = COLS_PHI3_WARPS;
-    size_t smem;
-    for (;; --warps) {
-      smem = ColsPhi3Smem::per_cta(KG) + (size_t)warps * ColsPhi3Smem::per_warp(KG);
-      if (smem <= c->smem_optin || warps == 1) break;
-    }
-    AMMSB_REQUIRE(smem <= c->smem_optin, "column update_phi: shared memory request exceeds the device limit");
-    auto kern = k_cols_phi3<KPL, G>;
-    static bool attr_set[64] = {false};  // per device
-    if (!attr_set[c->device & 63]) {
-      AMMSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-      attr_set[c->device & 63] = true;
-    }
-    int occ = 0;
-    AMMSB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
-    AMMSB_REQUIRE(occ > 0, "column update_phi: kernel does not fit on an SM");
-    const uint32_t resident = (uint32_t)occ * cols_usable_sms(c);
-    const uint32_t active = a.units < a.V ? a.units : a.V;
-    const uint32_t ngroups = (active + G - 1) / G;
-    uint32_t ctas = resident / nv;
-    if (ctas * warps > ngroups) ctas = (ngroups + warps - 1) / warps;
-    if (ctas > 0) {  // an even share of groups per warp (a static schedule: the slowest warp ends the kernel)
-      const uint32_t per = (ngroups + ctas * warps - 1) / (ctas * warps);
-      const uint32_t need = (ngroups + per - 1) / per;
-      ctas = (need + warps - 1) / warps;
-    }
-    AMMSB_REQUIRE(ctas > 0, "column update_phi: no resident CTA available per rank");
-    AMMSB_REQUIRE((size_t)ctas * nv * warps <= nz_warps, "column update_phi: noise scratch too small");
-    a.ctas_per_rank = ctas;
-    a.nv = nv;
-    void* params[] = {&a, &d_nz};
-    AMMSB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(ctas * nv), dim3(warps * 32), params,
-                                                 smem, c->stream));
-    AMMSB_LAUNCH_CHECK();
-    return 0;
-  }
 }
 
 template <int KPL, int G>
@@ -2444,14 +2056,10 @@ extern "C" int ammsb_cols_update_phi(ammsb_ctx* c, ammsb_cols* const* ranks, uin
   const uint32_t kpl = p->K / 32, G = s0->G;
   const bool staged = getenv("AMMSB_COLS_STAGED") != nullptr;  // the per-neighbor stage-ring kernel (A/B measurements)
   AMMSB_REQUIRE(!(staged && a.nb_poll), "the stage-ring kernel needs the neighbor lists as an argument");
-  // pieces of at most 512 bytes and n <= 32: the register-buffered kernel (AMMSB_COLS_PHI2 keeps k_cols_phi2)
-  const bool phi3 = !staged && (p->K / G) <= 128 && a.n <= 32 && V > 2048 && !a.debug && cols_phi3_default();
 #define COLS_PHI_CASE(KPL_, G_)                                                                              \
-  if (kpl == KPL_ && G == G_) {                                                                              \
-    if (phi3) return cols_phi3_launch<KPL_, G_>(c, a, nv, ranks[0]->d_nz, ranks[0]->nz_warps);               \
+  if (kpl == KPL_ && G == G_)                                                                                \
     return staged ? cols_phi_launch<KPL_, G_>(c, a, nv)                                                      \
-                  : cols_phi2_launch<KPL_, G_>(c, a, nv, ranks[0]->d_nz, ranks[0]->nz_warps);                \
-  }
+                  : cols_phi2_launch<KPL_, G_>(c, a, nv, ranks[0]->d_nz, ranks[0]->nz_warps);
   COLS_PHI_CASE(4, 2) COLS_PHI_CASE(4, 4) COLS_PHI_CASE(4, 8)
   COLS_PHI_CASE(8, 2) COLS_PHI_CASE(8, 4) COLS_PHI_CASE(8, 8)
   COLS_PHI_CASE(16, 2) COLS_PHI_CASE(16, 4) COLS_PHI_CASE(16, 8)

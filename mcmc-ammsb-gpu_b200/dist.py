@@ -366,17 +366,25 @@ class ShardedLearner:
             self.dist.all_reduce(self.flag)
 
     def enqueue_neighbors(self, d_nodes, V, pool_index, seq, after=None):
-        """neighbor sampling of mini-batch number `seq` on the sampler stream, into neighbor
-        buffer seq & 1 -- concurrent with the kernels of the previous mini-batch, as the
-        reference prepares the next Sample on its own queue (learner.cc:216-232)"""
+        """neighbor sampling of mini-batch number `seq`, into neighbor buffer seq & 1, ahead of its
+        use -- as the reference prepares the next Sample on its own queue (learner.cc:216-232).
+        Row layouts: on the sampler stream, concurrent with the kernels of the previous mini-batch.
+        Column layout: the column kernels are persistent cooperative grids that wait for their
+        peers, and a concurrent kernel either starves on the SMs they leave free or holds up their
+        launch (measured on 8 GPUs: 0.5 ms on the side stream for 40 us of work); the sampler of the
+        NEXT mini-batch is therefore held back until update_phi of the current one has finished and
+        then runs beside update_pi -- an ordinary, short kernel -- before update_beta starts."""
         if self.ns_seq >= seq:
             return
+        if self.cols is not None and seq > self.step_count + 1:
+            self.pending_ns = (d_nodes, V, pool_index, seq, after)  # issued by device_step, after update_phi
+            self.ns_seq = seq
+            return
+        self._issue_neighbors(d_nodes, V, pool_index, seq, after, self.stream if self.cols is not None else self.ns_stream)
+        self.ns_seq = seq
+
+    def _issue_neighbors(self, d_nodes, V, pool_index, seq, after, ns_stream):
         b = seq & 1
-        # column shards: the sampler runs on the COMPUTE stream, between the kernels of the previous
-        # mini-batch -- the column kernels are persistent cooperative grids that wait for their peers,
-        # and a concurrent kernel on a side stream either starves on the SMs they leave free or holds
-        # up their launch (measured on 8 GPUs: 0.5 ms on the side stream for 40 us of work)
-        ns_stream = self.stream if self.cols is not None else self.ns_stream
         ns_stream.wait_event(self.ev_phi[b])  # update_phi of mini-batch seq-2 is done with the buffer
         if after is not None:
             ns_stream.wait_event(after)  # the nodes are on this GPU
@@ -387,7 +395,8 @@ class ShardedLearner:
         if self.cols is not None:
             # each rank draws the lists of the sampler states it owns and delivers them to every
             # rank's mailbox (third seq % 3); update_phi of step seq reads them there
-            self.A.cols_neighbor_sample(self.ctx, [self.cols], d_nodes, V, 32, seq, [self.npools[pool_index]])
+            ctx = self.ctx if ns_stream is self.stream else self.ctx_ns
+            self.A.cols_neighbor_sample(ctx, [self.cols], d_nodes, V, 32, seq, [self.npools[pool_index]])
         else:
             self.ctx_ns.neighbor_sample(self.npools[pool_index], d_nodes, V, self.N, self.n, 32, tbuf(self.d_nbs[b]))
         if ns_ev is not None:
@@ -395,7 +404,6 @@ class ShardedLearner:
             e1.record(ns_stream)
             ns_ev.append((V, e0, e1))
         self.ev_ns[b].record(ns_stream)
-        self.ns_seq = seq
 
     def device_step(self, d_nodes, d_edges, V, E_mb, weight, pool_index, phi_events=None, seq=None):
         """one iteration on device-resident mini-batch buffers (pyammsb-style buffers)"""
@@ -417,7 +425,13 @@ class ShardedLearner:
             if phi_events is not None:
                 phi_events[1].record(self.stream)
             self.ev_phi[seq & 1].record(self.stream)
+            pend, self.pending_ns = getattr(self, "pending_ns", None), None
+            if pend is not None:  # the next mini-batch's lists, beside update_pi
+                self.ns_stream.wait_event(self.ev_phi[seq & 1])
+                self._issue_neighbors(*pend, self.ns_stream)
             A.cols_update_pi(ctx, [self.cols], d_nodes, V, self.step_count)
+            if pend is not None:
+                self.stream.wait_event(self.ev_ns[pend[3] & 1])  # no ordinary kernel beside a cooperative grid
             if phi_events is not None and len(phi_events) > 2:
                 phi_events[2].record(self.stream)
             A.cols_update_beta(ctx, [self.cols], p, self.train, d_edges, E_mb, weight, self.step_count, [self.bpool])
@@ -670,7 +684,14 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
     ctx = lrn.ctx
 
     # ---- value leg: pre-sampled mini-batches resident in HBM ----
-    total = args.warmup + args.steps
+    # AMMSB_BENCH_VARIANTS="name:ENV=VAL,ENV2=VAL;name2:..." (development): after the contract run, the
+    # same number of steps again under each variant's environment, in the same process (the kernel
+    # switches are read at every launch) -- one set-up for several A/B measurements
+    variants = []
+    for item in filter(None, os.environ.get("AMMSB_BENCH_VARIANTS", "").split(";")):
+        name, _, kv = item.partition(":")
+        variants.append((name, dict(x.split("=", 1) for x in kv.split(",") if x)))
+    total = args.warmup + args.steps * (1 + len(variants))
     t0 = time.time()
     if graph is not None:
         # (weight, E_mb, V) per mini-batch, drawn by the device sampler into one resident buffer
@@ -728,12 +749,13 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
     dist.barrier()
     torch.cuda.synchronize()
     launches = A.launch_count() - launches0
+    main_ns_timing = list(getattr(lrn, "ns_timing", None) or [])
     t = torch.tensor([e_start.elapsed_time(e_stop), sum(e[0].elapsed_time(e[1]) for e in evs)],
                      dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
     dev_ms, phi_ms = float(t[0]), float(t[1])
     clk = clocks.stop() if rank == 0 else None
-    timed = batches[args.warmup:]
+    timed = batches[args.warmup:args.warmup + args.steps]
     edges_timed = int(sum(b[1] for b in timed))
     value = edges_timed / (dev_ms * 1e-3)
     Vs = [b[2] for b in timed]
@@ -779,24 +801,62 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
                     "share_of_step": round(phi_ms / dev_ms, 4),
                     "nvlink_outbound_GB_per_gpu_per_step": round(out_bytes / args.steps / 1e9, 4)}
     roofline["store"] = mode
-    stages_in_run = None
-    if nev == 4:
+    timed = timed[:args.steps]
+    Vs = Vs[:args.steps]
+
+    def stage_means(evs, Vs, ns_timing):
         # mean ms per stage over the timed steps of this rank, non-link and link mini-batches apart;
         # "gap" = from the end of update_beta to the start of the next update_phi on the stream
-        stages_in_run = {}
+        out = {}
         for kind, sel in (("non_link", lambda V: V > 1024), ("link", lambda V: V <= 1024)):
-            ks = [k for k in range(args.steps) if sel(Vs[k])]
+            ks = [k for k in range(len(evs)) if sel(Vs[k])]
             if not ks:
                 continue
             d = {"steps": len(ks),
                  "update_phi": float(np.mean([evs[k][0].elapsed_time(evs[k][1]) for k in ks])),
                  "update_pi": float(np.mean([evs[k][1].elapsed_time(evs[k][2]) for k in ks])),
                  "update_beta": float(np.mean([evs[k][2].elapsed_time(evs[k][3]) for k in ks]))}
-            ns = [a.elapsed_time(b) for V, a, b in lrn.ns_timing if sel(V)]
+            ns = [a.elapsed_time(b) for V, a, b in ns_timing if sel(V)]
             d["neighbor_sample"] = float(np.mean(ns)) if ns else 0.0
-            gaps = [evs[k][3].elapsed_time(evs[k + 1][0]) for k in ks if k + 1 < args.steps]
+            gaps = [evs[k][3].elapsed_time(evs[k + 1][0]) for k in ks if k + 1 < len(evs)]
             d["gap_to_next"] = float(np.mean(gaps)) if gaps else 0.0
-            stages_in_run[kind] = {a: round(b, 4) if isinstance(b, float) else b for a, b in d.items()}
+            out[kind] = {a: round(b, 4) if isinstance(b, float) else b for a, b in d.items()}
+        return out
+
+    variant_results = {}
+    for vi, (vname, venv) in enumerate(variants):
+        saved = {k: os.environ.get(k) for k in venv}
+        os.environ.update(venv)
+        first = args.warmup + args.steps * (1 + vi)
+        v_evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(nev)) for _ in range(args.steps)]
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        if nev == 4:
+            lrn.ns_timing = []
+        v0.record(stream)
+        for k in range(args.steps):
+            step(first + k, v_evs[k])
+        v1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        tv = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        vb = batches[first:first + args.steps]
+        res = {"env": venv, "ms_per_step": float(tv[0]) / args.steps,
+               "value": int(sum(b[1] for b in vb)) / (float(tv[0]) * 1e-3)}
+        if nev == 4:
+            res["stages_in_run_ms"] = stage_means(v_evs, [b[2] for b in vb], lrn.ns_timing)
+        variant_results[vname] = res
+        for k, v in saved.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+    stages_in_run = None
+    if nev == 4:
+        stages_in_run = stage_means(evs, Vs, main_ns_timing)
 
     # ---- perplexity (sharded) ----
     torch.cuda.synchronize()
@@ -844,6 +904,8 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
         }
         if stages_in_run is not None:
             line["stages_in_run_ms"] = stages_in_run
+        if variant_results:
+            line["variants"] = variant_results
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
