@@ -87,8 +87,13 @@ def sharded_plan(args, w, world):
     """layout decisions of a multi-GPU run -- a function of the arguments only, so that both
     arms describe the same run"""
     mode = args.store
-    if mode == "auto":  # replicate while a full copy (plus mini-batch buffers) is a small part of 180 GB
-        mode = "replicated" if 4.0 * w["N"] * w["K"] <= 48e9 else "partitioned"
+    if mode == "auto":
+        # column shards when a GPU's piece of a row is at most 512 bytes (the shape csrc/cols.cu's
+        # update_phi keeps 12+ slots per SM in flight at: 8 GPUs at K = 1024, 4 or 8 at K = 512 --
+        # measured 120 M edges/s against 97 M for the replicated layout at the DBLP shape on 8 GPUs);
+        # otherwise a full copy per GPU while it is a small part of 180 GB, else node partitions
+        cols_ok = world in (2, 4, 8) and w["K"] in (128, 256, 512, 1024) and w["K"] // world <= 128 and w["n"] <= 32
+        mode = "columns" if cols_ok else ("replicated" if 4.0 * w["N"] * w["K"] <= 48e9 else "partitioned")
     gmode = args.graph
     if gmode == "auto":
         gmode = "device" if w["E"] > 100e6 else "host"

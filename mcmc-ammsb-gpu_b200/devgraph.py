@@ -83,3 +83,60 @@ class DeviceGraph:
             b.free()
         self.train.free()
         self.heldout.free()
+
+
+def host_order_csr(N, training):
+    """mcmc::Graph (data.cc:12-25) as arrays: for every training edge (u, v) in list order, v joins
+    u's neighbors and u joins v's -- the order sampleNodeLink (sample.cc:253-272) walks them in"""
+    u = (training >> np.uint64(32)).astype(np.int64)
+    v = (training & np.uint64(0xffffffff)).astype(np.int64)
+    ends = np.stack([u, v], axis=1).ravel()
+    other = np.stack([v, u], axis=1).ravel()
+    order = np.argsort(ends, kind="stable")  # per vertex, in order of appearance
+    deg = np.bincount(ends, minlength=N)
+    off = np.zeros(N + 1, np.uint64)
+    off[1:] = np.cumsum(deg)
+    return off, other[order].astype(np.uint32), deg.astype(np.uint32)
+
+
+class UploadedGraph:
+    """A HOST-built graph (a pymcmc.Config after set_graph: the reference's own split, cuckoo
+    tables and Graph) put on the device once, with the interface of DeviceGraph.  The mini-batches
+    are then drawn on the GPU by the Node strategy in the reference's order (csrc/graph.cu +
+    csrc/orderset.cu): the same edges and nodes, element for element, as the host strategy
+    (sample.cc:253-302 + learner.cc:162-173) draws from the same seed -- the host only draws the
+    coin and the vertex.  This takes the host sampler out of the iteration loop."""
+
+    def __init__(self, ctx, cfg, log=lambda *a: None):
+        import time
+        t0 = time.time()
+        p = cfg.params()
+        self.ctx, self.N, self.E = ctx, int(p.N), int(p.E)
+        tr, he = cfg.edges()
+        self.num_training, self.num_heldout_links = len(tr), len(he) // 2
+        self.train = A.DevSet(ctx, *cfg.set_table(0))
+        self.heldout = A.DevSet(ctx, *cfg.set_table(1))
+        self.H = len(he)
+        self.d_heldout_pairs = ctx.from_host(he) if self.H else ctx.buf(np.uint64, 1)
+        off, adj, deg = host_order_csr(self.N, tr)
+        self.d_offsets, self.d_adj, self.degree = ctx.from_host(off), ctx.from_host(adj), deg
+        self.max_fan_out = int(deg.max()) if self.N else 0
+        assert self.max_fan_out == cfg.max_fan_out()
+        self._max_nodes, self._max_edges = cfg.max_nodes(), cfg.max_edges()
+        log("host graph on the device (sets, held-out pairs, adjacency in Graph order): %.1fs" % (time.time() - t0))
+
+    def max_nodes(self, m):
+        return max(2 * m, 1 + self.max_fan_out, self._max_nodes)
+
+    def max_edges(self, m):
+        return max(m, self.max_fan_out, self._max_edges)
+
+    def sampler(self, m, ctx=None):
+        return A.DeviceSampler(ctx or self.ctx, self.N, self.E, m, self.train, self.heldout, self.d_offsets,
+                               self.d_adj, self.degree, exact_order=True)
+
+    def free(self):
+        for b in (self.d_heldout_pairs, self.d_offsets, self.d_adj):
+            b.free()
+        self.train.free()
+        self.heldout.free()

@@ -298,6 +298,13 @@ class ShardedLearner:
             self.ev_mb_ready = [torch.cuda.Event() for _ in range(2)]
             self.mb_drawn = 0
         if prefetch:
+            # sampler threads per rank: the host cores divided over the ranks of the box, one left
+            # for the rank's launch thread (2 .. 6)
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except Exception:
+                cores = os.cpu_count() or 2
+            self.LOCAL = int(os.environ.get("AMMSB_SAMPLER_THREADS", max(2, min(6, cores // max(world, 1) - 1))))
             self.local_seeds = [C.c_uint(seed + 7919 * (rank * self.LOCAL + i) + 104729) for i in range(self.LOCAL)]
             self.q = [queue.Queue(maxsize=2) for _ in range(self.LOCAL)]
             self.threads = [threading.Thread(target=self._producer, args=(i,), daemon=True)
@@ -506,6 +513,7 @@ class ShardedLearner:
         if self.mb_drawn <= t:
             self.mb_meta[b] = self.draw_device_minibatch()
         weight, E_mb, V = self.mb_meta[b]
+        self.h2d_bytes += 16  # the coin, the vertex and the rand_r state travel as kernel arguments
         self.stream.wait_event(self.ev_mb_ready[b])
         d_nodes, d_edges = tbuf(self.mb_nodes[b]), tbuf(self.mb_edges[b])
         self.enqueue_neighbors(d_nodes, V, t % self.STREAMS, t + 1, after=self.ev_mb_ready[b])
@@ -868,7 +876,20 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
     # ---- e2e leg: host mini-batches through the sharded driver ----
     e2e = None
     if not args.no_e2e:
-        l2 = make_learner(True)
+        if graph is None and os.environ.get("AMMSB_E2E_DEVICE_SAMPLER"):
+            # the host-built graph is put on the device once; the Node mini-batches are then drawn
+            # there in the reference's order (the host draws the coin and the vertex)
+            import devgraph
+            up = devgraph.UploadedGraph(A.Ctx(local_rank), cfg, log=log)
+            l2 = ShardedLearner(None, rank, world, local_rank, store_mode=mode, collectives=coll, graph=up,
+                                shape=(K, n, m))
+            e2e_api = ("dist.ShardedLearner.device_graph_step() over the HOST-built graph (the reference's split, "
+                       "cuckoo tables and Graph, uploaded once): coin and vertex drawn on the host (rand_r), the Node "
+                       "mini-batch on every GPU by the device sampler in the reference's order (bit-identical to the "
+                       "host strategy), one step ahead (D2H of its 16-byte header), sharded kernels, D2H of beta")
+        else:
+            l2 = make_learner(True)
+            e2e_api = None
         l2.run(args.warmup)
         dist.barrier()
         torch.cuda.synchronize()
@@ -885,9 +906,10 @@ def bench_sharded(args, w, rank, world, local_rank, log, METRIC, UNIT, config, p
         e2e = {"value": (l2.edges_processed - e0) / dt, "unit": UNIT,
                "h2d_bytes_per_step": float(hb[0]) / args.steps, "d2h_bytes_per_step": (8 * K + 32) * world,
                "iterations_per_s": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
-               "api": ("dist.ShardedLearner.host_step(): mini-batch t drawn on rank t % N (2 sampler threads per "
+               "api": e2e_api if e2e_api is not None else
+                      ("dist.ShardedLearner.host_step(): mini-batch t drawn on rank t % N (2 sampler threads per "
                        "rank), H2D from pinned memory there, NCCL broadcast one step ahead, sharded kernels + "
-                       "all-reduces, D2H of beta") if graph is None else
+                       "all-reduces, D2H of beta").replace("2 sampler threads", "%d sampler threads" % l2.LOCAL) if graph is None else
                       ("dist.ShardedLearner.device_graph_step(): coin and vertex drawn on the host (rand_r), the "
                        "mini-batch on every GPU by the device sampler one step ahead (D2H of its 16-byte header), "
                        "sharded kernels + all-reduces, D2H of beta; the graph, the cuckoo sets and the adjacency "

@@ -60,6 +60,7 @@ int mcmc_config_set(void* vc, const char* key, double v) {
   else if (k == "calc_train_ppx") c->calc_train_ppx = v != 0;
   else if (k == "training_ppx_ratio") c->training_ppx_ratio = v;
   else if (k == "stage_timers") c->stage_timers = v != 0;
+  else if (k == "device_sampler") c->device_sampler = v != 0;
   else if (k == "N") c->N = static_cast<uint64_t>(v);
   else if (k == "E") c->E = static_cast<uint64_t>(v);
   else if (k == "ppx_wg_size") c->ppx_wg_size = static_cast<uint32_t>(v);

@@ -93,6 +93,7 @@ int main(int argc, char** argv) {
   Take(args, "--train-ppx", &cfg.calc_train_ppx);
   Take(args, "--train-ppx-ratio", &cfg.training_ppx_ratio);
   Take(args, "--stage-timers", &cfg.stage_timers);
+  Take(args, "--device-sampler", &cfg.device_sampler);
   Take(args, "--dump-data", &dumpDataset);
   Take(args, "--dump-file", &dumpFile);
   Take(args, "--load-data", &loadDataset);

@@ -71,6 +71,9 @@ struct Config {
   // B200 additions
   bool phi_strict = false;     // run the IEEE reference-association kernel instead of the fast one
   bool stage_timers = false;   // per-kernel timing with a sync after every stage (reference behaviour)
+  // draw the Node / NodeLink / NodeNonLink mini-batches on the device (same mini-batches, element
+  // for element; takes the host strategy and the H2D copies out of the iteration)
+  bool device_sampler = false;
 };
 
 std::ostream& operator<<(std::ostream& out, const Config& cfg);

@@ -87,9 +87,13 @@ Learner::Learner(const Config& cfg, clcuda::Queue queue)
                                                        compileFlags_));
   }
   for (auto& ev : iterDone_) AmmsbCheck(ammsb_event_create(queue_(), &ev));
+  std::shared_ptr<DeviceStrategyData> on_device;
+  if (cfg_.device_sampler)
+    on_device.reset(new DeviceStrategyData(cfg_, queue_, trainingSet_->Get(), heldoutSet_->Get()));
   for (auto& sample : samples_) {
     sample.reset(new Sample(cfg_, queue_));  // seed = rand(), as in the reference (sample.cc:132)
-    sample->Start(sampler_, &stats_);
+    if (on_device) sample->StartOnDevice(cfg_.strategy, on_device, &stats_);
+    else sample->Start(sampler_, &stats_);
   }
   // phi lives in a Buffer of its own in the reference; the store adopts that memory
   AmmsbCheck(ammsb_store_bind_phi(pi_->Get(), phi_.data()));

@@ -340,6 +340,84 @@ Sample::~Sample() {
   if (a_.joinable()) a_.join();
   if (b_.joinable()) b_.join();
   if (c_.joinable()) c_.join();
+  if (dev_sampler_ != nullptr) ammsb_sampler_destroy(dev_sampler_);
+  if (dev_order_ != nullptr) ammsb_orderset_destroy(dev_order_);
+}
+
+namespace {
+// mcmc::Graph (data.cc:12-25) flattened: offsets[u] .. offsets[u + 1] index u's neighbors in the
+// order NeighborsOf(u) lists them -- the order sampleNodeLink inserts the edges in
+std::vector<uint64_t> GraphOffsets(const Config& cfg) {
+  std::vector<uint64_t> off(cfg.N + 1, 0);
+  for (uint64_t u = 0; u < cfg.N; ++u) off[u + 1] = off[u] + cfg.trainingGraph->NeighborsOf(static_cast<Vertex>(u)).size();
+  return off;
+}
+std::vector<Vertex> GraphAdjacency(const Config& cfg, const std::vector<uint64_t>& off) {
+  std::vector<Vertex> adj(std::max<uint64_t>(off.back(), 1));
+  for (uint64_t u = 0; u < cfg.N; ++u) {
+    const std::vector<Vertex>& nb = cfg.trainingGraph->NeighborsOf(static_cast<Vertex>(u));
+    std::copy(nb.begin(), nb.end(), adj.begin() + off[u]);
+  }
+  return adj;
+}
+}  // namespace
+
+DeviceStrategyData::DeviceStrategyData(const Config& cfg, clcuda::Queue queue, ammsb_set* tr, ammsb_set* he)
+    : offsets(queue.GetContext(), cfg.N + 1),
+      adjacency(queue.GetContext(), std::max<uint64_t>(2 * cfg.training_edges.size(), 1)),
+      degree(cfg.N),
+      training(tr),
+      heldout(he) {
+  if (!cfg.trainingGraph) throw BackendError("the device mini-batch strategies need Config::trainingGraph");
+  const std::vector<uint64_t> off = GraphOffsets(cfg);
+  const std::vector<Vertex> adj = GraphAdjacency(cfg, off);
+  for (uint64_t u = 0; u < cfg.N; ++u) degree[u] = static_cast<uint32_t>(off[u + 1] - off[u]);
+  offsets.Write(queue, off.size(), off.data());
+  adjacency.Write(queue, off.back(), adj.data());
+  queue.Finish();
+}
+
+void Sample::StartOnDevice(SampleStrategy which, std::shared_ptr<DeviceStrategyData> data, SamplerStats* stats) {
+  if (which != Node && which != NodeLink && which != NodeNonLink)
+    throw BackendError("device_sampler: only the Node strategies are drawn on the device (the breadth-first "
+                       "strategies are queue-driven and stay on the host)");
+  dev_ = data;
+  dev_strategy_ = which;
+  stats_ = stats;
+  AmmsbCheck(ammsb_sampler_create(queue(), cfg_.N, static_cast<uint32_t>(cfg_.mini_batch_size), &dev_sampler_));
+  AmmsbCheck(ammsb_orderset_create(queue(), static_cast<uint32_t>(2 * MaxMiniBatchEdges(cfg_) + 2), &dev_order_));
+  a_ = std::thread(&Sample::StageA, this);
+  c_ = std::thread(&Sample::StageC, this);
+}
+
+Float Sample::DrawOnDevice(SampleSlot* slot) {
+  bool link = dev_strategy_ == NodeLink;
+  if (dev_strategy_ == Node) link = (rand_r(&seed) % 2) != 0;  // sampleNode, sample.cc:295-302
+  uint32_t num_edges = 0, num_nodes = 0;
+  Float weight;
+  if (link) {  // sampleNodeLink: vertices until one has training neighbors (sample.cc:253-272)
+    Vertex u;
+    do {
+      u = static_cast<Vertex>(rand_r(&seed) % cfg_.N);
+    } while (dev_->degree[u] == 0);
+    num_edges = dev_->degree[u];
+    AmmsbCheck(ammsb_minibatch_link(queue(), u, num_edges, dev_->offsets.data(), dev_->adjacency.data(),
+                                    slot->dev_edges.data(), slot->dev_nodes.data()));
+    weight = static_cast<Float>(cfg_.N);
+  } else {  // sampleNodeNonLink (sample.cc:274-293)
+    const Vertex u = static_cast<Vertex>(rand_r(&seed) % cfg_.N);
+    AmmsbCheck(ammsb_minibatch_nonlink(dev_sampler_, queue(), u, &seed, dev_->training, dev_->heldout,
+                                       slot->dev_edges.data(), slot->dev_nodes.data(), &num_edges, &num_nodes));
+    weight = (2 * cfg_.E) / static_cast<Float>(cfg_.mini_batch_size);
+  }
+  AmmsbCheck(ammsb_minibatch_finish(dev_order_, queue(), slot->dev_edges.data(), num_edges, slot->dev_nodes.data(),
+                                    &num_nodes));
+  slot->edges.resize(num_edges);
+  slot->nodes_vec.resize(num_nodes);
+  slot->dev_edges.Read(queue, num_edges, slot->edges.data());
+  slot->dev_nodes.Read(queue, num_nodes, slot->nodes_vec.data());
+  if (slot->nodes_vec.empty()) throw BackendError("mini-batch size = 0!");
+  return weight;
 }
 
 void Sample::Start(Strategy strategy, SamplerStats* stats) {
@@ -369,15 +447,24 @@ void Sample::StageA() {
     std::exception_ptr err;
     const uint64_t t0 = NowNs();
     try {
-      slot.edges.clear();
-      slot.weight = strategy_(cfg_, &slot.edges, &seed);
+      if (dev_) {
+        slot.weight = DrawOnDevice(&slot);
+      } else {
+        slot.edges.clear();
+        slot.weight = strategy_(cfg_, &slot.edges, &seed);
+      }
     } catch (...) {
       err = std::current_exception();
     }
     stats_->strategy += NowNs() - t0;
     lock.lock();
     a_busy_ = false;
-    if (err) error_ = err; else ++drawn_;
+    if (err) {
+      error_ = err;
+    } else {
+      ++drawn_;
+      if (dev_) ++extracted_;  // the device strategy delivers the nodes as well: no stage B
+    }
     cv_.notify_all();
   }
 }
@@ -419,14 +506,16 @@ void Sample::StageC() {
       if (slot.edges.size() > slot.dev_edges.GetSize() / sizeof(Edge) ||
           slot.nodes_vec.size() > slot.dev_nodes.GetSize() / sizeof(Vertex))
         throw BackendError("mini-batch exceeds the device buffers");
-      slot.dev_edges.Write(queue, slot.edges.size(), slot.edges.data());
-      slot.dev_nodes.Write(queue, slot.nodes_vec.size(), slot.nodes_vec.data());
+      if (!dev_) {  // a device-drawn mini-batch is in the slot's device buffers already
+        slot.dev_edges.Write(queue, slot.edges.size(), slot.edges.data());
+        slot.dev_nodes.Write(queue, slot.nodes_vec.size(), slot.nodes_vec.data());
+      }
       const uint64_t t2 = NowNs();
       neighbor_sampler(static_cast<uint32_t>(slot.nodes_vec.size()), &slot.dev_nodes, &slot.neighbors);
       const uint64_t t3 = NowNs();
       stats_->copy += t2 - t1;
       stats_->neighbors += t3 - t2;
-      stats_->h2d_bytes += slot.edges.size() * sizeof(Edge) + slot.nodes_vec.size() * sizeof(Vertex);
+      stats_->h2d_bytes += dev_ ? 16 : slot.edges.size() * sizeof(Edge) + slot.nodes_vec.size() * sizeof(Vertex);
     } catch (...) {
       err = std::current_exception();
     }

@@ -90,6 +90,18 @@ struct SampleSlot {
   SampleSlot(const Config& cfg, const clcuda::Context& ctx);
 };
 
+// The graph side of the device mini-batch strategies (csrc/graph.cu + csrc/orderset.cu): the
+// training adjacency in mcmc::Graph's order (data.cc:12-25) and the vertex degrees, uploaded once
+// and shared by the sampler streams; the cuckoo sets are the Learner's device sets.
+struct DeviceStrategyData {
+  DeviceStrategyData(const Config& cfg, clcuda::Queue queue, ammsb_set* training, ammsb_set* heldout);
+  clcuda::Buffer<uint64_t> offsets;  // [N + 1]
+  clcuda::Buffer<Vertex> adjacency;  // [2 |training|]
+  std::vector<uint32_t> degree;
+  ammsb_set* training;
+  ammsb_set* heldout;
+};
+
 // One sampler stream (the reference's struct Sample, sample.h:51-92: its own seed, queue and
 // NeighborSampler with its own RNG pool).  The Learner alternates between two of them.
 //
@@ -117,6 +129,13 @@ struct Sample {
   Sample(const Config& cfg, clcuda::Queue queue);
   ~Sample();
   void Start(Strategy strategy, SamplerStats* stats);
+  // Config::device_sampler: stage A draws the mini-batch ON THE DEVICE -- the host draws the coin
+  // and the vertex with rand_r exactly as sampleNode / sampleNodeLink / sampleNodeNonLink do
+  // (sample.cc:253-302), the device examines the candidate stream, puts edges and nodes in the
+  // reference's std::unordered_set order and leaves the seed where the host strategy leaves it:
+  // the mini-batch is the host strategy's, element for element.  Stages B and the copies of stage
+  // C fall away; the host vectors are read back (Serialize() stores them).
+  void StartOnDevice(SampleStrategy which, std::shared_ptr<DeviceStrategyData> data, SamplerStats* stats);
   // let the stream draw until `more` mini-batches beyond the consumed ones exist
   void Allow(uint64_t more);
   // the oldest drawn-but-unconsumed mini-batch, fully on the device (blocks; rethrows a failure);
@@ -134,7 +153,12 @@ struct Sample {
   void StageA();
   void StageB();
   void StageC();
+  Float DrawOnDevice(SampleSlot* slot);
   const Config& cfg_;
+  std::shared_ptr<DeviceStrategyData> dev_;
+  SampleStrategy dev_strategy_ = Node;
+  ammsb_sampler* dev_sampler_ = nullptr;
+  ammsb_orderset* dev_order_ = nullptr;
   Strategy strategy_ = nullptr;
   SamplerStats* stats_ = nullptr;
   std::mutex mu_;

@@ -263,3 +263,35 @@ def test_learner_grqc_shape_matches_oracle(ctx, orc):
     assert abs(got - want) <= PPX_TOL * want
     lrn.close()
     cfg.close()
+
+
+@pytest.mark.parametrize("strategy", ["Node", "NodeLink", "NodeNonLink"])
+def test_learner_device_sampler_is_the_host_strategy(ctx, strategy):
+    """Config::device_sampler: mcmc::Learner::Run with the mini-batches drawn on the device
+    (csrc/graph.cu + csrc/orderset.cu) consumes the host strategy's mini-batches element for
+    element (sample.cc:253-302 + learner.cc:162-173) -- edges, nodes, weight, sampled neighbors --
+    and therefore reaches the same state bit for bit"""
+    N, K, n = 3000, 64, 16
+    runs = []
+    for dev in (0, 1):
+        cfg = make_cfg(N=N, E=40000, K=K, m=256, n=n, seed=6, strategy=strategy, device_sampler=dev)
+        lrn = pymcmc.Learner(cfg, 0)
+        mbs = []
+        for _ in range(10):
+            mbs.append(lrn.peek(n))
+            lrn.run(1)
+        lrn.run(7)  # several mini-batches in flight
+        runs.append((mbs, lrn.read(N, K), lrn.heldout_perplexity(), lrn.edges_processed()))
+        lrn.close()
+        cfg.close()
+    (mb_h, st_h, ppx_h, ne_h), (mb_d, st_d, ppx_d, ne_d) = runs
+    sizes = set()
+    for (e_h, v_h, nb_h, w_h), (e_d, v_d, nb_d, w_d) in zip(mb_h, mb_d):
+        assert np.array_equal(e_h, e_d) and np.array_equal(v_h, v_d), "device mini-batch differs from the host strategy's"
+        assert np.array_equal(nb_h, nb_d) and w_h == w_d
+        sizes.add(len(e_h) == 256)
+    if strategy == "Node":
+        assert sizes == {True, False}  # link and non-link mini-batches occurred
+    for a, b in zip(st_h, st_d):
+        assert np.array_equal(a, b)
+    assert ppx_h == ppx_d and ne_h == ne_d

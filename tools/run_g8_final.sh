@@ -2,7 +2,7 @@
 # 8-GPU runs of the column-sharded layout with per-stage events and the k_cols_phi3 A/B in the same process
 run() { # name, args
   name=$1; shift
-  AMMSB_STAGE_EVENTS=1 AMMSB_BENCH_VARIANTS="phi3:AMMSB_COLS_PHI3=1" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 200)) bench.py --gpus 8 --steps 100 --warmup 10 "$@" 2>gpurun_out/r2b_g8_$name.err | tail -1 > gpurun_out/r2b_g8_$name.json
+  AMMSB_STAGE_EVENTS=1 AMMSB_BENCH_VARIANTS="${VARIANTS:-}" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 200)) bench.py --gpus 8 --steps 100 --warmup 10 "$@" 2>gpurun_out/r2b_g8_$name.err | tail -1 > gpurun_out/r2b_g8_$name.json
   echo "== $name rc=$?"; grep -E "parity|Error|error" gpurun_out/r2b_g8_$name.err | tail -3
   python - <<PY
 import json
@@ -13,5 +13,5 @@ except Exception as e:
     print('no json', e)
 PY
 }
-run dblp_cols --store columns --no-e2e
+run dblp_cols --store columns
 run fr_cols --store columns --shape com-Friendster --graph device
