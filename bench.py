@@ -66,6 +66,8 @@ def parse_args():
                          "(the reference's path) or in HBM (csrc/graph.cu; auto: device above 100 M edges)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-device-sampler", action="store_true",
+                    help="N=1: also time mcmc::Learner::Run with Config::device_sampler (reported as e2e_device_sampler)")
     return ap.parse_args()
 
 
@@ -577,9 +579,8 @@ def run_b200(args, w):
     ctx.sync()
 
     # ---------------- e2e leg: mcmc::Learner::Run with host mini-batches ----------------------
-    e2e = None
-    if not args.no_e2e:
-        lrn = pymcmc.Learner(cfg, local_rank)
+    def learner_run(c, what):
+        lrn = pymcmc.Learner(c, local_rank)
         mirror = torch.empty(2 * K, dtype=torch.float32).pin_memory()
         lrn.mirror_beta(mirror.data_ptr())  # every iteration ends with a D2H copy of beta[2K]
         lrn.run(args.warmup)
@@ -596,13 +597,26 @@ def run_b200(args, w):
         t1 = time.perf_counter()
         ppx = lrn.heldout_perplexity()
         ppx_s = time.perf_counter() - t1
-        e2e = {"value": e_edges / dt, "unit": UNIT, "h2d_bytes_per_step": (lrn.h2d_bytes() - b0) / args.steps,
+        out = {"value": e_edges / dt, "unit": UNIT, "h2d_bytes_per_step": (lrn.h2d_bytes() - b0) / args.steps,
                "d2h_bytes_per_step": 8 * K, "iterations_per_s": args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
-               "api": "mcmc::Learner::Run(steps): per iteration the host mini-batch sampler (sample.cc strategies; "
-                      "two sampler streams, each a 3-stage thread pipeline over a ring of 6 mini-batches), H2D of "
-                      "edges/nodes, 5 kernels (neighbor sampling, update_phi, update_pi, beta partials, beta reduction + theta step), D2H of beta[2K] into pinned host memory; 2 iterations in flight",
-               "heldout_perplexity": ppx, "perplexity_eval_s": ppx_s}
+               "api": what, "heldout_perplexity": ppx, "perplexity_eval_s": ppx_s}
         lrn.close()
+        return out
+
+    e2e = e2e_dev = None
+    if not args.no_e2e:
+        e2e = learner_run(cfg, "mcmc::Learner::Run(steps): per iteration the host mini-batch sampler (sample.cc "
+                               "strategies; two sampler streams, each a 3-stage thread pipeline over a ring of 6 "
+                               "mini-batches), H2D of edges/nodes, 5 kernels (neighbor sampling, update_phi, update_pi, "
+                               "beta partials, beta reduction + theta step), D2H of beta[2K] into pinned host memory; "
+                               "2 iterations in flight")
+        if args.e2e_device_sampler:
+            cfg.set(device_sampler=1)
+            e2e_dev = learner_run(cfg, "mcmc::Learner::Run(steps) with Config::device_sampler: the host draws the coin "
+                                       "and the vertex, the device the mini-batch in the reference's order (the same "
+                                       "mini-batches element for element), D2H of edges/nodes for the checkpoint "
+                                       "state, neighbor sampling, 4 kernels, D2H of beta[2K]")
+            cfg.set(device_sampler=0)
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -617,6 +631,7 @@ def run_b200(args, w):
         "iterations_per_s": args.steps / (dev_ms * 1e-3),
         "perplexity_eval_s": stages["perplexity"]["ms"] * 1e-3,
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "e2e_device_sampler": e2e_dev,
         "stages": stages,
     }
     print(json.dumps(line), flush=True)
