@@ -376,6 +376,11 @@ int ammsb_cols_update_beta(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv
 int ammsb_cols_perplexity(ammsb_ctx* ctx, ammsb_cols* const* ranks, uint32_t nv, const ammsb_params* p,
                           ammsb_set* heldout, const uint64_t* d_edges, uint32_t H, uint32_t call_count,
                           double* h_sums /* [nv][4] or NULL */, double* h_avg /* [nv] or NULL */);
+/* results of a rank's last ammsb_cols_perplexity launch (waits for the stream): for callers that
+ * drive several devices from one thread and launch every device's kernel (NULL outputs) before
+ * they wait for any of them -- the kernels of the ranks wait for each other */
+int ammsb_cols_perplexity_result(ammsb_ctx* ctx, ammsb_cols* cols, double* h_sums /* [4] or NULL */,
+                                 double* h_avg /* or NULL */);
 
 /* ---- work-group helpers the reference tests directly (wg-sum-test.cc,
  *      wg-normalize-test.cc): rows of `len` floats, one warp per row, reference

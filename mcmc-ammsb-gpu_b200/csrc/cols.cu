@@ -83,6 +83,7 @@ struct ammsb_cols {
   VmmAlloc local, remote[AMMSB_MAX_SHARDS];
   unsigned char* box[AMMSB_MAX_SHARDS] = {nullptr};
   uint32_t ws_ctas = 0;
+  uint32_t ppx_ctas = 0;  // grid of the last perplexity launch: its four sums sit behind that many CTA partials
   ColsRankView view(ulonglong2* pool) const {
     ColsRankView v;
     v.pi = d_pi; v.phi = d_phi; v.phi_vec = d_phi_vec; v.ppx = d_ppx;
@@ -2247,15 +2248,26 @@ extern "C" int ammsb_cols_perplexity(ammsb_ctx* c, ammsb_cols* const* ranks, uin
 #undef COLS_PPX_CASE
   AMMSB_REQUIRE(found, "unsupported (K, world) for the column layout");
   if (rc) return rc;
+  for (uint32_t i = 0; i < nv; ++i) ranks[i]->ppx_ctas = a.ctas_per_rank;
   if (!h_sums && !h_avg) return 0;
   for (uint32_t i = 0; i < nv; ++i) {
-    double sums[4];
-    rc = ammsb_d2h(c, sums, ranks[i]->d_ws_d + (size_t)a.ctas_per_rank * 4, sizeof sums);
+    rc = ammsb_cols_perplexity_result(c, ranks[i], h_sums ? h_sums + 4 * i : nullptr, h_avg ? h_avg + i : nullptr);
     if (rc) return rc;
-    if (h_sums) for (int q = 0; q < 4; ++q) h_sums[4 * i + q] = sums[q];
-    double avg = 0.0;  // perplexity.cc:264-273
-    if (sums[2] + sums[3] != 0) avg = (sums[0] + sums[1]) / (sums[2] + sums[3]);
-    if (h_avg) h_avg[i] = -avg;
   }
+  return 0;
+}
+
+// the four sums / the average of the last ammsb_cols_perplexity launch of this rank (waits for the
+// stream).  A caller that drives several devices from one thread launches every device's kernel
+// with NULL outputs first -- the kernels wait for each other -- and collects the results here.
+extern "C" int ammsb_cols_perplexity_result(ammsb_ctx* c, ammsb_cols* s, double* h_sums, double* h_avg) {
+  AMMSB_REQUIRE(s->ppx_ctas > 0, "no perplexity launch to read");
+  double sums[4];
+  const int rc = ammsb_d2h(c, sums, s->d_ws_d + (size_t)s->ppx_ctas * 4, sizeof sums);
+  if (rc) return rc;
+  if (h_sums) for (int q = 0; q < 4; ++q) h_sums[q] = sums[q];
+  double avg = 0.0;  // perplexity.cc:264-273
+  if (sums[2] + sums[3] != 0) avg = (sums[0] + sums[1]) / (sums[2] + sums[3]);
+  if (h_avg) *h_avg = -avg;
   return 0;
 }

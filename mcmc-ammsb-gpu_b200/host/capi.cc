@@ -8,6 +8,7 @@
 #include <sstream>
 
 #include "mcmc/learner.h"
+#include "mcmc/sharded_learner.h"
 #include "mcmc/serialize.h"
 #include "mcmc/std_order_set.h"
 #include <unordered_set>
@@ -397,6 +398,31 @@ void mcmc_init_theta_host(uint32_t K, float eta0, float eta1, float* theta_out) 
   std::vector<Float> host(2 * K);
   std::generate(host.begin(), host.end(), gamma);
   std::memcpy(theta_out, host.data(), 4 * host.size());
+}
+
+// ---- ShardedLearner (several GPUs of one box, column-sharded pi) ----
+void* mcmc_sharded_create(void* vc, const int* devices, int n) {
+  ShardedLearner* l = nullptr;
+  const int rc = Guard([&] { l = new ShardedLearner(*static_cast<Config*>(vc), std::vector<int>(devices, devices + n)); });
+  return rc ? nullptr : l;
+}
+void mcmc_sharded_destroy(void* v) { delete static_cast<ShardedLearner*>(v); }
+int mcmc_sharded_run(void* v, uint32_t iters) {
+  return Guard([&] { static_cast<ShardedLearner*>(v)->Run(iters); });
+}
+int mcmc_sharded_heldout_perplexity(void* v, float* out) {
+  return Guard([&] { *out = static_cast<ShardedLearner*>(v)->HeldoutPerplexity(); });
+}
+uint64_t mcmc_sharded_edges_processed(void* v) { return static_cast<ShardedLearner*>(v)->EdgesProcessed(); }
+// pi [N][K], phi [N]; theta / beta [world][2K]: every rank's copy (they must agree)
+int mcmc_sharded_read(void* v, float* pi, float* phi, float* beta, float* theta, uint64_t N, uint64_t K) {
+  return Guard([&] {
+    ShardedLearner* l = static_cast<ShardedLearner*>(v);
+    if (pi) l->ReadPi(0, N, pi);
+    if (phi) l->ReadPhi(0, N, phi);
+    for (uint32_t r = 0; r < l->World(); ++r)
+      if (beta || theta) l->ReadTheta(r, theta ? theta + 2 * K * r : nullptr, beta ? beta + 2 * K * r : nullptr);
+  });
 }
 
 // ---- Learner ----

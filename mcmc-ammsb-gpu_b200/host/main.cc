@@ -9,6 +9,7 @@
 #include <sstream>
 
 #include "mcmc/learner.h"
+#include "mcmc/sharded_learner.h"
 
 static sig_atomic_t signaled = 0;
 static void handler(int) { signaled = 1; }
@@ -36,7 +37,8 @@ int main(int argc, char** argv) {
                    "  -r heldout-ratio --alpha -a -b -c -e epsilon --eta0 --eta1 -k K -m mini_batch -n neighbors\n"
                    "  --ppx-wg --ppx-interval/-i --phi-wg --beta-wg --max-iters/-x --sample/-s STRATEGY\n"
                    "  --sampler-wg --phi-seed a,b --beta-seed a,b --neighbor-seed a,b --phi-mode MODE\n"
-                   "  --phi-disable-noise 0|1 --phi-strict 0|1 --device D\n";
+                   "  --phi-disable-noise 0|1 --phi-strict 0|1 --device D --device-sampler 0|1\n"
+                   "  --devices 0-7 | 0,1,2,3   (2, 4 or 8 GPUs of one box, pi column-sharded)\n";
       return 1;
     }
     auto s = kShort.find(a);
@@ -60,6 +62,8 @@ int main(int argc, char** argv) {
   uint32_t max_iters = 100;
   bool dumpDataset = false, loadDataset = false;
   int device = 0;
+  std::string devices;  // "--devices 0,1,2,3" or "0-7": the iteration over several GPUs (column-sharded pi)
+  Take(args, "--devices", &devices);
   Take(args, "--file", &filename);
   Take(args, "--heldout-ratio", &cfg.heldout_ratio);
   Take(args, "--alpha", &cfg.alpha);
@@ -128,6 +132,27 @@ int main(int argc, char** argv) {
             << ", heldout max fan out = " << cfg.heldoutGraph->MaxFanOut() << ")\n" << cfg;
   signal(SIGINT, handler);
   try {
+    if (!devices.empty()) {
+      std::vector<int> list;
+      const size_t dash = devices.find('-');
+      if (dash != std::string::npos) {
+        for (int d = std::stoi(devices.substr(0, dash)); d <= std::stoi(devices.substr(dash + 1)); ++d) list.push_back(d);
+      } else {
+        std::stringstream ss(devices);
+        for (std::string tok; std::getline(ss, tok, ',');) list.push_back(std::stoi(tok));
+      }
+      mcmc::ShardedLearner learner(cfg, list);
+      std::cerr << "Devices: " << list.size() << " ranks, pi column-sharded" << std::endl;
+      std::cerr << "ppx[0] = " << learner.HeldoutPerplexity() << std::endl;
+      for (uint64_t i = 0; i < max_iters && !signaled; i += cfg.ppx_interval) {
+        const uint64_t step = std::min<uint64_t>(max_iters - i, cfg.ppx_interval);
+        learner.Run(step, &signaled);
+        if (!signaled) std::cerr << "ppx[" << i + step << "] = " << learner.HeldoutPerplexity() << std::endl;
+      }
+      if (signaled) std::cerr << "FORCED TERMINATE" << std::endl;
+      learner.PrintStats();
+      return 0;
+    }
     mcmc::clcuda::Device dev(device);
     mcmc::clcuda::Context context(dev);
     mcmc::clcuda::Queue queue(context, dev);

@@ -186,6 +186,44 @@ class Config:
             self.h = None
 
 
+class ShardedLearner:
+    """mcmc::ShardedLearner: the iteration over several GPUs of one box (column-sharded pi); ranks that
+    share a device are computed by one launch, so devices=[0, 0] runs the two-rank protocol on one GPU"""
+
+    def __init__(self, cfg, devices):
+        self.cfg, self.world = cfg, len(devices)
+        lib().mcmc_sharded_create.restype = C.c_void_p
+        lib().mcmc_sharded_edges_processed.restype = C.c_uint64
+        d = (C.c_int * len(devices))(*devices)
+        h = lib().mcmc_sharded_create(cfg.h, d, len(devices))
+        if not h:
+            raise pyammsb.AmmsbError(lib().mcmc_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def run(self, iters):
+        _ck(lib().mcmc_sharded_run(self.h, iters))
+
+    def heldout_perplexity(self):
+        out = C.c_float(0)
+        _ck(lib().mcmc_sharded_heldout_perplexity(self.h, C.byref(out)))
+        return out.value
+
+    def edges_processed(self):
+        return int(lib().mcmc_sharded_edges_processed(self.h))
+
+    def read(self, N, K):
+        """pi [N, K], phi [N], beta [world, 2K], theta [world, 2K] (every rank's copy)"""
+        pi, phi = np.zeros((N, K), np.float32), np.zeros(N, np.float32)
+        beta, theta = np.zeros((self.world, 2 * K), np.float32), np.zeros((self.world, 2 * K), np.float32)
+        _ck(lib().mcmc_sharded_read(self.h, _p(pi), _p(phi), _p(beta), _p(theta), C.c_uint64(N), C.c_uint64(K)))
+        return pi, phi, beta, theta
+
+    def close(self):
+        if self.h is not None:
+            lib().mcmc_sharded_destroy(self.h)
+            self.h = None
+
+
 class Learner:
     def __init__(self, cfg, device=0):
         self.cfg = cfg

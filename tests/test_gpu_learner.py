@@ -295,3 +295,46 @@ def test_learner_device_sampler_is_the_host_strategy(ctx, strategy):
     for a, b in zip(st_h, st_d):
         assert np.array_equal(a, b)
     assert ppx_h == ppx_d and ne_h == ne_d
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_learner_matches_the_one_gpu_learner(ctx, world):
+    """mcmc::ShardedLearner (column-sharded pi, host/mcmc/sharded_learner.cc) with all ranks emulated
+    on one device -- the very kernels and mailbox protocol of a multi-GPU run -- against mcmc::Learner:
+    after one iteration pi is the one-GPU result bit for bit (update_phi / update_pi complete their
+    sums in the reference's tree order), theta / beta agree on every rank and with one GPU within the
+    fp32 association of the gradient sum; free-running, the perplexity stays within 1e-3"""
+    N, K, n = 2400, 128, 16
+    os.environ["AMMSB_PHI_NOSPLIT"] = "1"  # one association of the gradient sum on both sides
+    try:
+        cfg = make_cfg(N=N, E=30000, K=K, m=128, n=n, seed=8, strategy="Node")
+        one = pymcmc.Learner(cfg, 0)
+        cfg2 = make_cfg(N=N, E=30000, K=K, m=128, n=n, seed=8, strategy="Node")  # srand again: same sampler seeds
+        many = pymcmc.ShardedLearner(cfg2, [0] * world)
+        pi0, phi0, beta0, theta0 = one.read(N, K)
+        spi, sphi, sbeta, stheta = many.read(N, K)
+        assert np.array_equal(spi, pi0) and np.array_equal(sphi, phi0)
+        assert all(np.array_equal(stheta[r], theta0) and np.array_equal(sbeta[r], beta0) for r in range(world))
+        one.run(1)
+        many.run(1)
+        pi1, phi1, beta1, theta1 = one.read(N, K)
+        spi, sphi, sbeta, stheta = many.read(N, K)
+        assert (pi1 != pi0).any()
+        assert np.array_equal(spi, pi1), "column-sharded update_phi / update_pi differ from the one-GPU kernels"
+        assert np.array_equal(sphi, phi1)
+        for r in range(1, world):
+            assert np.array_equal(stheta[r], stheta[0]) and np.array_equal(sbeta[r], sbeta[0])
+        close_enough(stheta[0], theta1, "theta", frac=2e-2)
+        close_enough(sbeta[0], beta1, "beta", frac=2e-2)
+        one.run(40)
+        many.run(40)
+        assert many.edges_processed() == one.edges_processed()
+        got, want = many.heldout_perplexity(), one.heldout_perplexity()
+        print("world %d: perplexity after 41 iterations %.6f, one GPU %.6f" % (world, got, want))
+        assert abs(got - want) <= PPX_TOL * want
+        spi, sphi, sbeta, stheta = many.read(N, K)
+        for r in range(1, world):
+            assert np.array_equal(sbeta[r], sbeta[0])
+        one.close(); many.close(); cfg.close(); cfg2.close()
+    finally:
+        del os.environ["AMMSB_PHI_NOSPLIT"]
