@@ -133,11 +133,51 @@ ShardedLearner::ShardedLearner(const Config& cfg, const std::vector<int>& device
     AmmsbCheck(ammsb_cols_write_theta(c, theta.data(), beta.data()));
   }
   for (auto& g : groups_) AmmsbCheck(ammsb_ctx_sync(g->ctx));
+  for (int s = 0; s < 2; ++s) producers_[s] = std::thread(&ShardedLearner::Producer, this, s);
 }
 
 ShardedLearner::~ShardedLearner() {
-  if (next_.valid()) next_.wait();
+  {
+    std::unique_lock<std::mutex> lock(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  for (std::thread& t : producers_)
+    if (t.joinable()) t.join();
   for (auto& g : groups_) ammsb_ctx_sync(g->ctx);
+}
+
+void ShardedLearner::Producer(int stream) {
+  std::unique_lock<std::mutex> lock(mu_);
+  for (;;) {
+    cv_.wait(lock, [&] { return stop_ || (ready_[stream].size() < kAhead && !error_); });
+    if (stop_) return;
+    lock.unlock();
+    MiniBatch mb;
+    std::exception_ptr err;
+    try {
+      mb = Draw(stream);
+    } catch (...) {
+      err = std::current_exception();
+    }
+    lock.lock();
+    if (err) error_ = err; else ready_[stream].push_back(std::move(mb));
+    cv_.notify_all();
+  }
+}
+
+ShardedLearner::MiniBatch ShardedLearner::Next(int stream) {
+  std::unique_lock<std::mutex> lock(mu_);
+  cv_.wait(lock, [&] { return !ready_[stream].empty() || error_; });
+  if (ready_[stream].empty()) {
+    std::exception_ptr e = error_;
+    error_ = nullptr;
+    std::rethrow_exception(e);
+  }
+  MiniBatch mb = std::move(ready_[stream].front());
+  ready_[stream].pop_front();
+  cv_.notify_all();
+  return mb;
 }
 
 ShardedLearner::MiniBatch ShardedLearner::Draw(int stream) {
@@ -165,10 +205,8 @@ void ShardedLearner::Run(uint32_t max_iters, sig_atomic_t* signaled) {
   const auto t1 = high_resolution_clock::now();
   for (uint32_t i = 0; i < max_iters && (signaled == nullptr || !*signaled); ++i) {
     const auto ts = high_resolution_clock::now();
-    // mini-batch t comes from sampler stream `phase_`; t + 1 is drawn meanwhile (learner.cc:216-232)
-    MiniBatch mb = next_.valid() ? next_.get() : Draw(phase_);
-    const int next_stream = 1 - phase_;
-    next_ = std::async(std::launch::async, [this, next_stream] { return Draw(next_stream); });
+    // mini-batch t comes from sampler stream `phase_` (learner.cc:216-232)
+    MiniBatch mb = Next(phase_);
     samplingTime_ += duration_cast<nanoseconds>(high_resolution_clock::now() - ts).count();
     ++stepCount_;
     const int slot = stepCount_ & 1;

@@ -15,9 +15,12 @@
 #ifndef MCMC_B200_SHARDED_LEARNER_H_
 #define MCMC_B200_SHARDED_LEARNER_H_
 
+#include <condition_variable>
 #include <csignal>
-#include <future>
+#include <deque>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "mcmc/config.h"
@@ -52,8 +55,9 @@ class ShardedLearner {
   };
   struct Group;  // the ranks of one device
   MiniBatch Draw(int stream);
+  void Producer(int stream);
+  MiniBatch Next(int stream);
   void Upload(const MiniBatch& mb, int slot);
-  void SampleNeighbors(const MiniBatch& mb, int slot, int stream, uint32_t seq);
 
   const Config& cfg_;
   ammsb_params params_;
@@ -61,8 +65,16 @@ class ShardedLearner {
   std::vector<ammsb_cols*> ranks_;             // by rank
   std::vector<std::unique_ptr<Group>> groups_;  // by device
   Float (*sampler_)(const Config&, std::vector<Edge>*, unsigned int*);
+  // the two sampler streams (the reference's Samples: own seed each, learner.cc:216-232), each drawn
+  // by its own thread a few mini-batches ahead; a stream's mini-batches are drawn strictly in order
+  static const size_t kAhead = 3;
   unsigned int seeds_[2];
-  std::future<MiniBatch> next_;
+  std::thread producers_[2];
+  std::deque<MiniBatch> ready_[2];
+  std::mutex mu_;
+  std::condition_variable cv_;
+  bool stop_ = false;
+  std::exception_ptr error_;
   uint32_t stepCount_ = 0, ppxCalls_ = 0;
   int phase_ = 0;
   uint64_t edgesProcessed_ = 0;

@@ -22,3 +22,41 @@ def test_sharded_driver_matches_single_gpu(mode, coll):
                         os.path.join(ROOT, "tests", "run_dist_gpu.py"), mode, coll], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "dist gpu check ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cxx_sharded_learner_on_real_devices():
+    """mcmc::ShardedLearner with one rank per DEVICE (NVLink peer mailboxes inside one process)
+    against mcmc::Learner on device 0: pi bit for bit after an iteration, perplexity within 1e-3"""
+    import numpy as np
+    import pymcmc
+    from test_gpu_learner import make_cfg, PPX_TOL
+    n_dev = A.device_count()
+    if n_dev < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = 8 if n_dev >= 8 else (4 if n_dev >= 4 else 2)
+    N, K, n = 6000, 256, 16
+    os.environ["AMMSB_PHI_NOSPLIT"] = "1"
+    try:
+        cfg = make_cfg(N=N, E=60000, K=K, m=512, n=n, seed=8, strategy="Node")
+        one = pymcmc.Learner(cfg, 0)
+        cfg2 = make_cfg(N=N, E=60000, K=K, m=512, n=n, seed=8, strategy="Node")
+        try:
+            many = pymcmc.ShardedLearner(cfg2, list(range(world)))
+        except Exception as e:
+            print("ShardedLearner failed:", e)
+            raise
+        one.run(1)
+        many.run(1)
+        pi1 = one.read(N, K)[0]
+        spi, sphi, sbeta, stheta = many.read(N, K)
+        assert np.array_equal(spi, pi1)
+        one.run(60)
+        many.run(60)
+        for r in range(1, world):
+            assert np.array_equal(many.read(N, K)[2][r], many.read(N, K)[2][0])
+        got, want = many.heldout_perplexity(), one.heldout_perplexity()
+        assert abs(got - want) <= PPX_TOL * want
+        one.close(); many.close(); cfg.close(); cfg2.close()
+    finally:
+        del os.environ["AMMSB_PHI_NOSPLIT"]
