@@ -129,3 +129,37 @@ def test_world2_gloo_reductions_match_single_device(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def test_bench_layout_plan_is_a_function_of_the_arguments():
+    """bench.sharded_plan: column shards exactly when a GPU's piece of a row is at most 512 bytes
+    (the shape the column update_phi keeps 12+ slots per SM in flight at), else a copy per GPU while
+    it fits, else node partitions; both arms of the bench derive the same plan from the arguments"""
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    def plan(world, K, N, n=32, store="auto", E=10 ** 6):
+        args = types.SimpleNamespace(store=store, collectives="peer", graph="auto")
+        return bench.sharded_plan(args, dict(N=N, K=K, n=n, E=E), world)
+    assert plan(8, 1024, 317080)[0] == "columns"
+    assert plan(4, 1024, 317080)[0] == "replicated"
+    assert plan(2, 1024, 317080)[0] == "replicated"
+    assert plan(8, 512, 65608366, E=1806067135) == ("columns", "peer", "device")
+    assert plan(4, 512, 65608366)[0] == "columns"
+    assert plan(2, 512, 65608366)[0] == "partitioned"      # 134 GB of pi: no copy per GPU
+    assert plan(8, 1024, 317080, n=64)[0] == "replicated"  # the slot-at-a-time kernel stages one chunk of 32 neighbors
+    assert plan(8, 1024, 317080, store="partitioned")[0] == "partitioned"
+
+
+def test_host_order_csr_is_the_graph_adjacency():
+    """devgraph.host_order_csr: mcmc::Graph's neighbor lists (data.cc:12-25), in its order"""
+    sys.path.insert(0, os.path.join(ROOT, "mcmc-ammsb-gpu_b200"))
+    try:
+        import devgraph
+    except OSError:
+        pytest.skip("libammsb.so not built")
+    tr = np.array([(3 << 32) | 5, (1 << 32) | 3, (0 << 32) | 5, (3 << 32) | 4], dtype=np.uint64)
+    off, adj, deg = devgraph.host_order_csr(6, tr)
+    lists = [adj[int(off[u]):int(off[u + 1])].tolist() for u in range(6)]
+    assert lists == [[5], [3], [], [5, 1, 4], [3], [3, 0]]
+    assert deg.tolist() == [1, 1, 0, 3, 1, 2]
