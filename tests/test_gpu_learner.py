@@ -219,6 +219,29 @@ def test_cli_runs_on_a_snap_file(ctx, tmp_path):
     assert (r.stdout + r.stderr).count("ppx[") >= 3
 
 
+def test_cli_devices_and_device_sampler(ctx, tmp_path):
+    """ammsb-main --devices 0,0 (mcmc::ShardedLearner, two ranks on one GPU) and --device-sampler 1 print
+    the same kind of ppx[...] trace as the plain run; the device-sampler run prints the SAME trace
+    (its mini-batches are the host strategy's)"""
+    edges = make_edges(1500, 12000, 3)
+    f = tmp_path / "g.txt"
+    with open(f, "w") as out:
+        out.write("# a\n# b\n# c\n# d\n")
+        for e in edges:
+            out.write("%d\t%d\n" % (int(e) >> 32, int(e) & 0xffffffff))
+    exe = os.path.join(ROOT, "mcmc-ammsb-gpu_b200", "ammsb-main")
+    base = [exe, "-f", str(f), "-k", "128", "-m", "64", "-n", "16", "-x", "30", "-i", "10"]
+    traces = {}
+    for name, extra in (("plain", []), ("device-sampler", ["--device-sampler", "1"]), ("devices", ["--devices", "0,0"])):
+        r = subprocess.run(base + extra, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        traces[name] = [ln for ln in (r.stdout + r.stderr).splitlines() if ln.startswith("ppx[")]
+        assert len(traces[name]) >= 4, (name, r.stderr[-2000:])
+    assert traces["device-sampler"] == traces["plain"]
+    last = lambda t: float(t[-1].split("=")[1])
+    assert abs(last(traces["devices"]) - last(traces["plain"])) <= 1e-2 * last(traces["plain"])
+
+
 def test_training_perplexity_option(ctx, orc):
     """MCMC_CALC_TRAIN_PPX (learner.cc:47-75,204-212) as a run-time switch"""
     N, K, n = 900, 32, 8
