@@ -55,6 +55,23 @@ class StdOrderSet {
     std::fill(table_.begin(), table_.begin() + kMinTable, kEmptyKey);
   }
 
+  // Call right after Clear() when the number of keys to come is known (a non-link mini-batch: m
+  // edges; its endpoints: m + 1 vertices): the de-duplication table takes its final size at once
+  // instead of growing x4 from 64 entries with a refill of everything inserted so far each time
+  // (at m = 131072 that is 1.3 extra cache-missing inserts per key).  Order and results do not
+  // depend on the table size.
+  void Reserve(size_t n) {
+    unsigned log2 = kMinTableLog2;
+    while ((size_t(1) << log2) < 2 * (n + 1)) ++log2;
+    const size_t size = size_t(1) << log2;
+    if (size <= mask_ + 1) return;
+    if (table_.size() < size) table_.resize(size);
+    mask_ = size - 1;
+    shift_ = 64 - log2;
+    std::fill(table_.begin(), table_.begin() + size, kEmptyKey);
+    keys_.reserve(n);
+  }
+
   size_t size() const { return keys_.size(); }
 
   // true if k was not present
@@ -76,6 +93,11 @@ class StdOrderSet {
     keys_.push_back(k);
     return true;
   }
+
+  // Append a key the CALLER knows to be new (it de-duplicates by other means): the key joins the
+  // insert sequence without touching the table.  Not to be mixed with Insert() of keys that may
+  // repeat an appended one.
+  void AppendUnique(Key k) { keys_.push_back(k); }
 
   // From now on Insert(k) is refused (returns false) as if k were present, but k is not an
   // element: it is neither counted by size() nor emitted.  Lets a caller fold a small list of
