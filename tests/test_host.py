@@ -119,12 +119,14 @@ def test_flat_set_iterates_like_std_unordered_set(width):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("N,E,m", [(20000, 120000, 4096), (3000, 40000, 2500), (317080, 1049866, 16384)])
+@pytest.mark.parametrize("N,E,m", [(20000, 120000, 4096), (3000, 40000, 2500), (317080, 1049866, 16384),
+                                   (317080, 1049866, 131072)])
 def test_minibatch_strategies_match_reference_code_at_size(N, E, m):
     """the production strategies against the reference's own sample.cc / data.cc (compiled in place
     into oracle/_ref) at mini-batch sizes that go through every std::unordered_set growth step and,
     for the small dense graph, many refused and repeated candidates (the last shape is bench.py's:
-    com-DBLP-shaped, 16384 edges): edges and nodes in order, weight and rand_r stream position,
+    com-DBLP-shaped, 16384 edges, and the 8-GPU run's 131072 edges -- 41 % of all vertices picked):
+    edges and nodes in order, weight and rand_r stream position,
     8 mini-batches in a row per strategy"""
     if not RefSampler.available():
         pytest.skip("oracle/_ref not built (needs /root/reference); golden vectors still apply")
