@@ -34,7 +34,9 @@ def test_cxx_sharded_learner_on_real_devices():
     n_dev = A.device_count()
     if n_dev < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    world = 8 if n_dev >= 8 else (4 if n_dev >= 4 else 2)
+    world = int(os.environ.get("AMMSB_TEST_WORLD", "2"))  # 2 real devices is the measured configuration; 4 / 8 on request
+    if world > n_dev:
+        pytest.skip("needs %d GPUs" % world)
     N, K, n = 6000, 256, 16
     os.environ["AMMSB_PHI_NOSPLIT"] = "1"
     try:
