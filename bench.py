@@ -17,6 +17,14 @@ host sampling, H2D of edges/nodes and a D2H read of beta inside the timed region
 kernel text + host sampler compiled from /root/reference; falls back to the oracle port) on the
 box's host cores for the same metric on a bounded sample of the same workload.
 
+N > 1 (weak scaling, m edges per GPU): the pi layout is a function of the arguments
+(`sharded_plan`): column shards (csrc/cols.cu) when a GPU's piece of a row is at most 512 bytes
+(8 GPUs at K = 1024), else a copy per GPU while it fits, else node partitions; every run asserts one
+iteration bit-identical to one GPU (`parity_vs_n1`).  AMMSB_STAGE_EVENTS=1 adds per-stage CUDA-event
+times of the run itself (`stages_in_run_ms`), AMMSB_BENCH_VARIANTS="name:ENV=VAL,..;.." repeats the
+timed steps under other kernel switches in the same process, --e2e-device-sampler (N = 1) also times
+mcmc::Learner::Run with Config::device_sampler.
+
 Other shapes (development; the contract run uses the defaults): --shape com-LiveJournal |
 com-Friendster | com-Friendster-eighth ..., --K/--m/--n.  --graph device (default above 100 M
 edges) builds the synthetic graph, the cuckoo sets, the held-out pairs and the adjacency in HBM
