@@ -45,3 +45,26 @@ def test_wg_sum_tree_splits_into_rank_partials():
                 part[:h] = part[:h] + part[h:2 * h]
                 h //= 2
             assert part[0] == ref[0]
+
+
+def test_neighbor_sampler_divide_free_identities():
+    """the arithmetic ns_draw_slot (csrc/common.cuh) replaces generate_random_int's `%` with
+    (sample.cc:23-46): the 64-bit remainder by N as Lemire's multiply form with 128 fractional bits,
+    `x % capacity` as the 32-bit multiply form, and the probe sequence
+    (l1 + q (1 + 2 capacity)) % capacity as l1, l1 + 1, ... -- exact for every input"""
+    import random
+    rnd = random.Random(5)
+    M64, M128 = (1 << 64) - 1, (1 << 128) - 1
+    for N in (2, 3, 33, 317080, 3997962, 65608366, (1 << 32) - 5):
+        m = (M128 // N + 1) & M128  # ceil(2^128 / N), as NsGeom holds it (n_m_hi, n_m_lo)
+        for _ in range(2000):
+            a = rnd.getrandbits(64) if rnd.random() < 0.8 else rnd.choice([0, 1, N - 1, N, N + 1, M64])
+            low = (m * a) & M128                 # fractional part of a / N
+            assert (low * N) >> 128 == a % N
+    for cap in (16, 64, 66, 100, 128, 254):
+        cm = (M64 // cap + 1) & M64            # ceil(2^64 / capacity)
+        for _ in range(2000):
+            h = rnd.getrandbits(32)
+            assert (((cm * h) & M64) * cap) >> 64 == h % cap
+            l1, q = h % cap, rnd.randrange(cap)
+            assert (l1 + q * (1 + (cap << 1))) % cap == (l1 + q) % cap
